@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the anchor-grid hot path on the BASELINE.json headline config.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo (CUDA)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm
+
+Workload (one "step"): YOLOv4-608, 3 FPN scales x 3 anchors, 80 classes, batch 128
+per GPU of synthetic head outputs + labels:
+    fused CIoU loss forward+gradient (all scales, one launch)
+    -> decode at joint-confidence 0.5 -> per-class DIoU-NMS at 0.45.
+`value`  : images/s, inputs resident in HBM, timed with CUDA events (max over ranks).
+`e2e`    : same step through the reference-facing Python API with HOST buffers
+           (pinned H2D of labels + head outputs inside the timed region, D2H of the
+           loss scalars and the NMS survivors; the gradient stays on the device for
+           the backbone's backward pass, as in the reference's train step).
+`roofline`: the loss kernel (dominant) - algorithmic bytes / its CUDA-event time.
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's path
+           (torch-CPU fp32 loss fwd+bwd on all host threads; NumPy decode/NMS) on a
+           bounded sample of the same workload.  TensorFlow is not installable here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec YOLOv4-608 loss+grad+decode+NMS"
+UNIT = "images/s"
+CONFIG_NAME = "v4-608"
+CONF_THR, NMS_THR, NMS_MODE = 0.5, 0.45, 2
+ROW_CAPACITY_PER_IMG = 4096
+# my kernels per step: loss 1 | decode: count, 3 scan, emit | nms: classify, 3 scan,
+# scatter, small, big, 3 scan, emit
+LAUNCHES_PER_STEP = 1 + 5 + 12
+
+
+def loss_algorithmic_bytes(cfg, batch):
+    B, ch = cfg["bbox_num"], 5 + cfg["class_num"]
+    return sum(4 * batch * s * s * (2 * B * ch + ch) for s in cfg["grids"])
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    p = os.path.join(ROOT, "profiles", "loss_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: oracle port of the reference path
+# ---------------------------------------------------------------------------
+def cpu_step(cfg, y_trues, y_preds, n_threads):
+    """loss fwd+bwd (torch-CPU fp32, all threads) + decode + DIoU-NMS (NumPy) on the given images."""
+    import torch
+    from oracle import losses as ol
+    from oracle import tools as ot
+    B, C = cfg["bbox_num"], cfg["class_num"]
+    torch.set_num_threads(n_threads)
+    for si, S in enumerate(cfg["grids"]):
+        spec = ol.GridLossSpec(version=4, grid_shape=(S, S), bbox_num=B, class_num=C,
+                               anchors=cfg["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1])
+        ol.loss_and_grad(spec, y_trues[si], y_preds[si], dtype=torch.float32)
+    for i in range(y_preds[0].shape[0]):
+        rows = ot.decode(*[p[i] for p in y_preds], class_num=C, threshold=CONF_THR, version=4)
+        if len(rows):
+            ot.nms(rows, C, NMS_THR, NMS_MODE)
+
+
+def cpu_baseline(cfg, budget_s=12.0):
+    from tf2_yolo_b200 import synth
+    cores = os.cpu_count() or 1
+    small = synth.make_config(CONFIG_NAME, batch=4, seed=2, rank=999)
+    yt, yp = small["y_trues"], small["y_preds"]
+    cpu_step(small, [a[:1] for a in yt], [a[:1] for a in yp], cores)      # warm
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        cpu_step(small, yt, yp, cores)
+        n += 4
+        if time.perf_counter() - t0 > budget_s or n >= 64:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} images of the v4-608 workload in batches of 4 ({dt:.1f} s): oracle port of the "
+                      "reference path - loss fwd+bwd on torch-CPU fp32 (all threads), decode + DIoU-NMS in NumPy; "
+                      "TensorFlow not installable"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tf2_yolo_b200 import synth
+    cores = os.cpu_count() or 1
+    probe = synth.make_config(CONFIG_NAME, batch=1, seed=2, rank=998)
+    cpu_step(probe, probe["y_trues"], probe["y_preds"], cores)
+    t0 = time.perf_counter()
+    cpu_step(probe, probe["y_trues"], probe["y_preds"], cores)
+    t_img = max(time.perf_counter() - t0, 1e-3)
+    per_step = int(max(1, min(128, 150.0 / ((args.steps + args.warmup) * t_img))))
+    cfg = synth.make_config(CONFIG_NAME, batch=per_step, seed=2, rank=0)
+    for _ in range(args.warmup):
+        cpu_step(cfg, cfg["y_trues"], cfg["y_preds"], cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(cfg, cfg["y_trues"], cfg["y_preds"], cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = (f"{per_step} images/step of the v4-608 workload, oracle port of the reference path "
+              f"(torch-CPU fp32 loss fwd+bwd on {cores} threads; NumPy decode + DIoU-NMS); TensorFlow not installable")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "YOLOv4-608, 3 scales x 3 anchors, 80 classes: CIoU loss fwd+grad + decode(0.5) + "
+                               "DIoU-NMS(0.45); CPU arm processes a bounded sample per step",
+                   "images_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------
+# CUDA arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tf2_yolo_b200 import engine, synth
+    from tf2_yolo_b200.grid_loss import fused_losses
+    from tf2_yolo_b200.yolov4.losses import wrap_yolo_loss
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    batch = args.batch
+    cfg = synth.make_config(CONFIG_NAME, batch=batch, seed=2, rank=rank)
+    B, C = cfg["bbox_num"], cfg["class_num"]
+    fns = [wrap_yolo_loss((S, S), B, C, anchors=cfg["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1],
+                          wh_reg_weight=0.01, ignore_thresh=0.6)
+           for si, S in enumerate(cfg["grids"])]
+    global_batch = batch * world
+    host_t = [torch.from_numpy(a).pin_memory() for a in cfg["y_trues"]]
+    host_p = [torch.from_numpy(a).pin_memory() for a in cfg["y_preds"]]
+    dev_t = [a.to(dev) for a in host_t]
+    dev_p = [a.to(dev) for a in host_p]
+    dpreds = [torch.empty_like(a) for a in dev_p]
+    cap = ROW_CAPACITY_PER_IMG * batch
+    rows = torch.empty((cap, 7), dtype=torch.float64, device=dev)
+    loss_ev = []
+
+    def step(y_t, y_p, record=False):
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        loss, _, _ = fused_losses(fns, y_t, y_p, global_batch=global_batch, dpreds=dpreds)
+        if record:
+            e1.record()
+            loss_ev.append((e0, e1))
+        if world > 1:
+            dist.all_reduce(loss)             # the only collective: 3 scalars
+        _, offs = engine.decode_batch(y_p, C, CONF_THR, 4, rows=rows)
+        res = engine.nms_batch(rows, offs, C, NMS_THR, NMS_MODE)
+        return loss, offs, res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------
+    for _ in range(args.warmup):
+        out = step(dev_t, dev_p)
+    barrier()
+    total_rows = int(out[1][-1].item())
+    if total_rows > cap:
+        raise SystemExit(f"decode produced {total_rows} rows > capacity {cap}")
+    kept_rows = int(out[2]["out_offsets"][-1].item())
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(dev_t, dev_p, record=True)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    loss_ms = float(np.mean([a.elapsed_time(b) for a, b in loss_ev]))
+    clock_info = clocks.stop() if rank == 0 else None
+    loss_vals = out[0].cpu().numpy().tolist()
+
+    # ---- end to end through the host-buffer API -----------------------------------
+    h2d = sum(a.numel() * 4 for a in host_t + host_p)
+    stage_t = [torch.empty_like(a, device=dev) for a in host_t]
+    stage_p = [torch.empty_like(a, device=dev) for a in host_p]
+    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
+    offs_host = torch.empty(batch + 1, dtype=torch.int64).pin_memory()
+    rows_host = torch.empty((cap, 7), dtype=torch.float64).pin_memory()
+    d2h = [0]
+
+    def e2e_step():
+        for s, h in zip(stage_t + stage_p, host_t + host_p):
+            s.copy_(h, non_blocking=True)
+        loss, offs, res = step(stage_t, stage_p)
+        loss_host.copy_(loss, non_blocking=True)
+        offs_host.copy_(res["out_offsets"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the row count sizes the result read
+        n = int(offs_host[-1])
+        rows_host[:n].copy_(res["out_rows"][:n], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        d2h[0] = 12 + 8 * (batch + 1) + 56 * n
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
+
+    t = torch.tensor([ms, loss_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, loss_ms, e2e_ms = (float(x) for x in t.cpu())
+
+    if rank == 0:
+        algo = loss_algorithmic_bytes(cfg, batch)
+        peak, peak_src = peak_hbm()
+        achieved = algo / (loss_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": batch * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": f"YOLOv4-608 (BASELINE configs[2]): 3 scales (19/38/76) x 3 anchors, 80 classes, "
+                            f"batch {batch} per GPU; fused CIoU loss fwd+grad + decode(thr {CONF_THR}) + "
+                            f"per-class DIoU-NMS(thr {NMS_THR})",
+                "global_batch": batch * world, "per_gpu_batch": batch,
+                "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB read + {sum(d.numel() * 4 for d in dpreds) / 1e6:.0f} MB "
+                             "written per step vs 126 MB L2",
+                "decode_rows_per_image": total_rows / batch, "nms_kept_per_image": kept_rows / batch,
+                "loss_per_scale": loss_vals, "sharding": "batch split across ranks; all-reduce of 3 loss scalars",
+                "precision_note": "loss/decode fp32 (objectness, class, box terms of responsible boxes in fp64), "
+                                  "NMS fp64 bit-exact",
+            },
+            "clocks": clock_info,
+            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h[0], "ms_per_step": e2e_ms,
+                    "note": "pinned H2D of labels+heads, loss scalars + NMS survivors D2H; gradient stays on device"},
+            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "loss_fwd_bwd_kernel<4>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(),
+                         "algorithmic_bytes_per_launch": algo, "ms_per_launch": loss_ms, "peak_source": peak_src,
+                         "kernel_share_of_step": loss_ms / ms},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="images per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,209 @@
+/*
+ * yolo_b200.h -- C ABI of the B200-native tf2_YOLO anchor-grid engine.
+ *
+ * Every entry point replaces one Python function of samson6460/tf2_YOLO (cited
+ * per function as reference file:line).  Conventions, all entry points:
+ *   - every pointer is CALLER-OWNED DEVICE memory unless the name ends in _host;
+ *   - the library allocates nothing persistent and keeps no global mutable
+ *     state (re-entrant; safe from several host threads / streams);
+ *   - every launch is asynchronous on the given stream (a cudaStream_t);
+ *   - return 0 = OK, negative = invalid argument (YB_E_*), positive = the
+ *     cudaError_t of the failing runtime call.  yb_status_string() names both.
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef YOLO_B200_H_
+#define YOLO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
+
+#define YB_ABI_VERSION 1
+#define YB_MAX_BOXES 16  /* anchors per cell */
+#define YB_MAX_SCALES 4  /* FPN outputs per fused loss launch */
+#define YB_LOSS_TERMS 8  /* doubles per scale in terms_out */
+
+enum {
+    YB_OK = 0,
+    YB_E_NULL = -1,      /* required pointer is NULL */
+    YB_E_SHAPE = -2,     /* bad grid / box / class count */
+    YB_E_PARAM = -3,     /* bad enum / version / mode */
+    YB_E_WORKSPACE = -4, /* workspace too small or misaligned */
+    YB_E_ALIGN = -5,     /* tensor pointer not 4-byte (f32) / 8-byte (f64) aligned */
+    YB_E_CAPACITY = -6   /* output capacity too small (decode rows) */
+};
+
+int yb_abi_version(void);
+const char* yb_status_string(int status);
+
+/* ------------------------------------------------------------------------
+ * Grid losses: fused forward + gradient.
+ * Replaces the closures returned by wrap_yolo_loss:
+ *   v4  yolov4/losses/loss.py:64-169   (+ cal_iou/CIoU :10-61)
+ *   v3  yolov3/losses/loss.py:40-164   (+ cal_iou :9-37)
+ *   v2  yolov2/losses/loss.py:40-137
+ *   v1  yolov1_5/losses/loss.py:40-118 (different cell layout, IoU differentiated)
+ * The keyword arguments of wrap_yolo_loss become this POD struct.
+ * ---------------------------------------------------------------------- */
+typedef struct yb_loss_params {
+    int32_t version;                 /* 1 | 2 | 3 | 4 */
+    int32_t grid_h, grid_w;          /* grid_shape */
+    int32_t bbox_num, class_num;
+    int32_t has_anchors;             /* 0: anchors=None -> divisor 1 */
+    float anchors[2 * YB_MAX_BOXES]; /* (w,h) per box, image-normalised */
+    float binary_weight;
+    float loss_weight[4];            /* v4: box,conf,prob ; v1-v3: xy,wh,conf,prob */
+    float wh_reg_weight;             /* v4 kwarg; v2/v3 hard-code 0.01; v1 none (0) */
+    float ignore_thresh;
+    float truth_thresh;              /* v4 (>=1 disables) */
+    float label_smooth;              /* v4 */
+    float focal_gamma;               /* v4, v3 when use_focal */
+    int32_t use_focal;               /* v3: use_focal_loss */
+    int32_t use_scale;               /* v3: use_scale (v2: always 1) */
+    double inv_batch;                /* 1 / N of reduce_mean(axis=0); N = GLOBAL batch when sharded */
+} yb_loss_params;
+
+typedef struct yb_loss_scale {
+    const float* y_true; /* (n_cells, 5+C)            fp32 */
+    const float* y_pred; /* (n_cells, B*(5+C)) | v1 (n_cells, 5B+C) */
+    float* dpred;        /* like y_pred; NULL = forward only */
+    int64_t n_cells;     /* N_local * grid_h * grid_w */
+    yb_loss_params p;
+} yb_loss_scale;
+
+/* Workspace for a fused launch over n_scales scales. */
+size_t yb_loss_workspace_bytes(int n_scales);
+
+/* One launch over up to YB_MAX_SCALES scales (the three Keras outputs of one
+ * train step).  loss_out[s] = loss of scale s (fp32, what yolo_loss returns);
+ * terms_out (optional, may be NULL) = YB_LOSS_TERMS doubles per scale:
+ * [total, term0..term4, 0, 0] already divided by N (v4: box,conf,prob,reg;
+ * v2/v3: xy,wh,conf,prob,reg; v1: xy,wh,conf,prob). */
+int yb_loss_fwd_bwd(const yb_loss_scale* scales_host, int n_scales, float* loss_out,
+                    double* terms_out, void* workspace, size_t workspace_bytes,
+                    yb_stream_t stream);
+
+/* Single-scale conveniences, one per reference package. */
+int yb_loss_v1_fwd_bwd(const float* y_true, const float* y_pred, int64_t n_cells,
+                       float* loss_out, float* dpred, const yb_loss_params* p,
+                       void* workspace, size_t workspace_bytes, yb_stream_t stream);
+int yb_loss_v2_fwd_bwd(const float* y_true, const float* y_pred, int64_t n_cells,
+                       float* loss_out, float* dpred, const yb_loss_params* p,
+                       void* workspace, size_t workspace_bytes, yb_stream_t stream);
+int yb_loss_v3_fwd_bwd(const float* y_true, const float* y_pred, int64_t n_cells,
+                       float* loss_out, float* dpred, const yb_loss_params* p,
+                       void* workspace, size_t workspace_bytes, yb_stream_t stream);
+int yb_loss_v4_fwd_bwd(const float* y_true, const float* y_pred, int64_t n_cells,
+                       float* loss_out, float* dpred, const yb_loss_params* p,
+                       void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+/* Grid IoU (and CIoU) of the label box of a cell against its B predicted boxes:
+ * yolov4/losses/loss.py:10-61 (cal_iou); v1-v3 loss.py:9-37.  box_true is
+ * (n_cells, true_stride) with xywh at [0:4]; box_pred (n_cells, B, pred_stride).
+ * iou_out / ciou_out are (n_cells, B) fp32; ciou_out may be NULL. */
+int yb_grid_iou(const float* box_true, int true_stride, const float* box_pred,
+                int pred_stride, int64_t n_cells, int bbox_num, int grid_h, int grid_w,
+                float* iou_out, float* ciou_out, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Head decode: utils/tools.py:370-438 (decode), batched over images.
+ * Input: n_scales tensors (n_img, grid_h, grid_w, B*(5+C)) [v1: 5B+C], dtype
+ * f32 (model output) or f64 (labels).  Output rows [x,y,w,h,c,class,p] float64
+ * in the reference's order: image-major, then scale in argument order, then
+ * row-major (y, x, box, class).  row_offsets has n_img+1 entries (int64).
+ * If more than row_capacity rows pass the threshold, rows beyond the capacity
+ * are not written, *n_rows still holds the true total and the call reports it
+ * through row_offsets; the host mirror re-runs with a larger buffer.
+ * ---------------------------------------------------------------------- */
+typedef struct yb_decode_params {
+    int32_t version;   /* 1 | 2 | 3 | 4 */
+    int32_t class_num;
+    int32_t n_scales;
+    int32_t is_f64;    /* 0: float inputs, 1: double inputs */
+    int32_t grid_h[YB_MAX_SCALES], grid_w[YB_MAX_SCALES];
+    int32_t bbox_num[YB_MAX_SCALES];
+    double threshold;  /* compared in the input dtype, like numpy */
+} yb_decode_params;
+
+size_t yb_decode_workspace_bytes(const yb_decode_params* p, int64_t n_img);
+
+int yb_decode(const void* const* preds_host /* n_scales device pointers */,
+              int64_t n_img, const yb_decode_params* p, double* rows,
+              int64_t row_capacity, int64_t* row_offsets, void* workspace,
+              size_t workspace_bytes, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Per-class greedy NMS / DIoU-NMS: utils/tools.py:687-733 (nms) with the
+ * pairwise IoU of utils/tools.py:630-684 (cal_iou, mode 1 IoU / mode 2 DIoU),
+ * batched over images.  rows: (n_rows,7) float64 as produced by yb_decode;
+ * row_offsets: n_img+1 int64 (device).  keep[i] = 1 if row i survives.
+ * out_rows (optional) receives the survivors in the reference's output order
+ * (per image: class 0..C-1, original order inside a class), out_offsets
+ * (n_img+1 int64) their per-image extents, out_seg_offsets (optional,
+ * n_img*class_num+1 int64) their per-(image, class) extents.  n_rows is the
+ * capacity of rows/keep; the true count is read on the device from
+ * row_offsets[n_img], so a decode -> NMS chain needs no host round trip.
+ * Ties: suppression on IoU >= threshold; equal confidences are visited
+ * higher-original-index first.
+ * ---------------------------------------------------------------------- */
+size_t yb_nms_workspace_bytes(int64_t n_rows, int64_t n_img, int class_num);
+
+int yb_nms(const double* rows, const int64_t* row_offsets, int64_t n_rows, int64_t n_img,
+           int class_num, double nms_threshold, int iou_mode, uint8_t* keep,
+           double* out_rows, int64_t* out_offsets, int64_t* out_seg_offsets,
+           void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+/* Pairwise IoU / DIoU matrix, utils/tools.py:630-684 on (g,1,.) x (1,d,.):
+ * a: (na, stride_a) doubles, b: (nb, stride_b) doubles, out (na, nb). */
+int yb_pairwise_iou(const double* a, int64_t na, int stride_a, const double* b, int64_t nb,
+                    int stride_b, int iou_mode, double* out, yb_stream_t stream);
+
+/* Same arithmetic, element by element: a (n, stride_a), b (n, stride_b) -> out (n). */
+int yb_elementwise_iou(const double* a, int stride_a, const double* b, int stride_b, int64_t n,
+                       int iou_mode, double* out, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Anchor k-means, one Lloyd assignment pass: utils/kmeans.py:79-90 with the
+ * distances of :9-33 (iou_dist, area ratio) and :36-40 (euclidean).
+ * data (M,d) float64; centers (k,d) float64.  Outputs: assign[M] (first
+ * minimum, like np.argmin), sums (k,d), counts[k], all complete when the
+ * stream reaches the end of the call.  assign may be NULL.
+ * ---------------------------------------------------------------------- */
+enum { YB_DIST_IOU = 0, YB_DIST_EUCLID = 1 };
+
+size_t yb_kmeans_workspace_bytes(int64_t n_points, int k, int n_dim);
+
+int yb_kmeans_assign(const double* data, int64_t n_points, int n_dim, const double* centers,
+                     int k, int dist_kind, int32_t* assign, double* sums, int64_t* counts,
+                     void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+/* min / max over all elements of data (kmeans.py:68-69). out2 = {min,max}. */
+int yb_minmax_f64(const double* data, int64_t n, double* out2, void* workspace,
+                  size_t workspace_bytes, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * PR-curve / mAP matching: utils/measurement.py:252-292 (PRfunc) and :104-130
+ * (create_score_mat).  Per (image, class): every detection takes max/argmax
+ * IoU over the ground truths of that class.
+ * gt_rows / det_rows: (.,7) float64 rows in decode layout with int64 per-image
+ * offsets (the true row counts are read on the device from offsets[n_img];
+ * *_capacity only bound the launch).  Outputs per detection row: best_iou
+ * (float64; -1 when the image has no ground truth of that class), best_gt (int32
+ * index of the argmax among the image's ground truths OF THAT CLASS, first
+ * maximum; -1 if none).  gt_class_counts (n_img, class_num) int32 counts ground
+ * truths per image and class.
+ * ---------------------------------------------------------------------- */
+int yb_map_match(const double* gt_rows, const int64_t* gt_offsets, const double* det_rows,
+                 const int64_t* det_offsets, int64_t n_img, int class_num, int64_t gt_capacity,
+                 int64_t det_capacity, double* best_iou, int32_t* best_gt,
+                 int32_t* gt_class_counts, yb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO_B200_H_ */

@@ -1,0 +1,196 @@
+"""Execute the UNMODIFIED reference source (container only; test infrastructure).
+
+The reference (/root/reference) is pure Python on TensorFlow/NumPy.  Its NumPy
+half imports here once seven absent third-party imports are stubbed; its TF
+half (the four ``losses/loss.py`` files) uses 16 TensorFlow symbols, which a
+small shim maps onto torch so the files run verbatim with autograd providing
+dL/dy_pred.
+
+This module exists to (a) generate tests/golden/ and (b) cross-check the
+restatements in oracle/{losses,tools,kmeans,measurement}.py.  It cannot travel
+to the GPU box (no /root/reference there); everything that runs on the box
+uses the restatements plus the committed fixtures.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REFERENCE_ROOT = os.environ.get("YB_REFERENCE_ROOT", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "utils"))
+
+
+# --------------------------------------------------------------------------
+# TensorFlow -> torch shim with TF gradient tie rules
+# --------------------------------------------------------------------------
+class _TFMax(torch.autograd.Function):
+    """tf.maximum: on ties the whole gradient goes to the FIRST argument
+    (TF's MaximumGrad uses x >= y)."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x >= y)
+        return torch.maximum(x, y)
+
+    @staticmethod
+    def backward(ctx, g):
+        (m,) = ctx.saved_tensors
+        return g * m, g * (~m)
+
+
+class _TFMin(torch.autograd.Function):
+    """tf.minimum: MinimumGrad uses x <= y."""
+
+    @staticmethod
+    def forward(ctx, x, y):
+        ctx.save_for_backward(x <= y)
+        return torch.minimum(x, y)
+
+    @staticmethod
+    def backward(ctx, g):
+        (m,) = ctx.saved_tensors
+        return g * m, g * (~m)
+
+
+def _bcast2(fn):
+    def wrapped(x, y):
+        ref = x if torch.is_tensor(x) else y
+        x = torch.as_tensor(x, dtype=ref.dtype)
+        y = torch.as_tensor(y, dtype=ref.dtype)
+        xb, yb = torch.broadcast_tensors(x, y)
+        return fn(xb, yb)  # autograd handles un-broadcast of expanded views
+    return wrapped
+
+
+def make_tf_shim():
+    tf = types.ModuleType("tensorflow")
+    tf.reshape = lambda x, shape: torch.reshape(torch.as_tensor(x), tuple(int(s) for s in shape))
+    tf.maximum = _bcast2(_TFMax.apply)
+    tf.minimum = _bcast2(_TFMin.apply)
+    tf.pow = lambda x, p: torch.pow(x, p)
+    tf.atan = torch.atan
+    tf.square = lambda x: x * x
+    tf.sqrt = torch.sqrt
+    tf.argmax = lambda x, axis=-1: torch.argmax(x, dim=axis)
+    tf.one_hot = lambda i, depth, dtype=None: torch.nn.functional.one_hot(i, depth).to(dtype)
+    tf.cast = lambda x, dtype: x.to(dtype)
+    tf.expand_dims = lambda x, axis: torch.unsqueeze(x, axis)
+    tf.reduce_sum = lambda x, axis=None: x.sum() if axis is None else x.sum(dim=axis)
+    tf.reduce_mean = lambda x, axis=None: x.mean() if axis is None else x.mean(dim=axis)
+    tf.clip_by_value = lambda x, lo, hi: torch.clamp(x, lo, hi)
+    tf.math = types.SimpleNamespace(log=torch.log, abs=torch.abs)
+    return tf
+
+
+class _TorchNP:
+    """Stand-in for the module-global ``np`` of the loss files: ``np.array`` must
+    return something a grad-requiring torch tensor can be divided by."""
+
+    def __init__(self, dtype):
+        self._dtype = dtype
+
+    def array(self, x):
+        return torch.tensor(list(x), dtype=self._dtype)
+
+
+_STUBS = {
+    "matplotlib": {},
+    "matplotlib.pyplot": {},
+    "matplotlib.patches": {"Rectangle": object, "Circle": object, "BoxStyle": object},
+    "bs4": {"BeautifulSoup": object},
+    "imgaug": {},
+    "imgaug.augmentables": {},
+    "imgaug.augmentables.bbs": {"BoundingBox": object, "BoundingBoxesOnImage": object},
+    "tensorflow.keras": {},
+    "tensorflow.keras.utils": {"Sequence": object},
+    "cv2": {},
+}
+
+
+def _install_stubs():
+    for name, attrs in _STUBS.items():
+        if name in sys.modules:
+            continue
+        try:
+            if name.split(".")[0] in ("cv2",):
+                importlib.import_module(name)
+                continue
+        except Exception:
+            pass
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+    if "tensorflow" not in sys.modules:
+        sys.modules["tensorflow"] = make_tf_shim()
+    try:
+        import PIL  # noqa: F401
+    except Exception:
+        pil = types.ModuleType("PIL")
+        pil.Image = types.ModuleType("PIL.Image")
+        sys.modules["PIL"] = pil
+        sys.modules["PIL.Image"] = pil.Image
+
+
+_np_half = None
+
+
+def load_numpy_half():
+    """Return (tools, kmeans, measurement) modules of the reference, unmodified."""
+    global _np_half
+    if _np_half is None:
+        if not available():
+            raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+        _install_stubs()
+        mods = {}
+        pkg = types.ModuleType("yb_ref_utils")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "utils")]
+        sys.modules["yb_ref_utils"] = pkg
+        for name in ("tools", "kmeans", "measurement"):
+            spec = importlib.util.spec_from_file_location(
+                "yb_ref_utils." + name, os.path.join(REFERENCE_ROOT, "utils", name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules["yb_ref_utils." + name] = mod
+            spec.loader.exec_module(mod)
+            mods[name] = mod
+        _np_half = (mods["tools"], mods["kmeans"], mods["measurement"])
+    return _np_half
+
+
+def load_loss_module(version, dtype=torch.float64):
+    """Load yolov{1_5,2,3,4}/losses/loss.py verbatim over the TF shim."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    _install_stubs()
+    pkg = {1: "yolov1_5", 2: "yolov2", 3: "yolov3", 4: "yolov4"}[version]
+    path = os.path.join(REFERENCE_ROOT, pkg, "losses", "loss.py")
+    spec = importlib.util.spec_from_file_location(f"yb_ref_{pkg}_loss", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.tf = make_tf_shim()
+    mod.np = _TorchNP(dtype)
+    return mod
+
+
+def reference_loss(version, y_true, y_pred, dtype=torch.float64, **wrap_kwargs):
+    """loss, dL/dy_pred of the verbatim reference closure, on CPU."""
+    mod = load_loss_module(version, dtype)
+    kw = dict(wrap_kwargs)
+    if kw.get("anchors") is not None:
+        kw["anchors"] = torch.tensor(np.asarray(kw["anchors"], dtype=np.float64), dtype=dtype)
+    if isinstance(kw.get("binary_weight"), np.ndarray):
+        # TF multiplies ndarray * Tensor by converting the ndarray; torch needs help.
+        kw["binary_weight"] = torch.tensor(kw["binary_weight"], dtype=dtype)
+    fn = mod.wrap_yolo_loss(**kw)
+    yt = torch.as_tensor(np.asarray(y_true), dtype=dtype)
+    yp = torch.as_tensor(np.asarray(y_pred), dtype=dtype).clone().requires_grad_(True)
+    loss = fn(yt, yp)
+    loss = loss.reshape(()) if loss.numel() == 1 else loss
+    loss.backward()
+    return loss.detach().numpy().copy(), yp.grad.detach().numpy().copy()

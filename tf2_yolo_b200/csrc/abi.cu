@@ -1,0 +1,19 @@
+// ABI version + status strings.
+#include "common.cuh"
+
+extern "C" int yb_abi_version(void) { return YB_ABI_VERSION; }
+
+extern "C" const char* yb_status_string(int status) {
+    switch (status) {
+        case YB_OK: return "ok";
+        case YB_E_NULL: return "required pointer is NULL";
+        case YB_E_SHAPE: return "invalid shape (grid / boxes / classes / counts)";
+        case YB_E_PARAM: return "invalid parameter (version / mode / enum)";
+        case YB_E_WORKSPACE: return "workspace too small or not 256-byte aligned";
+        case YB_E_ALIGN: return "tensor pointer misaligned for its element type";
+        case YB_E_CAPACITY: return "output capacity too small";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+    return "unknown yolo_b200 status";
+}

@@ -1,0 +1,761 @@
+// Fused YOLO grid loss: forward + gradient in one pass over the head tensors.
+//
+// Replaces the TensorFlow op chains of
+//   yolov4/losses/loss.py:10-61,64-169   yolov3/losses/loss.py:9-37,40-164
+//   yolov2/losses/loss.py:9-37,40-137    yolov1_5/losses/loss.py:9-37,40-118
+// with one persistent, warp-specialised kernel per launch (all FPN scales):
+//
+//   producer warp : 1-D bulk-async (TMA) loads of a tile of cells (y_pred + y_true)
+//                   into a shared-memory ring, bulk-async store of the same
+//                   buffer -- by then overwritten in place with dL/dy_pred -- back
+//                   to HBM.
+//   consumer warps: A1 one thread per (cell, box): fp32 IoU against the label box
+//                   A2 argmax over the B boxes -> responsible / ignore masks,
+//                      box + objectness + wh terms and their 5 gradients (in place)
+//                   B  one warp per (cell, box) row: class cross-entropy and its
+//                      gradient for responsible boxes, zero-fill for all others
+//   reduction     : fp64 partial sums per thread -> warp -> CTA -> global partials,
+//                   last CTA sums them in a fixed order (deterministic) and emits
+//                   the fp32 loss of every scale.
+//
+// The loss is cell-local; the only coupling is the argmax over the boxes of one
+// cell and the final sum, so HBM traffic is exactly: read y_pred, read y_true,
+// write dpred, once each.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace yb {
+
+constexpr int kLossConsumerWarps = 4;
+constexpr int kLossConsumers = kLossConsumerWarps * 32;
+constexpr int kLossThreads = kLossConsumers + 32;
+constexpr int kMaxStages = 4;
+constexpr int kTerms = 5;
+constexpr float kEpsF = 1e-07f;
+constexpr double kEps = 1e-07;
+
+struct LossScaleDev {
+    const float* y_true;
+    const float* y_pred;
+    float* dpred;
+    long long n_cells;
+    int tile_cells;  // cells per tile (multiple of 4)
+    int n_tiles;
+    int tile_base;   // first tile id of this scale in the launch-wide tile list
+    int pcf, tcf;    // floats per cell in y_pred / y_true
+    int bulk_ok;     // all three base pointers 16-byte aligned
+    int B, C;
+    float gw, gh;
+    float anc[2 * YB_MAX_BOXES];
+    float bw;
+    float lw[4];
+    float whw;
+    float ignore_thr, truth_thr, label_smooth, gamma;
+    int use_focal, use_scale;
+    float inv_n;
+    double term_w[kTerms];  // weights combining the raw terms into the loss
+    double inv_n_d;
+};
+
+struct LossLaunch {
+    LossScaleDev sc[YB_MAX_SCALES];
+    int n_scales;
+    int total_tiles;
+    int stage_bytes;       // bytes of one ring stage
+    int max_rows;          // max over scales of tile_cells * B
+    int n_stages;
+    double* partials;      // [gridDim][n_scales][kTerms]
+    unsigned int* counter;
+    float* loss_out;       // [n_scales]
+    double* terms_out;     // [n_scales][YB_LOSS_TERMS] or null
+};
+
+// ---- box geometry ------------------------------------------------------------
+
+// fp32 IoU with one rounding per operation, in the reference's operation order
+// (loss.py:14-38) so that masks match a TensorFlow fp32 evaluation.
+__device__ __forceinline__ float grid_iou_f32(float px, float py, float pw, float ph, float tx,
+                                              float ty, float tw, float th, float gw, float gh) {
+    const float pcx = __fdiv_rn(px, gw), pcy = __fdiv_rn(py, gh);
+    const float tcx = __fdiv_rn(tx, gw), tcy = __fdiv_rn(ty, gh);
+    const float phw = __fmul_rn(pw, 0.5f), phh = __fmul_rn(ph, 0.5f);
+    const float thw = __fmul_rn(tw, 0.5f), thh = __fmul_rn(th, 0.5f);
+    const float ix0 = fmaxf(__fsub_rn(pcx, phw), __fsub_rn(tcx, thw));
+    const float iy0 = fmaxf(__fsub_rn(pcy, phh), __fsub_rn(tcy, thh));
+    const float ix1 = fminf(__fadd_rn(pcx, phw), __fadd_rn(tcx, thw));
+    const float iy1 = fminf(__fadd_rn(pcy, phh), __fadd_rn(tcy, thh));
+    const float iw = fmaxf(__fsub_rn(ix1, ix0), 0.f);
+    const float ih = fmaxf(__fsub_rn(iy1, iy0), 0.f);
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(pw, ph), __fmul_rn(tw, th)), inter);
+    return __fdiv_rn(inter, __fadd_rn(uni, kEpsF));
+}
+
+// IoU / CIoU and their derivatives w.r.t. the predicted (x, y, w, h), fp64.
+// Selection rules follow TensorFlow's Maximum/Minimum gradients (first operand
+// = the predicted box wins ties; max(.,0) passes the gradient at 0).
+struct BoxGrad {
+    double iou, ciou;
+    double diou[4], dciou[4];
+};
+
+template <bool kCiou>
+__device__ __forceinline__ void box_fwd_bwd(double x, double y, double w, double h, double X,
+                                            double Y, double W, double H, double gw, double gh,
+                                            BoxGrad& o) {
+    const double pcx = x / gw, pcy = y / gh, tcx = X / gw, tcy = Y / gh;
+    const double p0x = pcx - w / 2.0, p1x = pcx + w / 2.0, p0y = pcy - h / 2.0, p1y = pcy + h / 2.0;
+    const double t0x = tcx - W / 2.0, t1x = tcx + W / 2.0, t0y = tcy - H / 2.0, t1y = tcy + H / 2.0;
+    // intersection
+    const double a0x = (p0x >= t0x) ? 1.0 : 0.0, a1x = (p1x <= t1x) ? 1.0 : 0.0;
+    const double a0y = (p0y >= t0y) ? 1.0 : 0.0, a1y = (p1y <= t1y) ? 1.0 : 0.0;
+    const double rx = fmin(p1x, t1x) - fmax(p0x, t0x), ry = fmin(p1y, t1y) - fmax(p0y, t0y);
+    const double gx0 = (rx >= 0.0) ? 1.0 : 0.0, gy0 = (ry >= 0.0) ? 1.0 : 0.0;
+    const double iw = fmax(rx, 0.0), ih = fmax(ry, 0.0);
+    const double inter = iw * ih;
+    const double uni = w * h + W * H - inter;
+    const double den = uni + kEps;
+    const double iou = inter / den;
+    // d(iw)/dx, d(iw)/dw ; d(ih)/dy, d(ih)/dh
+    const double diw_dx = gx0 * (a1x - a0x) / gw, diw_dw = gx0 * (a1x + a0x) * 0.5;
+    const double dih_dy = gy0 * (a1y - a0y) / gh, dih_dh = gy0 * (a1y + a0y) * 0.5;
+    const double dI[4] = {ih * diw_dx, iw * dih_dy, ih * diw_dw, iw * dih_dh};
+    const double dU[4] = {-dI[0], -dI[1], h - dI[2], w - dI[3]};
+    const double inv_den2 = 1.0 / (den * den);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.diou[k] = (dI[k] * den - inter * dU[k]) * inv_den2;
+    o.iou = iou;
+    if (!kCiou) return;
+    // enclosing box diagonal
+    const double b0x = (p0x <= t0x) ? 1.0 : 0.0, b1x = (p1x >= t1x) ? 1.0 : 0.0;
+    const double b0y = (p0y <= t0y) ? 1.0 : 0.0, b1y = (p1y >= t1y) ? 1.0 : 0.0;
+    const double ew = fmax(p1x, t1x) - fmin(p0x, t0x), eh = fmax(p1y, t1y) - fmin(p0y, t0y);
+    const double c2 = ew * ew + eh * eh;
+    const double dc2[4] = {2.0 * ew * (b1x - b0x) / gw, 2.0 * eh * (b1y - b0y) / gh,
+                           2.0 * ew * (b1x + b0x) * 0.5, 2.0 * eh * (b1y + b0y) * 0.5};
+    const double ddx = tcx - pcx, ddy = tcy - pcy;
+    const double rho2 = ddx * ddx + ddy * ddy;
+    const double drho2[4] = {-2.0 * ddx / gw, -2.0 * ddy / gh, 0.0, 0.0};
+    // aspect-ratio term, alpha is differentiated (loss.py:51-57)
+    const double hh = h + kEps;
+    const double at = atan(W / (H + kEps)), ap = atan(w / hh);
+    const double kk = 4.0 / (3.14159265358979323846 * 3.14159265358979323846);
+    const double da = at - ap;
+    const double v = kk * da * da;
+    const double r2 = hh * hh + w * w;
+    const double dv[4] = {0.0, 0.0, -2.0 * kk * da * (hh / r2), 2.0 * kk * da * (w / r2)};
+    const double D = 1.0 - iou + v;
+    const double av = v * v / D;  // alpha * v
+    o.ciou = iou - rho2 / c2 - av;
+    const double inv_c4 = 1.0 / (c2 * c2), inv_D2 = 1.0 / (D * D);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double dR = (drho2[k] * c2 - rho2 * dc2[k]) * inv_c4;
+        const double dav = (2.0 * v * dv[k] * D - v * v * (dv[k] - o.diou[k])) * inv_D2;
+        o.dciou[k] = o.diou[k] - dR - dav;
+    }
+}
+
+// focal-style term f(e) = -e^g * log(1-e) and its derivative.
+__device__ __forceinline__ void focal_term(float e, float g, float& f, float& df) {
+    const float l = logf(1.f - e);
+    float eg, eg1;
+    if (g == 2.f) {
+        eg = e * e;
+        eg1 = e;
+    } else if (g == 1.f) {
+        eg = e;
+        eg1 = 1.f;
+    } else if (g == 0.f) {
+        eg = 1.f;
+        eg1 = 0.f;
+    } else {
+        eg1 = powf(e, g - 1.f);
+        eg = eg1 * e;
+    }
+    f = -eg * l;
+    df = -g * eg1 * l + eg / (1.f - e);
+}
+
+// ---- the kernel --------------------------------------------------------------
+
+template <int V>
+__global__ void __launch_bounds__(kLossThreads)
+loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int n_stages = L.n_stages;
+
+    unsigned char* ring = smem;
+    float* s_iou = reinterpret_cast<float*>(smem + (size_t)n_stages * L.stage_bytes);
+    float* s_pos = s_iou + L.max_rows;
+    double* s_acc = reinterpret_cast<double*>(
+        smem + align_up((size_t)n_stages * L.stage_bytes + 2 * sizeof(float) * L.max_rows, 16));
+    // s_acc: [kLossConsumerWarps][YB_MAX_SCALES][kTerms]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + kLossConsumerWarps * YB_MAX_SCALES * kTerms);
+    uint64_t* done = full + kMaxStages;
+    __shared__ int s_is_last;
+
+    if (tid == 0) {
+        for (int i = 0; i < kMaxStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&done[i], kLossConsumers);
+        }
+        mbar_fence_init();
+    }
+    for (int i = tid; i < kLossConsumerWarps * YB_MAX_SCALES * kTerms; i += kLossThreads) s_acc[i] = 0.0;
+    __syncthreads();
+
+    const int n_my = (L.total_tiles > (int)blockIdx.x)
+                         ? (L.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                         : 0;
+
+    if (warp == kLossConsumerWarps) {
+        // ===================== producer warp =====================
+        int s_ld = 0, s_st = 0;
+        for (int t = 0; t < n_my + n_stages - 1; ++t) {
+            if (t < n_my) {
+                const int tile = blockIdx.x + t * gridDim.x;
+                while (tile >= L.sc[s_ld].tile_base + L.sc[s_ld].n_tiles) ++s_ld;
+                const LossScaleDev& S = L.sc[s_ld];
+                const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
+                const int nc = (int)min((long long)S.tile_cells, S.n_cells - cell0);
+                const int stage = t % n_stages;
+                float* sp = reinterpret_cast<float*>(ring + (size_t)stage * L.stage_bytes);
+                float* st = sp + S.tile_cells * S.pcf;
+                const float* gp = S.y_pred + cell0 * S.pcf;
+                const float* gt = S.y_true + cell0 * S.tcf;
+                if (S.bulk_ok && (nc & 3) == 0) {
+                    if (lane == 0) {
+                        const uint32_t bp = (uint32_t)nc * S.pcf * 4u, bt = (uint32_t)nc * S.tcf * 4u;
+                        mbar_arrive_expect_tx(&full[stage], bp + bt);
+                        bulk_g2s(sp, gp, bp, &full[stage]);
+                        bulk_g2s(st, gt, bt, &full[stage]);
+                    }
+                } else {  // ragged tail / unaligned tensors: plain loads
+                    for (int i = lane; i < nc * S.pcf; i += 32) sp[i] = __ldg(gp + i);
+                    for (int i = lane; i < nc * S.tcf; i += 32) st[i] = __ldg(gt + i);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[stage]);
+                }
+            }
+            const int j = t - (n_stages - 1);
+            if (j >= 0) {
+                const int tile = blockIdx.x + j * gridDim.x;
+                while (tile >= L.sc[s_st].tile_base + L.sc[s_st].n_tiles) ++s_st;
+                const LossScaleDev& S = L.sc[s_st];
+                const int stage = j % n_stages;
+                mbar_wait(&done[stage], (j / n_stages) & 1);
+                if (S.dpred != nullptr) {
+                    const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
+                    const int nc = (int)min((long long)S.tile_cells, S.n_cells - cell0);
+                    float* sp = reinterpret_cast<float*>(ring + (size_t)stage * L.stage_bytes);
+                    float* gd = S.dpred + cell0 * S.pcf;
+                    if (S.bulk_ok && (nc & 3) == 0) {
+                        if (lane == 0) {
+                            bulk_s2g(gd, sp, (uint32_t)nc * S.pcf * 4u);
+                            bulk_commit();
+                            bulk_wait_read<0>();
+                        }
+                    } else {
+                        for (int i = lane; i < nc * S.pcf; i += 32) gd[i] = sp[i];
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all<0>();
+    } else {
+        // ===================== consumer warps =====================
+        double acc[kTerms];
+#pragma unroll
+        for (int k = 0; k < kTerms; ++k) acc[k] = 0.0;
+        int cur = 0;
+        auto flush = [&](int s) {
+#pragma unroll
+            for (int k = 0; k < kTerms; ++k) {
+                const double v = warp_sum(acc[k]);
+                if (lane == 0) s_acc[(warp * YB_MAX_SCALES + s) * kTerms + k] += v;
+                acc[k] = 0.0;
+            }
+        };
+
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            int s = cur;
+            while (tile >= L.sc[s].tile_base + L.sc[s].n_tiles) ++s;
+            if (s != cur) {
+                flush(cur);
+                cur = s;
+            }
+            const LossScaleDev& S = L.sc[s];
+            const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
+            const int nc = (int)min((long long)S.tile_cells, S.n_cells - cell0);
+            const int stage = it % n_stages;
+            float* sp = reinterpret_cast<float*>(ring + (size_t)stage * L.stage_bytes);
+            const float* st = sp + S.tile_cells * S.pcf;
+            const int B = S.B, C = S.C;
+            const int bstride = (V == 1) ? 5 : (5 + C);
+            const int nb = nc * B;
+            const bool write = S.dpred != nullptr;
+
+            mbar_wait(&full[stage], (it / n_stages) & 1);
+
+            // ---- A1: IoU of every predicted box with the label box of its cell
+            for (int j = tid; j < nb; j += kLossConsumers) {
+                const int cell = j / B, b = j - cell * B;
+                const float* pc = sp + cell * S.pcf + b * bstride;
+                const float* tc = st + cell * S.tcf;
+                s_iou[j] = grid_iou_f32(pc[0], pc[1], pc[2], pc[3], tc[0], tc[1], tc[2], tc[3], S.gw, S.gh);
+            }
+            bar_sync(1, kLossConsumers);
+
+            // ---- A2: masks, box / objectness / size terms, 5 gradients per box
+            for (int j = tid; j < nb; j += kLossConsumers) {
+                const int cell = j / B, b = j - cell * B;
+                float* pc = sp + cell * S.pcf + b * bstride;
+                const float* tc = st + cell * S.tcf;
+                const float* ci = s_iou + cell * B;
+                int amax = 0;
+                float best = ci[0];
+                for (int q = 1; q < B; ++q) {
+                    const float v = ci[q];
+                    if (v > best) {
+                        best = v;
+                        amax = q;
+                    }
+                }
+                const float iou = ci[b];
+                const float px = pc[0], py = pc[1], pw = pc[2], ph = pc[3], c = pc[4];
+                const float tx = tc[0], ty = tc[1], tw = tc[2], th = tc[3], obj = tc[4];
+                const float resp = (b == amax) ? 1.f : 0.f;
+                const float inv_n = S.inv_n;
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
+                float pos;
+
+                if (V == 1) {
+                    pos = obj * resp;
+                    const float neg = 1.f - pos;
+                    const float dx = tx - px, dy = ty - py;
+                    acc[0] += (double)(pos * (dx * dx + dy * dy));
+                    g0 = -2.f * S.lw[0] * pos * dx * inv_n;
+                    g1 = -2.f * S.lw[0] * pos * dy * inv_n;
+                    const float sw = sqrtf(fmaxf(pw, kEpsF)), sh = sqrtf(fmaxf(ph, kEpsF));
+                    const float dw = sqrtf(fmaxf(tw, kEpsF)) - sw, dh = sqrtf(fmaxf(th, kEpsF)) - sh;
+                    acc[1] += (double)(pos * (dw * dw + dh * dh));
+                    g2 = (pw >= kEpsF) ? -S.lw[1] * pos * dw / sw * inv_n : 0.f;
+                    g3 = (ph >= kEpsF) ? -S.lw[1] * pos * dh / sh * inv_n : 0.f;
+                    if (pos != 0.f) {
+                        BoxGrad bg;
+                        box_fwd_bwd<false>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
+                        const double d = bg.iou - (double)c;
+                        acc[2] += (double)pos * d * d + (double)(S.bw * neg * c * c);
+                        const double gi = 2.0 * S.lw[2] * pos * d * S.inv_n_d;
+                        g0 += (float)(gi * bg.diou[0]);
+                        g1 += (float)(gi * bg.diou[1]);
+                        g2 += (float)(gi * bg.diou[2]);
+                        g3 += (float)(gi * bg.diou[3]);
+                        g4 = (float)(-gi) + 2.f * S.lw[2] * S.bw * neg * c * inv_n;
+                    } else {
+                        acc[2] += (double)(S.bw * neg * c * c);
+                        g4 = 2.f * S.lw[2] * S.bw * neg * c * inv_n;
+                    }
+                } else {
+                    pos = obj * resp;
+                    if (V == 4 && S.truth_thr < 1.f)
+                        pos = pos + ((iou > S.truth_thr) ? 1.f : 0.f) * (1.f - pos);
+                    const float neg = (1.f - pos) * ((iou < S.ignore_thr) ? 1.f : 0.f);
+                    const float aw = S.anc[2 * b], ah = S.anc[2 * b + 1];
+                    const float lpw = logf(pw / aw), lph = logf(ph / ah);
+
+                    if (V == 4) {
+                        // wh regulariser, every box (loss.py:156-160)
+                        acc[3] += (double)(lpw * lpw + lph * lph);
+                        g2 = 2.f * S.whw * lpw / pw * inv_n;
+                        g3 = 2.f * S.whw * lph / ph * inv_n;
+                        // focal objectness with label smoothing (loss.py:119-143)
+                        const float cc = fminf(fmaxf(c, kEpsF), 1.f - kEpsF);
+                        const float band = (c >= kEpsF && c <= 1.f - kEpsF) ? 1.f : 0.f;
+                        float e_p, e_n, de_p, de_n;
+                        if (S.label_smooth > 0.f) {
+                            const float u = 1.f - S.label_smooth - cc, w2 = S.label_smooth - cc;
+                            e_p = fabsf(u);
+                            de_p = (u > 0.f) ? -1.f : ((u < 0.f) ? 1.f : 0.f);
+                            e_n = fabsf(w2);
+                            de_n = (w2 > 0.f) ? -1.f : ((w2 < 0.f) ? 1.f : 0.f);
+                        } else {
+                            e_p = 1.f - cc;
+                            de_p = -1.f;
+                            e_n = cc;
+                            de_n = 1.f;
+                        }
+                        float fn, dfn;
+                        focal_term(e_n, S.gamma, fn, dfn);
+                        float lc = S.bw * neg * fn;
+                        float gc = S.bw * neg * dfn * de_n;
+                        if (pos != 0.f) {
+                            float fp, dfp;
+                            focal_term(e_p, S.gamma, fp, dfp);
+                            lc += pos * fp;
+                            gc += pos * dfp * de_p;
+                            // CIoU box term (loss.py:113-117)
+                            BoxGrad bg;
+                            box_fwd_bwd<true>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
+                            acc[0] += (double)pos * (1.0 - bg.ciou);
+                            const double gb = -(double)S.lw[0] * pos * S.inv_n_d;
+                            g0 += (float)(gb * bg.dciou[0]);
+                            g1 += (float)(gb * bg.dciou[1]);
+                            g2 += (float)(gb * bg.dciou[2]);
+                            g3 += (float)(gb * bg.dciou[3]);
+                        }
+                        acc[1] += (double)lc;
+                        g4 = S.lw[1] * gc * band * inv_n;
+                    } else {  // V == 2 or 3
+                        acc[4] += (double)(lpw * lpw + lph * lph);
+                        g2 = 2.f * S.whw * lpw / pw * inv_n;
+                        g3 = 2.f * S.whw * lph / ph * inv_n;
+                        if (pos != 0.f) {
+                            const float sc = S.use_scale ? (2.f - tw * th) : 1.f;
+                            const float dx = tx - px, dy = ty - py;
+                            acc[0] += (double)(pos * sc * (dx * dx + dy * dy));
+                            g0 = -2.f * S.lw[0] * pos * sc * dx * inv_n;
+                            g1 = -2.f * S.lw[0] * pos * sc * dy * inv_n;
+                            const float dlw = logf(fmaxf(tw / aw, kEpsF)) - lpw;
+                            const float dlh = logf(fmaxf(th / ah, kEpsF)) - lph;
+                            acc[1] += (double)(pos * sc * (dlw * dlw + dlh * dlh));
+                            g2 += -2.f * S.lw[1] * pos * sc * dlw / pw * inv_n;
+                            g3 += -2.f * S.lw[1] * pos * sc * dlh / ph * inv_n;
+                        }
+                        if (V == 3 && S.use_focal) {
+                            const float cc = fminf(fmaxf(c, kEpsF), 1.f - kEpsF);
+                            const float band = (c >= kEpsF && c <= 1.f - kEpsF) ? 1.f : 0.f;
+                            float fn, dfn;
+                            focal_term(cc, S.gamma, fn, dfn);
+                            float lc = S.bw * neg * fn, gc = S.bw * neg * dfn;
+                            if (pos != 0.f) {
+                                float fp, dfp;
+                                focal_term(1.f - cc, S.gamma, fp, dfp);
+                                lc += pos * fp;
+                                gc -= pos * dfp;
+                            }
+                            acc[2] += (double)lc;
+                            g4 = S.lw[2] * gc * band * inv_n;
+                        } else {
+                            const float om = 1.f - c;
+                            acc[2] += (double)(pos * om * om + S.bw * neg * c * c);
+                            g4 = S.lw[2] * (-2.f * pos * om + 2.f * S.bw * neg * c) * inv_n;
+                        }
+                    }
+                }
+                s_pos[j] = pos;
+                if (write) {
+                    pc[0] = g0;
+                    pc[1] = g1;
+                    pc[2] = g2;
+                    pc[3] = g3;
+                    pc[4] = g4;
+                }
+            }
+            bar_sync(1, kLossConsumers);
+
+            // ---- B: class term.  v2-v4: one row per (cell, box); v1: one row per cell.
+            const int n_rows = (V == 1) ? nc : nb;
+            for (int r = warp; r < n_rows; r += kLossConsumerWarps) {
+                float* q;
+                const float* t;
+                float m;
+                if (V == 1) {
+                    q = sp + r * S.pcf + 5 * B;
+                    t = st + r * S.tcf + 5;
+                    m = st[r * S.tcf + 4];
+                } else {
+                    const int cell = r / B, b = r - cell * B;
+                    q = sp + cell * S.pcf + b * bstride + 5;
+                    t = st + cell * S.tcf + 5;
+                    m = s_pos[r];
+                }
+                if (m == 0.f) {
+                    if (write)
+                        for (int k = lane; k < C; k += 32) q[k] = 0.f;
+                } else {
+                    const double lwc = (double)S.lw[(V == 4) ? 2 : 3] * (double)m * S.inv_n_d;
+                    double part = 0.0;
+                    for (int k = lane; k < C; k += 32) {
+                        const double p = (double)q[k], tk = (double)t[k];
+                        const double pc = fmin(fmax(p, kEps), 1.0 - kEps);
+                        const double band = (p >= kEps && p <= 1.0 - kEps) ? 1.0 : 0.0;
+                        double l, g;
+                        if (V == 1 || V == 2) {
+                            l = tk * log(pc);
+                            g = -tk / pc;
+                        } else {
+                            l = tk * log(pc) + (1.0 - tk) * log(1.0 - pc);
+                            g = -(tk / pc - (1.0 - tk) / (1.0 - pc));
+                        }
+                        part -= (double)m * l;
+                        if (write) q[k] = (float)(lwc * g * band);
+                    }
+                    acc[3 - (V == 4)] += part;  // v4: term 2, others: term 3
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(&done[stage]);
+        }
+        flush(cur);
+    }
+
+    // ---- CTA partials -> global, last CTA reduces in a fixed order ------------
+    __syncthreads();
+    const int n_vals = L.n_scales * kTerms;
+    if (tid < n_vals) {
+        const int s = tid / kTerms, k = tid - s * kTerms;
+        double v = 0.0;
+        for (int w = 0; w < kLossConsumerWarps; ++w) v += s_acc[(w * YB_MAX_SCALES + s) * kTerms + k];
+        L.partials[(size_t)blockIdx.x * n_vals + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_is_last = (atomicAdd(L.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_is_last) return;
+    __threadfence();
+    double* s_fin = s_acc;  // reuse: [n_vals]
+    for (int i = warp; i < n_vals; i += kLossThreads / 32) {
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&L.partials[(size_t)b * n_vals + i]);
+        v = warp_sum(v);
+        if (lane == 0) s_fin[i] = v;
+    }
+    __syncthreads();
+    if (tid < L.n_scales) {
+        const LossScaleDev& S = L.sc[tid];
+        double total = 0.0;
+        for (int k = 0; k < kTerms; ++k) total += S.term_w[k] * s_fin[tid * kTerms + k];
+        total *= S.inv_n_d;
+        L.loss_out[tid] = (float)total;
+        if (L.terms_out != nullptr) {
+            double* o = L.terms_out + tid * YB_LOSS_TERMS;
+            o[0] = total;
+            for (int k = 0; k < kTerms; ++k) o[1 + k] = s_fin[tid * kTerms + k] * S.inv_n_d;
+            o[6] = 0.0;
+            o[7] = 0.0;
+        }
+    }
+    if (tid == 0) *L.counter = 0u;  // leave the workspace reusable
+}
+
+// ---- grid IoU (public cal_iou of the loss modules) ----------------------------
+__global__ void grid_iou_kernel(const float* __restrict__ bt, int ts, const float* __restrict__ bp,
+                                int ps, long long n_boxes, int B, float gw, float gh,
+                                float* __restrict__ iou_out, float* __restrict__ ciou_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_boxes) return;
+    const long long cell = i / B;
+    const float* t = bt + cell * ts;
+    const float* p = bp + i * ps;
+    const float iou = grid_iou_f32(p[0], p[1], p[2], p[3], t[0], t[1], t[2], t[3], gw, gh);
+    iou_out[i] = iou;
+    if (ciou_out != nullptr) {
+        BoxGrad bg;
+        box_fwd_bwd<true>(p[0], p[1], p[2], p[3], t[0], t[1], t[2], t[3], gw, gh, bg);
+        ciou_out[i] = (float)bg.ciou;
+    }
+}
+
+// ---- host side ----------------------------------------------------------------
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+static size_t loss_partials_bytes(int n_scales) {
+    return align_up((size_t)kNumSMs * 8 * n_scales * kTerms * sizeof(double), 256);
+}
+
+static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
+    const yb_loss_params& p = in.p;
+    if (in.y_true == nullptr || in.y_pred == nullptr) return YB_E_NULL;
+    if (p.version < 1 || p.version > 4) return YB_E_PARAM;
+    if (p.grid_h <= 0 || p.grid_w <= 0 || p.bbox_num <= 0 || p.bbox_num > YB_MAX_BOXES ||
+        p.class_num <= 0 || in.n_cells < 0)
+        return YB_E_SHAPE;
+    if (((uintptr_t)in.y_true | (uintptr_t)in.y_pred | (uintptr_t)in.dpred) & 3) return YB_E_ALIGN;
+    d.y_true = in.y_true;
+    d.y_pred = in.y_pred;
+    d.dpred = in.dpred;
+    d.n_cells = in.n_cells;
+    d.B = p.bbox_num;
+    d.C = p.class_num;
+    d.tcf = 5 + p.class_num;
+    d.pcf = (p.version == 1) ? 5 * p.bbox_num + p.class_num : p.bbox_num * (5 + p.class_num);
+    d.bulk_ok = ((((uintptr_t)in.y_true | (uintptr_t)in.y_pred | (uintptr_t)in.dpred) & 15) == 0) ? 1 : 0;
+    d.gw = (float)p.grid_w;
+    d.gh = (float)p.grid_h;
+    for (int i = 0; i < 2 * YB_MAX_BOXES; ++i)
+        d.anc[i] = (p.has_anchors && i < 2 * p.bbox_num) ? p.anchors[i] : 1.f;
+    d.bw = p.binary_weight;
+    for (int i = 0; i < 4; ++i) d.lw[i] = p.loss_weight[i];
+    d.ignore_thr = p.ignore_thresh;
+    d.truth_thr = p.truth_thresh;
+    d.label_smooth = p.label_smooth;
+    d.gamma = p.focal_gamma;
+    d.use_focal = p.use_focal;
+    d.use_scale = (p.version == 2) ? 1 : p.use_scale;
+    d.inv_n = (float)p.inv_batch;
+    d.inv_n_d = p.inv_batch;
+    for (int k = 0; k < kTerms; ++k) d.term_w[k] = 0.0;
+    if (p.version == 4) {
+        d.whw = p.wh_reg_weight;
+        d.term_w[0] = p.loss_weight[0];
+        d.term_w[1] = p.loss_weight[1];
+        d.term_w[2] = p.loss_weight[2];
+        d.term_w[3] = p.wh_reg_weight;
+    } else {
+        d.whw = (p.version == 1) ? 0.f : 0.01f;
+        for (int k = 0; k < 4; ++k) d.term_w[k] = p.loss_weight[k];
+        d.term_w[4] = (p.version == 1) ? 0.0 : 0.01;
+    }
+    return YB_OK;
+}
+
+template <int V>
+static int launch_loss(const LossLaunch& L, int grid, size_t smem, cudaStream_t stream) {
+    YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    loss_fwd_bwd_kernel<V><<<grid, kLossThreads, smem, stream>>>(L);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" size_t yb_loss_workspace_bytes(int n_scales) {
+    if (n_scales < 1) n_scales = 1;
+    if (n_scales > YB_MAX_SCALES) n_scales = YB_MAX_SCALES;
+    return loss_partials_bytes(n_scales) + 256;
+}
+
+extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                               double* terms_out, void* workspace, size_t workspace_bytes,
+                               yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (scales == nullptr || loss_out == nullptr || workspace == nullptr) return YB_E_NULL;
+    if (n_scales < 1 || n_scales > YB_MAX_SCALES) return YB_E_SHAPE;
+    if (workspace_bytes < yb_loss_workspace_bytes(n_scales) || ((uintptr_t)workspace & 255))
+        return YB_E_WORKSPACE;
+
+    LossLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.n_scales = n_scales;
+    const int version = scales[0].p.version;
+    int cell_bytes_max = 0;
+    for (int s = 0; s < n_scales; ++s) {
+        if (scales[s].p.version != version) return YB_E_PARAM;
+        int rc = fill_scale(scales[s], L.sc[s]);
+        if (rc != YB_OK) return rc;
+        cell_bytes_max = max(cell_bytes_max, (L.sc[s].pcf + L.sc[s].tcf) * 4);
+    }
+
+    // Ring geometry: prefer 3 stages of ~22 KB (3 CTAs/SM); shrink for fat cells.
+    int n_stages = env_int("YB_LOSS_STAGES", 3);
+    n_stages = max(2, min(kMaxStages, n_stages));
+    int ctas_per_sm = env_int("YB_LOSS_CTAS_PER_SM", 3);
+    const int tile_env = env_int("YB_LOSS_TILE_CELLS", 0);
+    const size_t smem_cap = 227 * 1024;
+    int stage_budget = 0;
+    for (;;) {
+        const size_t per_cta = smem_cap / ctas_per_sm - 2048;
+        stage_budget = (int)(per_cta / n_stages);
+        if (stage_budget >= 4 * cell_bytes_max + 64) break;
+        if (ctas_per_sm > 1) {
+            --ctas_per_sm;
+        } else if (n_stages > 2) {
+            --n_stages;
+        } else {
+            return YB_E_SHAPE;  // 4 cells do not fit a stage: B*(5+C) too large
+        }
+    }
+    int total_tiles = 0, stage_bytes = 0, max_rows = 0;
+    for (int s = 0; s < n_scales; ++s) {
+        LossScaleDev& d = L.sc[s];
+        const int cb = (d.pcf + d.tcf) * 4;
+        int t = (stage_budget - 64) / cb / 4 * 4;
+        if (tile_env > 0) t = min(t, max(4, tile_env / 4 * 4));
+        t = max(4, min(t, 64));
+        d.tile_cells = t;
+        d.n_tiles = (int)((d.n_cells + t - 1) / t);
+        d.tile_base = total_tiles;
+        total_tiles += d.n_tiles;
+        stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
+        max_rows = max(max_rows, t * d.B);
+    }
+    L.total_tiles = total_tiles;
+    L.stage_bytes = stage_bytes;
+    L.max_rows = max_rows;
+    L.n_stages = n_stages;
+    L.partials = reinterpret_cast<double*>(workspace);
+    L.counter = reinterpret_cast<unsigned int*>((char*)workspace + loss_partials_bytes(n_scales));
+    L.loss_out = loss_out;
+    L.terms_out = terms_out;
+
+    const size_t smem = align_up((size_t)n_stages * stage_bytes + 2 * sizeof(float) * max_rows, 16) +
+                        sizeof(double) * kLossConsumerWarps * YB_MAX_SCALES * kTerms +
+                        2 * kMaxStages * sizeof(uint64_t);
+    int grid = min(max(total_tiles, 1), kNumSMs * min(ctas_per_sm, 8));
+    YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
+    switch (version) {
+        case 1: return launch_loss<1>(L, grid, smem, stream);
+        case 2: return launch_loss<2>(L, grid, smem, stream);
+        case 3: return launch_loss<3>(L, grid, smem, stream);
+        default: return launch_loss<4>(L, grid, smem, stream);
+    }
+}
+
+static int loss_single(int version, const float* y_true, const float* y_pred, int64_t n_cells,
+                       float* loss_out, float* dpred, const yb_loss_params* p, void* workspace,
+                       size_t workspace_bytes, yb_stream_t stream) {
+    if (p == nullptr) return YB_E_NULL;
+    if (p->version != version) return YB_E_PARAM;
+    yb_loss_scale sc;
+    sc.y_true = y_true;
+    sc.y_pred = y_pred;
+    sc.dpred = dpred;
+    sc.n_cells = n_cells;
+    sc.p = *p;
+    return yb_loss_fwd_bwd(&sc, 1, loss_out, nullptr, workspace, workspace_bytes, stream);
+}
+
+#define YB_DEFINE_LOSS(V)                                                                          \
+    extern "C" int yb_loss_v##V##_fwd_bwd(const float* y_true, const float* y_pred, int64_t n_cells, \
+                                          float* loss_out, float* dpred, const yb_loss_params* p,   \
+                                          void* workspace, size_t workspace_bytes,                  \
+                                          yb_stream_t stream) {                                     \
+        return loss_single(V, y_true, y_pred, n_cells, loss_out, dpred, p, workspace,               \
+                           workspace_bytes, stream);                                                \
+    }
+YB_DEFINE_LOSS(1)
+YB_DEFINE_LOSS(2)
+YB_DEFINE_LOSS(3)
+YB_DEFINE_LOSS(4)
+
+extern "C" int yb_grid_iou(const float* box_true, int true_stride, const float* box_pred,
+                           int pred_stride, int64_t n_cells, int bbox_num, int grid_h, int grid_w,
+                           float* iou_out, float* ciou_out, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (box_true == nullptr || box_pred == nullptr || iou_out == nullptr) return YB_E_NULL;
+    if (n_cells < 0 || bbox_num <= 0 || grid_h <= 0 || grid_w <= 0 || true_stride < 4 || pred_stride < 4)
+        return YB_E_SHAPE;
+    const long long n = (long long)n_cells * bbox_num;
+    if (n == 0) return YB_OK;
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    grid_iou_kernel<<<(unsigned)blocks, threads, 0, stream>>>(box_true, true_stride, box_pred, pred_stride,
+                                                              n, bbox_num, (float)grid_w, (float)grid_h,
+                                                              iou_out, ciou_out);
+    return (int)cudaGetLastError();
+}

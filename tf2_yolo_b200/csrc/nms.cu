@@ -1,0 +1,522 @@
+// Per-class greedy NMS / DIoU-NMS, batched over images, bit-exact against the
+// reference's float64 arithmetic (utils/tools.py:630-684 cal_iou, :687-733 nms).
+// Compiled with -fmad=false: NumPy rounds every multiply/add/subtract separately.
+//
+// Pipeline (all on the caller's stream, no host round trip; the true row count is
+// read on the device from row_offsets[n_img]):
+//   classify  : row -> segment (image, class); per-segment counts (atomics)
+//   scan      : segment start offsets
+//   scatter   : row ids grouped by segment; segments binned into work lists
+//   small     : segments of <= 32 boxes, one WARP each: rank by confidence with
+//               shuffles, 32-bit suppression masks from warp-broadcast boxes,
+//               mask sweep in registers
+//   big       : larger segments, one CTA each: bitonic sorts (row id, confidence),
+//               boxes staged in shared memory in visit order, blocked greedy sweep
+//               (64x64 IoU bitmask per block, serial resolve of the block, kept
+//               boxes of the block suppress the rest of the segment in parallel)
+//   scan+emit : survivors written in the reference's order (class-major, original
+//               order inside a class)
+#include <climits>
+#include <cstring>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace yb {
+
+constexpr double kIouEps = 1e-07;  // utils/tools.py:26
+constexpr int kBigThreads = 256;
+constexpr int kBigCap = 2048;      // boxes per segment held in shared memory
+constexpr int kSweep = 64;         // sweep block (one 64-bit mask word per box)
+
+// IoU (MODE 1) or DIoU (MODE 2) of "true" box t against "pred" box p, the
+// reference's operation order (tools.py:649-682).
+template <int MODE>
+__device__ __forceinline__ double pair_iou(double tx, double ty, double tw, double th, double px,
+                                           double py, double pw, double ph) {
+    const double thw = tw / 2.0, thh = th / 2.0, phw = pw / 2.0, phh = ph / 2.0;
+    const double t0x = tx - thw, t0y = ty - thh, t1x = tx + thw, t1y = ty + thh;
+    const double p0x = px - phw, p0y = py - phh, p1x = px + phw, p1y = py + phh;
+    const double iw = fmax(fmin(p1x, t1x) - fmax(p0x, t0x), 0.0);
+    const double ih = fmax(fmin(p1y, t1y) - fmax(p0y, t0y), 0.0);
+    const double inter = iw * ih;
+    const double uni = pw * ph + tw * th - inter;
+    const double iou = inter / (uni + kIouEps);
+    if (MODE == 1) return iou;
+    const double ew = fmax(p1x, t1x) - fmin(p0x, t0x), eh = fmax(p1y, t1y) - fmin(p0y, t0y);
+    const double c2 = ew * ew + eh * eh;
+    const double dx = tx - px, dy = ty - py;
+    const double rho2 = dx * dx + dy * dy;
+    return iou - rho2 / c2;
+}
+
+struct NmsWs {
+    int* row_seg;            // [R]
+    unsigned int* seg_count; // [n_seg + 1]
+    unsigned int* seg_fill;  // [n_seg]
+    unsigned int* seg_kept;  // [n_seg + 1]
+    unsigned int* ctrl;      // [8]: small_n, big_n, small_cursor, big_cursor
+    long long* seg_start;    // [n_seg + 2]
+    long long* out_start;    // [n_seg + 2]
+    int* members;            // [R]
+    int* local_rank;         // [R]
+    int* small_list;         // [n_seg]
+    int* big_list;           // [n_seg]
+    double* gbox;            // [5][R]: x, y, w, h, conf  (segments > kBigCap)
+    int* gmem_pad;           // [2R] padded handle array
+    int* gord_pad;           // [2R]
+    unsigned char* gremoved; // [R]
+    void* scan_ws;
+};
+
+__device__ __forceinline__ long long device_row_count(const long long* row_offsets, long long n_img,
+                                                      long long cap) {
+    const long long n = row_offsets[n_img];
+    return n < cap ? n : cap;
+}
+
+__global__ void nms_classify_kernel(const double* __restrict__ rows, const long long* __restrict__ row_offsets,
+                                    long long n_img, long long cap, int C, NmsWs W,
+                                    unsigned char* __restrict__ keep) {
+    const long long n = device_row_count(row_offsets, n_img, cap);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        // image of row i: last img with row_offsets[img] <= i
+        long long lo = 0, hi = n_img;  // invariant: row_offsets[lo] <= i < row_offsets[hi]
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (row_offsets[mid] <= i) lo = mid; else hi = mid;
+        }
+        const double cf = rows[i * 7 + 5];
+        const long long cls = (long long)cf;  // astype("int"): truncation toward zero
+        int seg = -1;
+        if (cls >= 0 && cls < C && cf == cf) {
+            seg = (int)(lo * C + cls);
+            atomicAdd(&W.seg_count[seg], 1u);
+        }
+        W.row_seg[i] = seg;
+        keep[i] = 0;
+    }
+}
+
+__global__ void nms_scatter_kernel(const long long* __restrict__ row_offsets, long long n_img, long long cap,
+                                   long long n_seg, NmsWs W) {
+    const long long n = device_row_count(row_offsets, n_img, cap);
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n; i += nth) {
+        const int seg = W.row_seg[i];
+        if (seg >= 0) {
+            const long long pos = W.seg_start[seg] + atomicAdd(&W.seg_fill[seg], 1u);
+            W.members[pos] = (int)i;
+        }
+    }
+    for (long long s = tid; s < n_seg; s += nth) {
+        const unsigned c = W.seg_count[s];
+        if (c == 0u) {
+            W.seg_kept[s] = 0u;
+        } else if (c <= 32u) {
+            W.small_list[atomicAdd(&W.ctrl[0], 1u)] = (int)s;
+        } else {
+            W.big_list[atomicAdd(&W.ctrl[1], 1u)] = (int)s;
+        }
+    }
+}
+
+// ---- small segments: one warp each ---------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+nms_small_kernel(const double* __restrict__ rows, double thr, NmsWs W, unsigned char* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned w = 0;
+        if (lane == 0) w = atomicAdd(&W.ctrl[2], 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= W.ctrl[0]) break;
+        const int seg = W.small_list[w];
+        const int n = (int)W.seg_count[seg];
+        const long long start = W.seg_start[seg];
+        const unsigned valid = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
+
+        // restore original order: sort the (atomically scattered) row ids
+        int m = (lane < n) ? W.members[start + lane] : INT_MAX;
+        int rk = 0;
+        for (int j = 0; j < n; ++j) rk += (__shfl_sync(0xffffffffu, m, j) < m) ? 1 : 0;
+        __syncwarp();
+        if (lane < n) W.members[start + rk] = m;
+        __syncwarp();
+        m = (lane < n) ? W.members[start + lane] : INT_MAX;
+
+        double x = 0, y = 0, bw = 0, bh = 0, conf = 0;
+        if (lane < n) {
+            const double* r = rows + (long long)m * 7;
+            x = r[0]; y = r[1]; bw = r[2]; bh = r[3];
+            conf = __dmul_rn(r[4], r[6]);
+        }
+        // visit rank: descending confidence, ties -> higher original index first
+        int vis = 0;
+        unsigned sup = 0;
+        for (int j = 0; j < n; ++j) {
+            const double cj = __shfl_sync(0xffffffffu, conf, j);
+            vis += (cj > conf || (cj == conf && j > lane)) ? 1 : 0;
+            const double xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
+            const double wj = __shfl_sync(0xffffffffu, bw, j), hj = __shfl_sync(0xffffffffu, bh, j);
+            if (pair_iou<MODE>(x, y, bw, bh, xj, yj, wj, hj) >= thr) sup |= 1u << j;
+        }
+        // greedy sweep, state replicated in every lane
+        unsigned dead = 0, seen = 0;
+        for (int v = 0; v < n; ++v) {
+            const unsigned who = __ballot_sync(0xffffffffu, lane < n && vis == v);
+            if (who == 0u) continue;  // only with NaN confidences
+            const int src = __ffs(who) - 1;
+            const unsigned s = __shfl_sync(0xffffffffu, sup, src);
+            seen |= 1u << src;
+            if (!((dead >> src) & 1u)) dead |= s & ~seen & valid;
+        }
+        const unsigned alive = valid & ~dead;
+        if (lane < n) {
+            const bool k = (alive >> lane) & 1u;
+            keep[m] = k ? 1 : 0;
+            W.local_rank[start + lane] = k ? __popc(alive & ((1u << lane) - 1u)) : -1;
+        }
+        if (lane == 0) W.seg_kept[seg] = (unsigned)__popc(alive);
+    }
+}
+
+// ---- big segments: one CTA each ---------------------------------------------------
+template <typename Less>
+__device__ __forceinline__ void block_bitonic(int* h, int P, Less less) {
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < P; t += blockDim.x) {
+                const int u = t ^ j;
+                if (u > t) {
+                    const int a = h[t], b = h[u];
+                    const bool up = (t & k) == 0;
+                    if (up ? less(b, a) : less(a, b)) {
+                        h[t] = b;
+                        h[u] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBigThreads)
+nms_big_kernel(const double* __restrict__ rows, double thr, NmsWs W, long long R,
+               unsigned char* __restrict__ keep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* s_box = reinterpret_cast<double*>(smem_raw);                 // [5][kBigCap]
+    int* s_mem = reinterpret_cast<int*>(s_box + 5 * kBigCap);            // [kBigCap]
+    int* s_ord = s_mem + kBigCap;                                        // [kBigCap]
+    unsigned char* s_rem = reinterpret_cast<unsigned char*>(s_ord + kBigCap);  // [kBigCap]
+    __shared__ unsigned long long s_mask[kSweep];
+    __shared__ int s_kept[kSweep];
+    __shared__ int s_nkept;
+    __shared__ unsigned s_work;
+    __shared__ long long s_scan[32];
+    const int tid = threadIdx.x;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_work = atomicAdd(&W.ctrl[3], 1u);
+        __syncthreads();
+        const unsigned wi = s_work;
+        if (wi >= W.ctrl[1]) break;
+        const int seg = W.big_list[wi];
+        const int n = (int)W.seg_count[seg];
+        const long long start = W.seg_start[seg];
+        int P = 1;
+        while (P < n) P <<= 1;
+        const bool in_smem = n <= kBigCap;
+        int* mem = in_smem ? s_mem : W.gmem_pad + 2 * start;
+        int* ord = in_smem ? s_ord : W.gord_pad + 2 * start;
+        double* bx = in_smem ? s_box : W.gbox + start;
+        const long long bs = in_smem ? kBigCap : R;  // stride between the 5 planes
+        double* by = bx + bs; double* bwd = bx + 2 * bs; double* bht = bx + 3 * bs; double* cf = bx + 4 * bs;
+        unsigned char* rem = in_smem ? s_rem : W.gremoved + start;
+
+        // 1. original order: sort row ids ascending
+        for (int i = tid; i < P; i += kBigThreads) mem[i] = (i < n) ? W.members[start + i] : INT_MAX;
+        __syncthreads();
+        block_bitonic(mem, P, [](int a, int b) { return a < b; });
+        for (int i = tid; i < n; i += kBigThreads) {
+            const int m = mem[i];
+            W.members[start + i] = m;
+            const double* r = rows + (long long)m * 7;
+            cf[i] = __dmul_rn(r[4], r[6]);
+            ord[i] = i;
+        }
+        for (int i = n + tid; i < P; i += kBigThreads) ord[i] = INT_MAX;
+        __syncthreads();
+        // 2. visit order: confidence descending, ties -> higher original index first
+        block_bitonic(ord, P, [cf, n](int a, int b) {
+            if (a >= n || b >= n) return a < b;
+            const double ca = cf[a], cb = cf[b];
+            return ca > cb || (ca == cb && a > b);
+        });
+        // boxes in visit order (conf plane is dead from here on)
+        for (int v = tid; v < n; v += kBigThreads) {
+            const double* r = rows + (long long)mem[ord[v]] * 7;
+            bx[v] = r[0]; by[v] = r[1]; bwd[v] = r[2]; bht[v] = r[3];
+            rem[v] = 0;
+        }
+        __syncthreads();
+        // 3. blocked greedy sweep
+        for (int blk = 0; blk < n; blk += kSweep) {
+            const int m = min(kSweep, n - blk);
+            if (tid < kSweep) s_mask[tid] = 0ull;
+            __syncthreads();
+            {   // 64x64 upper-triangular mask, 4 threads per row (16 columns each)
+                const int i = tid >> 2, part = tid & 3;
+                if (i < m && !rem[blk + i]) {
+                    const double x = bx[blk + i], y = by[blk + i], w = bwd[blk + i], h = bht[blk + i];
+                    unsigned long long bits = 0ull;
+                    const int j0 = max(part * 16, i + 1), j1 = min(part * 16 + 16, m);
+                    for (int j = j0; j < j1; ++j)
+                        if (pair_iou<MODE>(x, y, w, h, bx[blk + j], by[blk + j], bwd[blk + j], bht[blk + j]) >= thr)
+                            bits |= 1ull << j;
+                    if (bits) atomicOr(&s_mask[i], bits);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long dead = 0ull;
+                for (int i = 0; i < m; ++i) if (rem[blk + i]) dead |= 1ull << i;
+                int nk = 0;
+                for (int i = 0; i < m; ++i) {
+                    if (!((dead >> i) & 1ull)) {
+                        dead |= s_mask[i];
+                        s_kept[nk++] = blk + i;
+                    }
+                }
+                for (int i = 0; i < m; ++i) rem[blk + i] = (unsigned char)((dead >> i) & 1ull);
+                s_nkept = nk;
+            }
+            __syncthreads();
+            const int nk = s_nkept;
+            for (int j = blk + m + tid; j < n; j += kBigThreads) {
+                if (rem[j]) continue;
+                const double x = bx[j], y = by[j], w = bwd[j], h = bht[j];
+                for (int q = 0; q < nk; ++q) {
+                    const int i = s_kept[q];
+                    if (pair_iou<MODE>(bx[i], by[i], bwd[i], bht[i], x, y, w, h) >= thr) {
+                        rem[j] = 1;
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // 4. survivors back in original order: keep flag per original position goes into
+        //    the (now dead) confidence plane, then a block scan gives each survivor its rank
+        for (int v = tid; v < n; v += kBigThreads) cf[ord[v]] = rem[v] ? 0.0 : 1.0;
+        __syncthreads();
+        long long carry = 0;
+        for (int base = 0; base < n; base += kBigThreads) {
+            const int i = base + tid;
+            const int kf = (i < n && cf[i] != 0.0) ? 1 : 0;
+            long long total;
+            const long long ex = block_exclusive_scan((long long)kf, s_scan, total);
+            if (i < n) {
+                W.local_rank[start + i] = kf ? (int)(carry + ex) : -1;
+                keep[mem[i]] = (unsigned char)kf;
+            }
+            carry += total;
+        }
+        if (tid == 0) W.seg_kept[seg] = (unsigned)carry;
+    }
+}
+
+__global__ void nms_emit_kernel(const double* __restrict__ rows, const long long* __restrict__ row_offsets,
+                                long long n_img, long long cap, int C, NmsWs W, double* __restrict__ out_rows,
+                                long long* __restrict__ out_offsets, long long* __restrict__ out_seg_offsets) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    const long long n_seg = n_img * C;
+    if (out_offsets != nullptr)
+        for (long long i = tid; i <= n_img; i += nth) out_offsets[i] = W.out_start[i * C];
+    if (out_seg_offsets != nullptr)
+        for (long long i = tid; i <= n_seg; i += nth) out_seg_offsets[i] = W.out_start[i];
+    if (out_rows == nullptr) return;
+    const long long n_grouped = W.seg_start[n_seg];
+    for (long long pos = tid; pos < n_grouped; pos += nth) {
+        const int r = W.local_rank[pos];
+        if (r < 0) continue;
+        const int m = W.members[pos];
+        const int seg = W.row_seg[m];
+        const double* src = rows + (long long)m * 7;
+        double* dst = out_rows + (W.out_start[seg] + r) * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) dst[k] = src[k];
+    }
+}
+
+template <int MODE>
+__global__ void pairwise_iou_kernel(const double* __restrict__ a, long long na, int sa,
+                                    const double* __restrict__ b, long long nb, int sb,
+                                    double* __restrict__ out) {
+    const long long total = na * nb;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long ia = i / nb, ib = i - ia * nb;
+        const double* t = a + ia * sa;
+        const double* p = b + ib * sb;
+        out[i] = pair_iou<MODE>(t[0], t[1], t[2], t[3], p[0], p[1], p[2], p[3]);
+    }
+}
+
+template <int MODE>
+__global__ void elementwise_iou_kernel(const double* __restrict__ a, int sa, const double* __restrict__ b,
+                                       int sb, long long n, double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double* t = a + i * sa;
+        const double* p = b + i * sb;
+        out[i] = pair_iou<MODE>(t[0], t[1], t[2], t[3], p[0], p[1], p[2], p[3]);
+    }
+}
+
+static size_t carve(size_t& off, size_t bytes) {
+    const size_t at = off;
+    off += align_up(bytes, 256);
+    return at;
+}
+
+static size_t nms_layout(long long R, long long n_seg, NmsWs* W, char* base) {
+    size_t off = 0;
+    if (R < 1) R = 1;
+    if (n_seg < 1) n_seg = 1;
+#define YB_CARVE(field, type, count)                                   \
+    {                                                                  \
+        const size_t at = carve(off, sizeof(type) * (size_t)(count));  \
+        if (W) W->field = reinterpret_cast<type*>(base + at);          \
+    }
+    // zero-initialised block first: seg_count, seg_fill, ctrl
+    YB_CARVE(seg_count, unsigned int, n_seg + 1)
+    YB_CARVE(seg_fill, unsigned int, n_seg)
+    YB_CARVE(ctrl, unsigned int, 8)
+    const size_t zero_bytes = off;
+    YB_CARVE(seg_kept, unsigned int, n_seg + 1)
+    YB_CARVE(row_seg, int, R)
+    YB_CARVE(seg_start, long long, n_seg + 2)
+    YB_CARVE(out_start, long long, n_seg + 2)
+    YB_CARVE(members, int, R)
+    YB_CARVE(local_rank, int, R)
+    YB_CARVE(small_list, int, n_seg)
+    YB_CARVE(big_list, int, n_seg)
+    YB_CARVE(gbox, double, 5 * R)
+    YB_CARVE(gmem_pad, int, 2 * R)
+    YB_CARVE(gord_pad, int, 2 * R)
+    YB_CARVE(gremoved, unsigned char, R)
+#undef YB_CARVE
+    const size_t at = carve(off, scan_workspace_bytes(n_seg + 1));
+    if (W) W->scan_ws = base + at;
+    (void)zero_bytes;
+    return off;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" size_t yb_nms_workspace_bytes(int64_t n_rows, int64_t n_img, int class_num) {
+    if (n_rows < 0 || n_img < 0 || class_num <= 0) return 0;
+    return nms_layout(n_rows, n_img * class_num, nullptr, nullptr);
+}
+
+extern "C" int yb_nms(const double* rows, const int64_t* row_offsets_, int64_t n_rows, int64_t n_img,
+                      int class_num, double nms_threshold, int iou_mode, uint8_t* keep, double* out_rows,
+                      int64_t* out_offsets_, int64_t* out_seg_offsets_, void* workspace,
+                      size_t workspace_bytes, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    const long long* row_offsets = reinterpret_cast<const long long*>(row_offsets_);
+    long long* out_offsets = reinterpret_cast<long long*>(out_offsets_);
+    long long* out_seg_offsets = reinterpret_cast<long long*>(out_seg_offsets_);
+    if (row_offsets == nullptr || workspace == nullptr) return YB_E_NULL;
+    if (n_rows < 0 || n_img < 0 || class_num <= 0) return YB_E_SHAPE;
+    if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
+    if (n_rows > 0 && (rows == nullptr || keep == nullptr)) return YB_E_NULL;
+    if (n_rows > (int64_t)INT_MAX / 2) return YB_E_SHAPE;
+    if (workspace_bytes < yb_nms_workspace_bytes(n_rows, n_img, class_num) || ((uintptr_t)workspace & 255))
+        return YB_E_WORKSPACE;
+    const long long n_seg = n_img * class_num;
+    if (n_img == 0 || n_rows == 0) {
+        if (out_offsets != nullptr)
+            YB_CUDA_TRY(cudaMemsetAsync(out_offsets, 0, sizeof(long long) * (n_img + 1), stream));
+        if (out_seg_offsets != nullptr)
+            YB_CUDA_TRY(cudaMemsetAsync(out_seg_offsets, 0, sizeof(long long) * (n_seg + 1), stream));
+        return YB_OK;
+    }
+    NmsWs W;
+    nms_layout(n_rows, n_seg, &W, reinterpret_cast<char*>(workspace));
+    const size_t zero_bytes = (char*)W.seg_kept - (char*)workspace;
+    YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, zero_bytes, stream));
+
+    const int threads = 256;
+    const int row_blocks = (int)min((long long)kNumSMs * 8, ((long long)n_rows + threads - 1) / threads);
+    nms_classify_kernel<<<row_blocks, threads, 0, stream>>>(rows, row_offsets, n_img, n_rows, class_num, W, keep);
+    YB_CUDA_TRY(cudaGetLastError());
+    int rc = exclusive_scan_u32(W.seg_count, n_seg, W.seg_start, W.scan_ws, stream);
+    if (rc != 0) return rc;
+    const int sc_blocks = (int)min((long long)kNumSMs * 8, (max((long long)n_rows, (long long)n_seg) + threads - 1) / threads);
+    nms_scatter_kernel<<<sc_blocks, threads, 0, stream>>>(row_offsets, n_img, n_rows, n_seg, W);
+    YB_CUDA_TRY(cudaGetLastError());
+
+    const int small_blocks = (int)min((long long)kNumSMs * 4, (n_seg * 32 + threads - 1) / threads);
+    const size_t big_smem = sizeof(double) * 5 * kBigCap + sizeof(int) * 2 * kBigCap + kBigCap;
+    const int big_blocks = (int)min((long long)kNumSMs * 2, n_seg);
+    if (iou_mode == 1) {
+        nms_small_kernel<1><<<small_blocks, threads, 0, stream>>>(rows, nms_threshold, W, keep);
+        YB_CUDA_TRY(cudaFuncSetAttribute(nms_big_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
+        nms_big_kernel<1><<<big_blocks, kBigThreads, big_smem, stream>>>(rows, nms_threshold, W, n_rows, keep);
+    } else {
+        nms_small_kernel<2><<<small_blocks, threads, 0, stream>>>(rows, nms_threshold, W, keep);
+        YB_CUDA_TRY(cudaFuncSetAttribute(nms_big_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
+        nms_big_kernel<2><<<big_blocks, kBigThreads, big_smem, stream>>>(rows, nms_threshold, W, n_rows, keep);
+    }
+    YB_CUDA_TRY(cudaGetLastError());
+    rc = exclusive_scan_u32(W.seg_kept, n_seg, W.out_start, W.scan_ws, stream);
+    if (rc != 0) return rc;
+    if (out_rows != nullptr || out_offsets != nullptr || out_seg_offsets != nullptr) {
+        nms_emit_kernel<<<row_blocks, threads, 0, stream>>>(rows, row_offsets, n_img, n_rows, class_num, W,
+                                                            out_rows, out_offsets, out_seg_offsets);
+        YB_CUDA_TRY(cudaGetLastError());
+    }
+    return YB_OK;
+}
+
+extern "C" int yb_pairwise_iou(const double* a, int64_t na, int stride_a, const double* b, int64_t nb,
+                               int stride_b, int iou_mode, double* out, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (na < 0 || nb < 0 || stride_a < 4 || stride_b < 4) return YB_E_SHAPE;
+    if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
+    if (na == 0 || nb == 0) return YB_OK;
+    if (a == nullptr || b == nullptr || out == nullptr) return YB_E_NULL;
+    const int threads = 256;
+    const int blocks = (int)min((long long)kNumSMs * 8, ((long long)na * nb + threads - 1) / threads);
+    if (iou_mode == 1)
+        pairwise_iou_kernel<1><<<blocks, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
+    else
+        pairwise_iou_kernel<2><<<blocks, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int yb_elementwise_iou(const double* a, int stride_a, const double* b, int stride_b, int64_t n,
+                                  int iou_mode, double* out, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n < 0 || stride_a < 4 || stride_b < 4) return YB_E_SHAPE;
+    if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
+    if (n == 0) return YB_OK;
+    if (a == nullptr || b == nullptr || out == nullptr) return YB_E_NULL;
+    const int threads = 256;
+    const int blocks = (int)min((long long)kNumSMs * 8, ((long long)n + threads - 1) / threads);
+    if (iou_mode == 1)
+        elementwise_iou_kernel<1><<<blocks, threads, 0, stream>>>(a, stride_a, b, stride_b, n, out);
+    else
+        elementwise_iou_kernel<2><<<blocks, threads, 0, stream>>>(a, stride_a, b, stride_b, n, out);
+    return (int)cudaGetLastError();
+}

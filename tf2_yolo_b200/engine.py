@@ -1,0 +1,324 @@
+"""Device-side entry points: thin wrappers that hand torch CUDA tensors' device
+pointers (torch is only the tensor carrier / allocator here) and the current
+CUDA stream to the C ABI in libyolo_b200.so.  Everything is asynchronous on the
+current stream; nothing here computes on the host and nothing falls back to
+PyTorch ops.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+_I64 = torch.int64
+_F64 = torch.float64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not torch.is_tensor(t) or not t.is_cuda:
+            raise N.YoloB200Error("tf2_yolo_b200 ops need CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise N.YoloB200Error("tf2_yolo_b200 ops need contiguous tensors")
+
+
+class _WorkspacePool:
+    """Grow-only scratch buffers, one per (device, stream, tag).  Host-side
+    convenience only: the C library itself owns no memory."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, tag, nbytes, device):
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            nbytes = int(max(nbytes, 4096))
+            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        off = (-buf.data_ptr()) % 256
+        return buf[off:off + nbytes]
+
+    def clear(self):
+        self._bufs.clear()
+
+
+workspaces = _WorkspacePool()
+
+
+# --------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------
+def make_loss_params(version, grid_shape, bbox_num, class_num, anchors=None, binary_weight=1.0,
+                     loss_weight=(1, 1, 1, 1), wh_reg_weight=0.01, ignore_thresh=0.6,
+                     truth_thresh=1.0, label_smooth=0.0, focal_loss_gamma=2.0,
+                     use_focal_loss=False, use_scale=True):
+    if version not in (1, 2, 3, 4):
+        raise ValueError(f"Invalid version: {version}")
+    if bbox_num > N.YB_MAX_BOXES:
+        raise ValueError(f"bbox_num {bbox_num} exceeds {N.YB_MAX_BOXES}")
+    p = N.LossParams()
+    p.version = version
+    p.grid_h, p.grid_w = int(grid_shape[0]), int(grid_shape[1])
+    p.bbox_num, p.class_num = int(bbox_num), int(class_num)
+    if anchors is not None and version != 1:
+        a = np.asarray(anchors, dtype=np.float32).reshape(-1)
+        if a.size != 2 * bbox_num:
+            raise ValueError("anchors must hold bbox_num (w, h) pairs")
+        p.has_anchors = 1
+        for i, v in enumerate(a):
+            p.anchors[i] = float(v)
+    else:
+        p.has_anchors = 0
+    p.binary_weight = float(np.asarray(binary_weight, dtype=np.float64).reshape(-1)[0])
+    lw = list(loss_weight) + [0.0] * 4
+    for i in range(4):
+        p.loss_weight[i] = float(lw[i])
+    p.wh_reg_weight = float(wh_reg_weight)
+    p.ignore_thresh = float(ignore_thresh)
+    p.truth_thresh = float(truth_thresh)
+    p.label_smooth = float(label_smooth)
+    p.focal_gamma = float(focal_loss_gamma)
+    p.use_focal = int(bool(use_focal_loss))
+    p.use_scale = int(bool(use_scale))
+    p.inv_batch = 1.0
+    return p
+
+
+def loss_fwd_bwd(params, y_trues, y_preds, global_batch=None, want_grad=True, want_terms=False,
+                 dpreds=None):
+    """One fused launch over the scales in ``params``.
+
+    y_trues[i]: (N, gh, gw, 5+C) fp32 CUDA; y_preds[i]: (N, gh, gw, B*(5+C)) fp32 CUDA.
+    Returns (loss [n_scales] fp32 CUDA, dpreds list or None, terms [n_scales, 8] f64 or None).
+    ``global_batch`` = divisor of reduce_mean(axis=0) (defaults to the local N).
+    """
+    n = len(params)
+    if not (1 <= n <= N.YB_MAX_SCALES) or len(y_trues) != n or len(y_preds) != n:
+        raise ValueError("between 1 and 4 scales, one y_true / y_pred each")
+    require_cuda(*y_trues, *y_preds)
+    dev = y_preds[0].device
+    scales = (N.LossScale * n)()
+    outs = []
+    for i, (p, yt, yp) in enumerate(zip(params, y_trues, y_preds)):
+        if yt.dtype != torch.float32 or yp.dtype != torch.float32:
+            raise N.YoloB200Error("loss tensors must be float32 (Keras casts y_true to y_pred.dtype)")
+        cells_per_img = p.grid_h * p.grid_w
+        pcf = (5 * p.bbox_num + p.class_num) if p.version == 1 else p.bbox_num * (5 + p.class_num)
+        tcf = 5 + p.class_num
+        if yp.numel() % (cells_per_img * pcf) != 0:
+            raise ValueError(f"y_pred with {yp.numel()} elements does not reshape to (-1,{p.grid_h},{p.grid_w},{pcf})")
+        n_img = yp.numel() // (cells_per_img * pcf)
+        if yt.numel() != n_img * cells_per_img * tcf:
+            raise ValueError(f"y_true with {yt.numel()} elements does not reshape to ({n_img},{p.grid_h},{p.grid_w},{tcf})")
+        q = N.LossParams.from_buffer_copy(p)
+        q.inv_batch = 1.0 / float(global_batch if global_batch is not None else max(n_img, 1))
+        d = None
+        if want_grad:
+            d = dpreds[i] if dpreds is not None else torch.empty_like(yp)
+            require_cuda(d)
+        outs.append(d)
+        scales[i].y_true = yt.data_ptr()
+        scales[i].y_pred = yp.data_ptr()
+        scales[i].dpred = d.data_ptr() if d is not None else None
+        scales[i].n_cells = n_img * cells_per_img
+        scales[i].p = q
+    with torch.cuda.device(dev):
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        terms = torch.empty((n, N.YB_LOSS_TERMS), dtype=_F64, device=dev) if want_terms else None
+        ws_bytes = N.lib.yb_loss_workspace_bytes(n)
+        ws = workspaces.get("loss", ws_bytes, dev)
+        N.check(N.lib.yb_loss_fwd_bwd(scales, n, _ptr(loss), _ptr(terms), _ptr(ws), ws_bytes, _stream()),
+                "yb_loss_fwd_bwd")
+    return loss, (outs if want_grad else None), terms
+
+
+def grid_iou(box_true, box_pred, grid_shape, want_ciou=False):
+    """box_true (..., 1, >=4), box_pred (..., B, >=4) fp32 CUDA, last-dim strides kept."""
+    require_cuda(box_true, box_pred)
+    B = box_pred.shape[-2]
+    n_cells = box_pred.numel() // (B * box_pred.shape[-1])
+    iou = torch.empty(box_pred.shape[:-1], dtype=torch.float32, device=box_pred.device)
+    ciou = torch.empty_like(iou) if want_ciou else None
+    with torch.cuda.device(box_pred.device):
+        N.check(N.lib.yb_grid_iou(_ptr(box_true), box_true.shape[-1], _ptr(box_pred), box_pred.shape[-1],
+                                  n_cells, B, int(grid_shape[0]), int(grid_shape[1]), _ptr(iou), _ptr(ciou),
+                                  _stream()), "yb_grid_iou")
+    return (iou, ciou) if want_ciou else iou
+
+
+# --------------------------------------------------------------------------
+# decode / NMS
+# --------------------------------------------------------------------------
+def make_decode_params(preds, class_num, threshold, version):
+    n = len(preds)
+    if not (1 <= n <= N.YB_MAX_SCALES):
+        raise ValueError("between 1 and 4 scales")
+    p = N.DecodeParams()
+    p.version, p.class_num, p.n_scales = int(version), int(class_num), n
+    if version not in (1, 2, 3, 4):
+        raise ValueError(f"Invalid version: {version}")
+    dt = preds[0].dtype
+    if dt not in (torch.float32, torch.float64):
+        raise N.YoloB200Error("decode inputs must be float32 or float64")
+    p.is_f64 = int(dt == torch.float64)
+    n_img = preds[0].shape[0]
+    for i, t in enumerate(preds):
+        if t.dim() != 4 or t.shape[0] != n_img or t.dtype != dt:
+            raise ValueError("decode inputs must be (n_img, gh, gw, info) tensors of one dtype")
+        p.grid_h[i], p.grid_w[i] = t.shape[1], t.shape[2]
+        info = t.shape[3]
+        if version == 1:
+            p.bbox_num[i] = (info - class_num) // 5
+            ok = p.bbox_num[i] * 5 + class_num == info
+        else:
+            p.bbox_num[i] = info // (5 + class_num)
+            ok = p.bbox_num[i] * (5 + class_num) == info
+        if not ok or p.bbox_num[i] < 1:
+            raise ValueError(f"cannot reshape info axis {info} for class_num={class_num}, version={version}")
+    p.threshold = float(threshold)
+    return p, n_img
+
+
+def decode_batch(preds, class_num=1, threshold=0.5, version=1, capacity=None, rows=None):
+    """Batched decode.  Returns (rows (capacity,7) f64, row_offsets (n_img+1) i64), both
+    CUDA; rows beyond row_offsets[-1] are unspecified.  If the true count exceeds the
+    capacity the caller must retry (see decode_batch_exact)."""
+    require_cuda(*preds)
+    p, n_img = make_decode_params(preds, class_num, threshold, version)
+    dev = preds[0].device
+    if rows is not None:
+        capacity = rows.shape[0]
+    if capacity is None:
+        capacity = max(1024, 512 * n_img)
+    with torch.cuda.device(dev):
+        if rows is None:
+            rows = torch.empty((capacity, 7), dtype=_F64, device=dev)
+        offsets = torch.empty(n_img + 1, dtype=_I64, device=dev)
+        ws_bytes = N.lib.yb_decode_workspace_bytes(C.byref(p), n_img)
+        ws = workspaces.get("decode", ws_bytes, dev)
+        ptrs = (C.c_void_p * len(preds))(*[t.data_ptr() for t in preds])
+        N.check(N.lib.yb_decode(ptrs, n_img, C.byref(p), _ptr(rows), capacity, _ptr(offsets), _ptr(ws),
+                                ws_bytes, _stream()), "yb_decode")
+    return rows, offsets
+
+
+def decode_batch_exact(preds, class_num=1, threshold=0.5, version=1, capacity=None):
+    """decode_batch + overflow check (one host sync); grows the buffer when needed."""
+    rows, offsets = decode_batch(preds, class_num, threshold, version, capacity)
+    total = int(offsets[-1].item())
+    if total > rows.shape[0]:
+        rows, offsets = decode_batch(preds, class_num, threshold, version, capacity=total)
+    return rows[:total], offsets
+
+
+def nms_batch(rows, row_offsets, class_num=1, nms_threshold=0.45, iou_mode=1, want_rows=True,
+              want_seg_offsets=False):
+    """Batched per-class NMS.  rows (R,7) f64 CUDA (R = capacity), row_offsets (n_img+1) i64
+    CUDA.  Returns dict(keep u8[R], out_rows (R,7), out_offsets (n_img+1), seg_offsets)."""
+    require_cuda(rows, row_offsets)
+    if rows.dtype != _F64 or row_offsets.dtype != _I64:
+        raise N.YoloB200Error("nms needs float64 rows and int64 offsets")
+    dev = rows.device
+    R = rows.shape[0]
+    n_img = row_offsets.numel() - 1
+    with torch.cuda.device(dev):
+        keep = torch.empty(max(R, 1), dtype=torch.uint8, device=dev)
+        out_rows = torch.empty((max(R, 1), 7), dtype=_F64, device=dev) if want_rows else None
+        out_offsets = torch.empty(n_img + 1, dtype=_I64, device=dev)
+        seg = torch.empty(n_img * class_num + 1, dtype=_I64, device=dev) if want_seg_offsets else None
+        ws_bytes = N.lib.yb_nms_workspace_bytes(R, n_img, class_num)
+        ws = workspaces.get("nms", ws_bytes, dev)
+        N.check(N.lib.yb_nms(_ptr(rows), _ptr(row_offsets), R, n_img, class_num, float(nms_threshold),
+                             int(iou_mode), _ptr(keep), _ptr(out_rows), _ptr(out_offsets), _ptr(seg),
+                             _ptr(ws), ws_bytes, _stream()), "yb_nms")
+    return dict(keep=keep[:R], out_rows=out_rows, out_offsets=out_offsets, seg_offsets=seg)
+
+
+def pairwise_iou(a, b, mode=1):
+    """(na, >=4) x (nb, >=4) f64 CUDA -> (na, nb) f64; a plays xywh_true."""
+    require_cuda(a, b)
+    if a.dtype != _F64 or b.dtype != _F64:
+        raise N.YoloB200Error("pairwise_iou needs float64")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=_F64, device=a.device)
+    with torch.cuda.device(a.device):
+        N.check(N.lib.yb_pairwise_iou(_ptr(a), a.shape[0], a.shape[1], _ptr(b), b.shape[0], b.shape[1],
+                                      int(mode), _ptr(out), _stream()), "yb_pairwise_iou")
+    return out
+
+
+def elementwise_iou(a, b, mode=1):
+    """(n, >=4) vs (n, >=4) f64 CUDA -> (n,) f64."""
+    require_cuda(a, b)
+    out = torch.empty(a.shape[0], dtype=_F64, device=a.device)
+    with torch.cuda.device(a.device):
+        N.check(N.lib.yb_elementwise_iou(_ptr(a), a.shape[1], _ptr(b), b.shape[1], a.shape[0], int(mode),
+                                         _ptr(out), _stream()), "yb_elementwise_iou")
+    return out
+
+
+# --------------------------------------------------------------------------
+# k-means
+# --------------------------------------------------------------------------
+def kmeans_assign(data, centers, dist_kind=N.YB_DIST_IOU, want_assign=False):
+    """data (M,d) f64 CUDA, centers (k,d) f64 CUDA -> (assign i32[M] | None, sums (k,d), counts i64[k])."""
+    require_cuda(data, centers)
+    if data.dtype != _F64 or centers.dtype != _F64:
+        raise N.YoloB200Error("kmeans needs float64")
+    M, d = data.shape
+    k = centers.shape[0]
+    dev = data.device
+    with torch.cuda.device(dev):
+        assign = torch.empty(M, dtype=torch.int32, device=dev) if want_assign else None
+        sums = torch.empty((k, d), dtype=_F64, device=dev)
+        counts = torch.empty(k, dtype=_I64, device=dev)
+        ws_bytes = N.lib.yb_kmeans_workspace_bytes(M, k, d)
+        if ws_bytes == 0:
+            raise ValueError("unsupported k / n_dim")
+        ws = workspaces.get("kmeans", ws_bytes, dev)
+        N.check(N.lib.yb_kmeans_assign(_ptr(data), M, d, _ptr(centers), k, int(dist_kind), _ptr(assign),
+                                       _ptr(sums), _ptr(counts), _ptr(ws), ws_bytes, _stream()),
+                "yb_kmeans_assign")
+    return assign, sums, counts
+
+
+def minmax(data):
+    require_cuda(data)
+    if data.dtype != _F64:
+        raise N.YoloB200Error("minmax needs float64")
+    dev = data.device
+    with torch.cuda.device(dev):
+        out = torch.empty(2, dtype=_F64, device=dev)
+        ws = workspaces.get("minmax", 64 * 1024, dev)
+        N.check(N.lib.yb_minmax_f64(_ptr(data), data.numel(), _ptr(out), _ptr(ws), 64 * 1024, _stream()),
+                "yb_minmax_f64")
+    return out
+
+
+# --------------------------------------------------------------------------
+# mAP matching
+# --------------------------------------------------------------------------
+def map_match(gt_rows, gt_offsets, det_rows, det_offsets, class_num):
+    require_cuda(gt_rows, gt_offsets, det_rows, det_offsets)
+    dev = det_offsets.device
+    n_img = det_offsets.numel() - 1
+    with torch.cuda.device(dev):
+        best_iou = torch.empty(max(det_rows.shape[0], 1), dtype=_F64, device=dev)
+        best_gt = torch.empty(max(det_rows.shape[0], 1), dtype=torch.int32, device=dev)
+        counts = torch.empty((n_img, class_num), dtype=torch.int32, device=dev)
+        N.check(N.lib.yb_map_match(_ptr(gt_rows), _ptr(gt_offsets), _ptr(det_rows), _ptr(det_offsets), n_img,
+                                   class_num, gt_rows.shape[0], det_rows.shape[0], _ptr(best_iou),
+                                   _ptr(best_gt), _ptr(counts), _stream()), "yb_map_match")
+    return best_iou[:det_rows.shape[0]], best_gt[:det_rows.shape[0]], counts

@@ -1,0 +1,101 @@
+"""Mirror of the hot-path functions of /root/reference/utils/tools.py:
+``decode`` (:370-438), ``cal_iou`` (:630-684), ``nms`` (:687-733) with the
+reference's NumPy signatures and return types, executed on the GPU through the
+C ABI (yb_decode / yb_pairwise_iou / yb_nms).  ``decode_batch`` / ``nms_batch``
+are the device-resident, whole-batch forms the per-image functions are built on.
+"""
+import numpy as np
+import torch
+
+from .. import engine
+from .._native import YoloB200Error
+
+EPSILON = 1e-07
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise YoloB200Error("no CUDA device: tf2_yolo_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _as_device_grid(a, dev, dtype=None):
+    if torch.is_tensor(a):
+        t = a
+    else:
+        a = np.asarray(a)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64 if a.dtype.itemsize > 4 else np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(dev, non_blocking=True).contiguous()
+
+
+decode_batch = engine.decode_batch_exact
+nms_batch = engine.nms_batch
+
+
+def decode(*label_datas, class_num=1, threshold=0.5, version=1):
+    """Decode the prediction (or label) grids of ONE image.
+
+    Args and return value as the reference: ndarrays (grid_h, grid_w, info) in,
+    ``(K, 7)`` float64 rows [x, y, w, h, c, class index, class probability] out;
+    shape ``(0,)`` when nothing passes the threshold.
+    """
+    if version not in (1, 2, 3, 4):
+        raise ValueError(f"Invalid version: {version}")
+    if len(label_datas) == 0:
+        return np.array([], dtype="float")
+    dev = _device()
+    f64 = any((torch.is_tensor(a) and a.dtype == torch.float64) or
+              (not torch.is_tensor(a) and np.asarray(a).dtype == np.float64) for a in label_datas)
+    dt = torch.float64 if f64 else torch.float32
+    chunks = []
+    # scales share one launch when they fit the ABI's scale table
+    for i in range(0, len(label_datas), 4):
+        grids = [_as_device_grid(a, dev, dt).unsqueeze(0) for a in label_datas[i:i + 4]]
+        rows, _ = engine.decode_batch_exact(grids, class_num, threshold, version)
+        chunks.append(rows)
+    rows = torch.cat(chunks, dim=0) if len(chunks) > 1 else chunks[0]
+    out = rows.cpu().numpy()
+    if out.shape[0] == 0:
+        return np.array([], dtype="float")
+    return out
+
+
+def cal_iou(xywh_true, xywh_pred, mode=1):
+    """IoU (mode 1) / DIoU (mode 2) with NumPy broadcasting semantics."""
+    if mode not in (1, 2):
+        return None  # the reference falls off the end of the function
+    a = np.asarray(xywh_true, dtype=np.float64)
+    b = np.asarray(xywh_pred, dtype=np.float64)
+    dev = _device()
+    lead = np.broadcast_shapes(a.shape[:-1], b.shape[:-1])
+    if (a.ndim == 3 and b.ndim == 3 and a.shape[1] == 1 and b.shape[0] == 1):
+        ta = torch.from_numpy(np.ascontiguousarray(a[:, 0, :])).to(dev)
+        tb = torch.from_numpy(np.ascontiguousarray(b[0, :, :])).to(dev)
+        return engine.pairwise_iou(ta, tb, mode).cpu().numpy()
+    ab = np.ascontiguousarray(np.broadcast_to(a, lead + a.shape[-1:])).reshape(-1, a.shape[-1])
+    bb = np.ascontiguousarray(np.broadcast_to(b, lead + b.shape[-1:])).reshape(-1, b.shape[-1])
+    out = engine.elementwise_iou(torch.from_numpy(ab).to(dev), torch.from_numpy(bb).to(dev), mode)
+    return out.cpu().numpy().reshape(lead)
+
+
+def nms(xywhcp, class_num=1, nms_threshold=0.45, iou_mode=1):
+    """Per-class greedy NMS (iou_mode 1) / DIoU-NMS (iou_mode 2) of one image's rows."""
+    xywhcp = np.asarray(xywhcp, dtype=np.float64)
+    if xywhcp.ndim != 2:
+        raise IndexError("too many indices for array: nms needs (K, 7) rows from decode()")
+    dev = _device()
+    rows = torch.from_numpy(np.ascontiguousarray(xywhcp)).to(dev)
+    offsets = torch.tensor([0, rows.shape[0]], dtype=torch.int64, device=dev)
+    r = engine.nms_batch(rows, offsets, class_num, nms_threshold, iou_mode)
+    n = int(r["out_offsets"][-1].item())
+    return r["out_rows"][:n].cpu().numpy()
+
+
+def soft_nms(xywhcp, class_num=1, nms_threshold=0.45, conf_threshold=0.5, sigma=0.5):
+    raise NotImplementedError(
+        "soft_nms (nms_mode=2) is not on the CUDA path yet (SURVEY.md 8f row 4); "
+        "there is deliberately no CPU fallback")

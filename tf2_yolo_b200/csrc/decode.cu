@@ -30,6 +30,11 @@ struct DecodeLaunch {
     int n_scales, C, version;
     long long n_img;
     double thr;
+    // K1 tiling
+    int tile_cells[YB_MAX_SCALES];
+    int tile_base[YB_MAX_SCALES + 1];
+    int bulk_ok[YB_MAX_SCALES];
+    int stage_bytes;
 };
 
 template <typename T>
@@ -78,59 +83,132 @@ __device__ __forceinline__ int cell_hits(const T* __restrict__ cell, int B, int 
     return n;
 }
 
+// K1: persistent CTAs; a producer warp streams tiles of cells through a shared-memory
+// ring with 1-D bulk-async copies (TMA), consumer warps own whole cells (lane = cell*B + box),
+// each lane walks the C class scores of its box (lanes are an odd number of words apart ->
+// conflict-free), per-cell counts by shuffle.  Cells with hits are appended to a work list.
+constexpr int kDecMaxConsumerWarps = 8;
+constexpr int kDecStages = 3;
+
 template <typename T>
-__global__ void __launch_bounds__(256)
-decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __restrict__ counts) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long total = L.scale_base[L.n_scales];
+__global__ void __launch_bounds__((kDecMaxConsumerWarps + 1) * 32)
+decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __restrict__ counts,
+                    unsigned int* __restrict__ n_hot, long long* __restrict__ hot_cells) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full[kDecStages], done[kDecStages];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncw = (int)(blockDim.x >> 5) - 1;
+    if (tid == 0) {
+        for (int i = 0; i < kDecStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&done[i], ncw * 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int total_tiles = L.tile_base[L.n_scales];
+    const int n_my = (total_tiles > (int)blockIdx.x)
+                         ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
+                         : 0;
     const T thr = (T)L.thr;
-    for (long long g = warp; g < total; g += n_warps) {
+
+    if (warp == ncw) {  // ---- producer ----
         int s = 0;
-        while (g >= L.scale_base[s + 1]) ++s;
-        const long long local = g - L.scale_base[s];  // img * cells + cell, memory order
-        const long long img = local / L.cells[s];
-        const long long cell = local - img * L.cells[s];
-        const T* ptr = reinterpret_cast<const T*>(L.preds[s]) + local * L.pcf[s];
-        const int n = cell_hits<T, false>(ptr, L.B[s], L.C, L.version, thr, lane, nullptr, 0, 0, 0, 0, 1, 1);
-        if (lane == 0) counts[img * L.cell_base[L.n_scales] + L.cell_base[s] + cell] = (unsigned)n;
+        for (int t = 0; t < n_my; ++t) {
+            const int tile = blockIdx.x + t * gridDim.x;
+            while (tile >= L.tile_base[s + 1]) ++s;
+            const long long cell0 = (long long)(tile - L.tile_base[s]) * L.tile_cells[s];
+            const long long n_cells = L.n_img * L.cells[s];
+            const int nc = (int)min((long long)L.tile_cells[s], n_cells - cell0);
+            const int stage = t % kDecStages;
+            if (t >= kDecStages) mbar_wait(&done[stage], ((t / kDecStages) - 1) & 1);
+            T* dst = reinterpret_cast<T*>(smem + (size_t)stage * L.stage_bytes);
+            const T* src = reinterpret_cast<const T*>(L.preds[s]) + cell0 * L.pcf[s];
+            const uint32_t bytes = (uint32_t)nc * L.pcf[s] * (uint32_t)sizeof(T);
+            if (L.bulk_ok[s] && (bytes & 15u) == 0u) {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    bulk_g2s(dst, src, bytes, &full[stage]);
+                }
+            } else {
+                for (int i = lane; i < nc * L.pcf[s]; i += 32) dst[i] = src[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+            }
+        }
+    } else {            // ---- consumers ----
+        int s = 0, cur = -1, cpw = 0, lc = 0, lb = 0;
+        bool lane_on = false;
+        for (int it = 0; it < n_my; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            while (tile >= L.tile_base[s + 1]) ++s;
+            if (s != cur) {
+                cur = s;
+                cpw = 32 / L.B[s];
+                lc = lane / L.B[s];
+                lb = lane - lc * L.B[s];
+                lane_on = lc < cpw;
+            }
+            const int B = L.B[s], C = L.C, pcf = L.pcf[s];
+            const long long cell0 = (long long)(tile - L.tile_base[s]) * L.tile_cells[s];
+            const long long n_cells = L.n_img * L.cells[s];
+            const int nc = (int)min((long long)L.tile_cells[s], n_cells - cell0);
+            const int stage = it % kDecStages;
+            const T* sp = reinterpret_cast<const T*>(smem + (size_t)stage * L.stage_bytes);
+            mbar_wait(&full[stage], (it / kDecStages) & 1);
+            for (int c0 = warp * cpw; c0 < nc; c0 += ncw * cpw) {
+                const int cell = c0 + lc;
+                const bool valid = lane_on && cell < nc;
+                int n = 0;
+                if (valid) {
+                    const T* box = sp + (size_t)cell * pcf + lb * ((L.version == 1) ? 5 : 5 + C);
+                    const T* prob = (L.version == 1) ? sp + (size_t)cell * pcf + 5 * B : box + 5;
+                    const T c = box[4];
+#pragma unroll 4
+                    for (int k = 0; k < C; ++k) n += (mul_rn<T>(c, prob[k]) >= thr) ? 1 : 0;
+                }
+                int tot = 0;
+                for (int q = 0; q < B; ++q) tot += __shfl_sync(0xffffffffu, n, lc * B + q);
+                if (valid && lb == 0) {
+                    const long long g = cell0 + cell;
+                    const long long img = g / L.cells[s];
+                    const long long o = img * L.cell_base[L.n_scales] + L.cell_base[s] + (g - img * L.cells[s]);
+                    counts[o] = (unsigned)tot;
+                    if (tot > 0) hot_cells[atomicAdd(n_hot, 1u)] = o;
+                }
+            }
+            mbar_arrive(&done[stage]);
+        }
     }
 }
 
+// K2: one warp per cell that has hits (work list from K1): re-evaluate it and write rows in
+// (box, class) order at the scanned offset.
 template <typename T>
 __global__ void __launch_bounds__(256)
-decode_emit_kernel(const __grid_constant__ DecodeLaunch L, const unsigned int* __restrict__ counts,
-                   const long long* __restrict__ offsets, double* __restrict__ rows, long long cap,
-                   long long* __restrict__ row_offsets) {
+decode_emit_kernel(const __grid_constant__ DecodeLaunch L, const unsigned int* __restrict__ n_hot,
+                   const long long* __restrict__ hot_cells, const long long* __restrict__ offsets,
+                   double* __restrict__ rows, long long cap, long long* __restrict__ row_offsets) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long per_img = L.cell_base[L.n_scales];
-    const long long total = L.n_img * per_img;
     const T thr = (T)L.thr;
-    // per-image extents
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= L.n_img;
          i += (long long)gridDim.x * blockDim.x)
         row_offsets[i] = offsets[i * per_img];
-    for (long long base = warp * 32; base < total; base += n_warps * 32) {
-        const long long idx = base + lane;
-        const unsigned cnt = (idx < total) ? counts[idx] : 0u;
-        unsigned m = __ballot_sync(0xffffffffu, cnt != 0u);
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const long long o = base + src;  // output-order cell index
-            const long long img = o / per_img;
-            const long long rem = o - img * per_img;
-            int s = 0;
-            while (rem >= L.cell_base[s + 1]) ++s;
-            const long long cell = rem - L.cell_base[s];
-            const int yi = (int)(cell / L.gw[s]), xi = (int)(cell - (long long)yi * L.gw[s]);
-            const T* ptr = reinterpret_cast<const T*>(L.preds[s]) + (img * L.cells[s] + cell) * L.pcf[s];
-            cell_hits<T, true>(ptr, L.B[s], L.C, L.version, thr, lane, rows, offsets[o], cap, xi, yi,
-                               L.gw[s], L.gh[s]);
-        }
+    const long long n = *n_hot;
+    for (long long w = warp; w < n; w += n_warps) {
+        const long long o = hot_cells[w];  // output-order cell index
+        const long long img = o / per_img;
+        const long long rem = o - img * per_img;
+        int s = 0;
+        while (rem >= L.cell_base[s + 1]) ++s;
+        const long long cell = rem - L.cell_base[s];
+        const int yi = (int)(cell / L.gw[s]), xi = (int)(cell - (long long)yi * L.gw[s]);
+        const T* ptr = reinterpret_cast<const T*>(L.preds[s]) + (img * L.cells[s] + cell) * L.pcf[s];
+        cell_hits<T, true>(ptr, L.B[s], L.C, L.version, thr, lane, rows, offsets[o], cap, xi, yi, L.gw[s],
+                           L.gh[s]);
     }
 }
 
@@ -148,7 +226,8 @@ static int fill_decode(const void* const* preds, int64_t n_img, const yb_decode_
     for (int s = 0; s < p->n_scales; ++s) {
         if (preds[s] == nullptr) return YB_E_NULL;
         if ((uintptr_t)preds[s] & (esz - 1)) return YB_E_ALIGN;
-        if (p->grid_h[s] <= 0 || p->grid_w[s] <= 0 || p->bbox_num[s] <= 0) return YB_E_SHAPE;
+        if (p->grid_h[s] <= 0 || p->grid_w[s] <= 0 || p->bbox_num[s] <= 0 || p->bbox_num[s] > 32)
+            return YB_E_SHAPE;
         L.preds[s] = preds[s];
         L.gh[s] = p->grid_h[s];
         L.gw[s] = p->grid_w[s];
@@ -172,6 +251,9 @@ static size_t decode_counts_bytes(long long total_cells) {
 static size_t decode_offsets_bytes(long long total_cells) {
     return align_up((size_t)(total_cells + 2) * sizeof(long long), 256);
 }
+static size_t decode_hot_bytes(long long total_cells) {
+    return align_up((size_t)(total_cells + 1) * sizeof(long long), 256);
+}
 
 extern "C" size_t yb_decode_workspace_bytes(const yb_decode_params* p, int64_t n_img) {
     if (p == nullptr || n_img < 0) return 0;
@@ -179,7 +261,8 @@ extern "C" size_t yb_decode_workspace_bytes(const yb_decode_params* p, int64_t n
     for (int s = 0; s < p->n_scales && s < YB_MAX_SCALES; ++s)
         per_img += (long long)p->grid_h[s] * p->grid_w[s];
     const long long total = per_img * n_img;
-    return decode_counts_bytes(total) + decode_offsets_bytes(total) + scan_workspace_bytes(total > 0 ? total : 1);
+    return 256 + decode_counts_bytes(total) + decode_offsets_bytes(total) + decode_hot_bytes(total) +
+           scan_workspace_bytes(total > 0 ? total : 1);
 }
 
 extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decode_params* p, double* rows,
@@ -199,27 +282,54 @@ extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decod
         YB_CUDA_TRY(cudaMemsetAsync(row_offsets, 0, sizeof(int64_t) * (n_img + 1), stream));
         return YB_OK;
     }
-    unsigned int* counts = reinterpret_cast<unsigned int*>(workspace);
-    long long* offsets = reinterpret_cast<long long*>((char*)workspace + decode_counts_bytes(total));
-    void* scan_ws = (char*)offsets + decode_offsets_bytes(total);
+    unsigned int* n_hot = reinterpret_cast<unsigned int*>(workspace);
+    unsigned int* counts = reinterpret_cast<unsigned int*>((char*)workspace + 256);
+    long long* offsets = reinterpret_cast<long long*>((char*)counts + decode_counts_bytes(total));
+    long long* hot = reinterpret_cast<long long*>((char*)offsets + decode_offsets_bytes(total));
+    void* scan_ws = (char*)hot + decode_hot_bytes(total);
 
-    const int threads = 256;
-    const long long warps_needed = total;
-    int blocks = (int)min((long long)kNumSMs * 8, (warps_needed * 32 + threads - 1) / threads);
-    if (p->is_f64)
-        decode_count_kernel<double><<<blocks, threads, 0, stream>>>(L, counts);
-    else
-        decode_count_kernel<float><<<blocks, threads, 0, stream>>>(L, counts);
+    // K1 geometry: 3 stages of <= 24 KB, 3 CTAs per SM
+    const size_t esz = p->is_f64 ? 8 : 4;
+    const int stage_budget = 24 * 1024;
+    int ncw = 1, n_tiles = 0, stage_bytes = 0;
+    for (int s = 0; s < L.n_scales; ++s) {
+        const int cb = (int)(L.pcf[s] * esz);
+        if (4 * cb > 72 * 1024) return YB_E_SHAPE;
+        const int cpw = 32 / min(L.B[s], 32);
+        if (cpw < 1) return YB_E_SHAPE;
+        int t = stage_budget / cb / 4 * 4;
+        t = min(t, kDecMaxConsumerWarps * cpw / 4 * 4);
+        t = max(4, t);
+        L.tile_cells[s] = t;
+        L.tile_base[s + 1] = L.tile_base[s] + (int)((L.n_img * L.cells[s] + t - 1) / t);
+        L.bulk_ok[s] = (((uintptr_t)L.preds[s] & 15) == 0) ? 1 : 0;
+        stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
+        ncw = max(ncw, min(kDecMaxConsumerWarps, (t + cpw - 1) / cpw));
+    }
+    n_tiles = L.tile_base[L.n_scales];
+    L.stage_bytes = stage_bytes;
+    const size_t smem = (size_t)kDecStages * stage_bytes;
+    const int ctas_per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 2048))));
+    const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
+    const int threads1 = (ncw + 1) * 32;
+    YB_CUDA_TRY(cudaMemsetAsync(n_hot, 0, sizeof(unsigned int), stream));
+    if (p->is_f64) {
+        YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot);
+    } else {
+        YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot);
+    }
     YB_CUDA_TRY(cudaGetLastError());
     rc = exclusive_scan_u32(counts, total, offsets, scan_ws, stream);
     if (rc != 0) return rc;
-    int blocks2 = (int)min((long long)kNumSMs * 8, (total + threads - 1) / threads);
-    if (blocks2 < 1) blocks2 = 1;
+    const int threads = 256;
+    const int blocks2 = kNumSMs * 4;
     if (p->is_f64)
         decode_emit_kernel<double><<<blocks2, threads, 0, stream>>>(
-            L, counts, offsets, rows, row_capacity, reinterpret_cast<long long*>(row_offsets));
+            L, n_hot, hot, offsets, rows, row_capacity, reinterpret_cast<long long*>(row_offsets));
     else
         decode_emit_kernel<float><<<blocks2, threads, 0, stream>>>(
-            L, counts, offsets, rows, row_capacity, reinterpret_cast<long long*>(row_offsets));
+            L, n_hot, hot, offsets, rows, row_capacity, reinterpret_cast<long long*>(row_offsets));
     return (int)cudaGetLastError();
 }

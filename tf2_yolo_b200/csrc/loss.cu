@@ -9,11 +9,12 @@
 //                   into a shared-memory ring, bulk-async store of the same
 //                   buffer -- by then overwritten in place with dL/dy_pred -- back
 //                   to HBM.
-//   consumer warps: A1 one thread per (cell, box): fp32 IoU against the label box
-//                   A2 argmax over the B boxes -> responsible / ignore masks,
-//                      box + objectness + wh terms and their 5 gradients (in place)
-//                   B  one warp per (cell, box) row: class cross-entropy and its
-//                      gradient for responsible boxes, zero-fill for all others
+//   consumer warps: a warp owns whole cells, one lane per (cell, box): fp32 IoU against
+//                   the label box, argmax over the B boxes by shuffle -> responsible /
+//                   ignore masks, box + objectness + wh terms and their 5 gradients
+//                   written in place, zero-fill of the box's class-score gradients;
+//                   the rare responsible boxes then get their class cross-entropy and
+//                   gradient from the whole warp (fp64).  No CTA-wide barrier.
 //   reduction     : fp64 partial sums per thread -> warp -> CTA -> global partials,
 //                   last CTA sums them in a fixed order (deterministic) and emits
 //                   the fp32 loss of every scale.
@@ -28,9 +29,8 @@
 
 namespace yb {
 
-constexpr int kLossConsumerWarps = 4;
-constexpr int kLossConsumers = kLossConsumerWarps * 32;
-constexpr int kLossThreads = kLossConsumers + 32;
+constexpr int kLossMaxConsumerWarps = 8;
+constexpr int kLossMaxThreads = (kLossMaxConsumerWarps + 1) * 32;
 constexpr int kMaxStages = 4;
 constexpr int kTerms = 5;
 constexpr float kEpsF = 1e-07f;
@@ -64,7 +64,6 @@ struct LossLaunch {
     int n_scales;
     int total_tiles;
     int stage_bytes;       // bytes of one ring stage
-    int max_rows;          // max over scales of tile_cells * B
     int n_stages;
     double* partials;      // [gridDim][n_scales][kTerms]
     unsigned int* counter;
@@ -180,40 +179,64 @@ __device__ __forceinline__ void focal_term(float e, float g, float& f, float& df
 }
 
 // ---- the kernel --------------------------------------------------------------
+//
+// Thread mapping of the consumer warps: a warp owns whole cells, lane = cell_local*B + box
+// (32/B cells per warp, the last 32 % B lanes idle), so the argmax over the boxes of a cell is
+// a handful of shuffles and the consumer warps never synchronise with each other - only with
+// the producer, through the full/done mbarriers of the stage.
 
 template <int V>
-__global__ void __launch_bounds__(kLossThreads)
+__device__ __forceinline__ void class_row(float* q, const float* t, float m, int C, int lane, bool write,
+                                          double lwc, double& part) {
+    // cross-entropy over the C class scores of one responsible box (v2-v4) / object cell (v1)
+    for (int k = lane; k < C; k += 32) {
+        const double p = (double)q[k], tk = (double)t[k];
+        const double pc = fmin(fmax(p, kEps), 1.0 - kEps);
+        const double band = (p >= kEps && p <= 1.0 - kEps) ? 1.0 : 0.0;
+        double l, g;
+        if (V == 1 || V == 2) {  // positive-only CE (yolov2/losses/loss.py:116-124, v1 :101-109)
+            l = tk * log(pc);
+            g = -tk / pc;
+        } else {                 // BCE (yolov4/losses/loss.py:145-154)
+            l = tk * log(pc) + (1.0 - tk) * log(1.0 - pc);
+            g = -(tk / pc - (1.0 - tk) / (1.0 - pc));
+        }
+        part -= (double)m * l;
+        if (write) q[k] = (float)(lwc * (double)m * g * band);
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kLossMaxThreads)
 loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int n_stages = L.n_stages;
+    const int ncw = (int)(blockDim.x >> 5) - 1;  // consumer warps; the last warp is the producer
 
     unsigned char* ring = smem;
-    float* s_iou = reinterpret_cast<float*>(smem + (size_t)n_stages * L.stage_bytes);
-    float* s_pos = s_iou + L.max_rows;
-    double* s_acc = reinterpret_cast<double*>(
-        smem + align_up((size_t)n_stages * L.stage_bytes + 2 * sizeof(float) * L.max_rows, 16));
-    // s_acc: [kLossConsumerWarps][YB_MAX_SCALES][kTerms]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + kLossConsumerWarps * YB_MAX_SCALES * kTerms);
+    double* s_acc = reinterpret_cast<double*>(smem + (size_t)n_stages * L.stage_bytes);
+    // s_acc: [kLossMaxConsumerWarps][YB_MAX_SCALES][kTerms]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms);
     uint64_t* done = full + kMaxStages;
     __shared__ int s_is_last;
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&done[i], kLossConsumers);
+            mbar_init(&done[i], ncw * 32);
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < kLossConsumerWarps * YB_MAX_SCALES * kTerms; i += kLossThreads) s_acc[i] = 0.0;
+    for (int i = tid; i < kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
 
     const int n_my = (L.total_tiles > (int)blockIdx.x)
                          ? (L.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
                          : 0;
 
-    if (warp == kLossConsumerWarps) {
+    if (warp == ncw) {
         // ===================== producer warp =====================
         int s_ld = 0, s_st = 0;
         for (int t = 0; t < n_my + n_stages - 1; ++t) {
@@ -273,7 +296,10 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
         double acc[kTerms];
 #pragma unroll
         for (int k = 0; k < kTerms; ++k) acc[k] = 0.0;
-        int cur = 0;
+        int cur = -1;
+        int cpw = 0, lc = 0, lb = 0;  // cells per warp, this lane's local cell / box
+        bool lane_on = false;
+        float aw = 1.f, ah = 1.f;
         auto flush = [&](int s) {
 #pragma unroll
             for (int k = 0; k < kTerms; ++k) {
@@ -285,11 +311,18 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
 
         for (int it = 0; it < n_my; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
-            int s = cur;
+            int s = (cur < 0) ? 0 : cur;
             while (tile >= L.sc[s].tile_base + L.sc[s].n_tiles) ++s;
             if (s != cur) {
-                flush(cur);
+                if (cur >= 0) flush(cur);
                 cur = s;
+                const int Bs = L.sc[s].B;
+                cpw = 32 / Bs;
+                lc = lane / Bs;
+                lb = lane - lc * Bs;
+                lane_on = lc < cpw;
+                aw = L.sc[s].anc[2 * (lane_on ? lb : 0)];
+                ah = L.sc[s].anc[2 * (lane_on ? lb : 0) + 1];
             }
             const LossScaleDev& S = L.sc[s];
             const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
@@ -299,212 +332,183 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
             const float* st = sp + S.tile_cells * S.pcf;
             const int B = S.B, C = S.C;
             const int bstride = (V == 1) ? 5 : (5 + C);
-            const int nb = nc * B;
             const bool write = S.dpred != nullptr;
+            const float inv_n = S.inv_n;
 
             mbar_wait(&full[stage], (it / n_stages) & 1);
 
-            // ---- A1: IoU of every predicted box with the label box of its cell
-            for (int j = tid; j < nb; j += kLossConsumers) {
-                const int cell = j / B, b = j - cell * B;
-                const float* pc = sp + cell * S.pcf + b * bstride;
-                const float* tc = st + cell * S.tcf;
-                s_iou[j] = grid_iou_f32(pc[0], pc[1], pc[2], pc[3], tc[0], tc[1], tc[2], tc[3], S.gw, S.gh);
-            }
-            bar_sync(1, kLossConsumers);
-
-            // ---- A2: masks, box / objectness / size terms, 5 gradients per box
-            for (int j = tid; j < nb; j += kLossConsumers) {
-                const int cell = j / B, b = j - cell * B;
-                float* pc = sp + cell * S.pcf + b * bstride;
-                const float* tc = st + cell * S.tcf;
-                const float* ci = s_iou + cell * B;
+            for (int c0 = warp * cpw; c0 < nc; c0 += ncw * cpw) {
+                const int cell = c0 + lc;
+                const bool valid = lane_on && cell < nc;
+                float* pc = sp + (valid ? cell : c0) * S.pcf + lb * bstride;
+                const float* tc = st + (valid ? cell : c0) * S.tcf;
+                float px = 0.f, py = 0.f, pw = 1.f, ph = 1.f, c = 0.5f;
+                float tx = 0.f, ty = 0.f, tw = 0.f, th = 0.f, obj = 0.f;
+                if (valid) {
+                    px = pc[0]; py = pc[1]; pw = pc[2]; ph = pc[3]; c = pc[4];
+                    tx = tc[0]; ty = tc[1]; tw = tc[2]; th = tc[3]; obj = tc[4];
+                }
+                const float iou = grid_iou_f32(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh);
+                // argmax over the boxes of the cell (first maximum, like tf.argmax)
                 int amax = 0;
-                float best = ci[0];
+                float best = __shfl_sync(0xffffffffu, iou, lc * B);
                 for (int q = 1; q < B; ++q) {
-                    const float v = ci[q];
+                    const float v = __shfl_sync(0xffffffffu, iou, lc * B + q);
                     if (v > best) {
                         best = v;
                         amax = q;
                     }
                 }
-                const float iou = ci[b];
-                const float px = pc[0], py = pc[1], pw = pc[2], ph = pc[3], c = pc[4];
-                const float tx = tc[0], ty = tc[1], tw = tc[2], th = tc[3], obj = tc[4];
-                const float resp = (b == amax) ? 1.f : 0.f;
-                const float inv_n = S.inv_n;
+                const float resp = (lb == amax) ? 1.f : 0.f;
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
-                float pos;
-
-                if (V == 1) {
-                    pos = obj * resp;
-                    const float neg = 1.f - pos;
-                    const float dx = tx - px, dy = ty - py;
-                    acc[0] += (double)(pos * (dx * dx + dy * dy));
-                    g0 = -2.f * S.lw[0] * pos * dx * inv_n;
-                    g1 = -2.f * S.lw[0] * pos * dy * inv_n;
-                    const float sw = sqrtf(fmaxf(pw, kEpsF)), sh = sqrtf(fmaxf(ph, kEpsF));
-                    const float dw = sqrtf(fmaxf(tw, kEpsF)) - sw, dh = sqrtf(fmaxf(th, kEpsF)) - sh;
-                    acc[1] += (double)(pos * (dw * dw + dh * dh));
-                    g2 = (pw >= kEpsF) ? -S.lw[1] * pos * dw / sw * inv_n : 0.f;
-                    g3 = (ph >= kEpsF) ? -S.lw[1] * pos * dh / sh * inv_n : 0.f;
-                    if (pos != 0.f) {
-                        BoxGrad bg;
-                        box_fwd_bwd<false>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
-                        const double d = bg.iou - (double)c;
-                        acc[2] += (double)pos * d * d + (double)(S.bw * neg * c * c);
-                        const double gi = 2.0 * S.lw[2] * pos * d * S.inv_n_d;
-                        g0 += (float)(gi * bg.diou[0]);
-                        g1 += (float)(gi * bg.diou[1]);
-                        g2 += (float)(gi * bg.diou[2]);
-                        g3 += (float)(gi * bg.diou[3]);
-                        g4 = (float)(-gi) + 2.f * S.lw[2] * S.bw * neg * c * inv_n;
-                    } else {
-                        acc[2] += (double)(S.bw * neg * c * c);
-                        g4 = 2.f * S.lw[2] * S.bw * neg * c * inv_n;
-                    }
-                } else {
-                    pos = obj * resp;
-                    if (V == 4 && S.truth_thr < 1.f)
-                        pos = pos + ((iou > S.truth_thr) ? 1.f : 0.f) * (1.f - pos);
-                    const float neg = (1.f - pos) * ((iou < S.ignore_thr) ? 1.f : 0.f);
-                    const float aw = S.anc[2 * b], ah = S.anc[2 * b + 1];
-                    const float lpw = logf(pw / aw), lph = logf(ph / ah);
-
-                    if (V == 4) {
-                        // wh regulariser, every box (loss.py:156-160)
-                        acc[3] += (double)(lpw * lpw + lph * lph);
-                        g2 = 2.f * S.whw * lpw / pw * inv_n;
-                        g3 = 2.f * S.whw * lph / ph * inv_n;
-                        // focal objectness with label smoothing (loss.py:119-143)
-                        const float cc = fminf(fmaxf(c, kEpsF), 1.f - kEpsF);
-                        const float band = (c >= kEpsF && c <= 1.f - kEpsF) ? 1.f : 0.f;
-                        float e_p, e_n, de_p, de_n;
-                        if (S.label_smooth > 0.f) {
-                            const float u = 1.f - S.label_smooth - cc, w2 = S.label_smooth - cc;
-                            e_p = fabsf(u);
-                            de_p = (u > 0.f) ? -1.f : ((u < 0.f) ? 1.f : 0.f);
-                            e_n = fabsf(w2);
-                            de_n = (w2 > 0.f) ? -1.f : ((w2 < 0.f) ? 1.f : 0.f);
-                        } else {
-                            e_p = 1.f - cc;
-                            de_p = -1.f;
-                            e_n = cc;
-                            de_n = 1.f;
-                        }
-                        float fn, dfn;
-                        focal_term(e_n, S.gamma, fn, dfn);
-                        float lc = S.bw * neg * fn;
-                        float gc = S.bw * neg * dfn * de_n;
-                        if (pos != 0.f) {
-                            float fp, dfp;
-                            focal_term(e_p, S.gamma, fp, dfp);
-                            lc += pos * fp;
-                            gc += pos * dfp * de_p;
-                            // CIoU box term (loss.py:113-117)
+                float pos = 0.f;
+                if (valid) {
+                    if (V == 1) {
+                        pos = obj * resp;
+                        const float neg = 1.f - pos;
+                        const float dx = tx - px, dy = ty - py;
+                        acc[0] += (double)(pos * (dx * dx + dy * dy));
+                        g0 = -2.f * S.lw[0] * pos * dx * inv_n;
+                        g1 = -2.f * S.lw[0] * pos * dy * inv_n;
+                        const float sw = sqrtf(fmaxf(pw, kEpsF)), sh = sqrtf(fmaxf(ph, kEpsF));
+                        const float dw = sqrtf(fmaxf(tw, kEpsF)) - sw, dh = sqrtf(fmaxf(th, kEpsF)) - sh;
+                        acc[1] += (double)(pos * (dw * dw + dh * dh));
+                        g2 = (pw >= kEpsF) ? -S.lw[1] * pos * dw / sw * inv_n : 0.f;
+                        g3 = (ph >= kEpsF) ? -S.lw[1] * pos * dh / sh * inv_n : 0.f;
+                        if (pos != 0.f) {  // objectness regresses to the IoU, which carries gradient
                             BoxGrad bg;
-                            box_fwd_bwd<true>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
-                            acc[0] += (double)pos * (1.0 - bg.ciou);
-                            const double gb = -(double)S.lw[0] * pos * S.inv_n_d;
-                            g0 += (float)(gb * bg.dciou[0]);
-                            g1 += (float)(gb * bg.dciou[1]);
-                            g2 += (float)(gb * bg.dciou[2]);
-                            g3 += (float)(gb * bg.dciou[3]);
+                            box_fwd_bwd<false>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
+                            const double d = bg.iou - (double)c;
+                            acc[2] += (double)pos * d * d + (double)(S.bw * neg * c * c);
+                            const double gi = 2.0 * S.lw[2] * pos * d * S.inv_n_d;
+                            g0 += (float)(gi * bg.diou[0]);
+                            g1 += (float)(gi * bg.diou[1]);
+                            g2 += (float)(gi * bg.diou[2]);
+                            g3 += (float)(gi * bg.diou[3]);
+                            g4 = (float)(-gi) + 2.f * S.lw[2] * S.bw * neg * c * inv_n;
+                        } else {
+                            acc[2] += (double)(S.bw * neg * c * c);
+                            g4 = 2.f * S.lw[2] * S.bw * neg * c * inv_n;
                         }
-                        acc[1] += (double)lc;
-                        g4 = S.lw[1] * gc * band * inv_n;
-                    } else {  // V == 2 or 3
-                        acc[4] += (double)(lpw * lpw + lph * lph);
-                        g2 = 2.f * S.whw * lpw / pw * inv_n;
-                        g3 = 2.f * S.whw * lph / ph * inv_n;
-                        if (pos != 0.f) {
-                            const float sc = S.use_scale ? (2.f - tw * th) : 1.f;
-                            const float dx = tx - px, dy = ty - py;
-                            acc[0] += (double)(pos * sc * (dx * dx + dy * dy));
-                            g0 = -2.f * S.lw[0] * pos * sc * dx * inv_n;
-                            g1 = -2.f * S.lw[0] * pos * sc * dy * inv_n;
-                            const float dlw = logf(fmaxf(tw / aw, kEpsF)) - lpw;
-                            const float dlh = logf(fmaxf(th / ah, kEpsF)) - lph;
-                            acc[1] += (double)(pos * sc * (dlw * dlw + dlh * dlh));
-                            g2 += -2.f * S.lw[1] * pos * sc * dlw / pw * inv_n;
-                            g3 += -2.f * S.lw[1] * pos * sc * dlh / ph * inv_n;
-                        }
-                        if (V == 3 && S.use_focal) {
+                    } else {
+                        pos = obj * resp;
+                        if (V == 4 && S.truth_thr < 1.f)
+                            pos = pos + ((iou > S.truth_thr) ? 1.f : 0.f) * (1.f - pos);
+                        const float neg = (1.f - pos) * ((iou < S.ignore_thr) ? 1.f : 0.f);
+                        const float lpw = logf(pw / aw), lph = logf(ph / ah);
+                        if (V == 4) {
+                            // wh regulariser, every box (loss.py:156-160)
+                            acc[3] += (double)(lpw * lpw + lph * lph);
+                            g2 = 2.f * S.whw * lpw / pw * inv_n;
+                            g3 = 2.f * S.whw * lph / ph * inv_n;
+                            // focal objectness with label smoothing (loss.py:119-143)
                             const float cc = fminf(fmaxf(c, kEpsF), 1.f - kEpsF);
                             const float band = (c >= kEpsF && c <= 1.f - kEpsF) ? 1.f : 0.f;
+                            float e_p, e_n, de_p, de_n;
+                            if (S.label_smooth > 0.f) {
+                                const float u = 1.f - S.label_smooth - cc, w2 = S.label_smooth - cc;
+                                e_p = fabsf(u);
+                                de_p = (u > 0.f) ? -1.f : ((u < 0.f) ? 1.f : 0.f);
+                                e_n = fabsf(w2);
+                                de_n = (w2 > 0.f) ? -1.f : ((w2 < 0.f) ? 1.f : 0.f);
+                            } else {
+                                e_p = 1.f - cc;
+                                de_p = -1.f;
+                                e_n = cc;
+                                de_n = 1.f;
+                            }
                             float fn, dfn;
-                            focal_term(cc, S.gamma, fn, dfn);
-                            float lc = S.bw * neg * fn, gc = S.bw * neg * dfn;
+                            focal_term(e_n, S.gamma, fn, dfn);
+                            float lcf = S.bw * neg * fn;
+                            float gc = S.bw * neg * dfn * de_n;
                             if (pos != 0.f) {
                                 float fp, dfp;
-                                focal_term(1.f - cc, S.gamma, fp, dfp);
-                                lc += pos * fp;
-                                gc -= pos * dfp;
+                                focal_term(e_p, S.gamma, fp, dfp);
+                                lcf += pos * fp;
+                                gc += pos * dfp * de_p;
+                                // CIoU box term (loss.py:113-117)
+                                BoxGrad bg;
+                                box_fwd_bwd<true>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
+                                acc[0] += (double)pos * (1.0 - bg.ciou);
+                                const double gb = -(double)S.lw[0] * pos * S.inv_n_d;
+                                g0 += (float)(gb * bg.dciou[0]);
+                                g1 += (float)(gb * bg.dciou[1]);
+                                g2 += (float)(gb * bg.dciou[2]);
+                                g3 += (float)(gb * bg.dciou[3]);
                             }
-                            acc[2] += (double)lc;
-                            g4 = S.lw[2] * gc * band * inv_n;
-                        } else {
-                            const float om = 1.f - c;
-                            acc[2] += (double)(pos * om * om + S.bw * neg * c * c);
-                            g4 = S.lw[2] * (-2.f * pos * om + 2.f * S.bw * neg * c) * inv_n;
+                            acc[1] += (double)lcf;
+                            g4 = S.lw[1] * gc * band * inv_n;
+                        } else {  // V == 2 or 3
+                            acc[4] += (double)(lpw * lpw + lph * lph);
+                            g2 = 2.f * S.whw * lpw / pw * inv_n;
+                            g3 = 2.f * S.whw * lph / ph * inv_n;
+                            if (pos != 0.f) {
+                                const float sc = S.use_scale ? (2.f - tw * th) : 1.f;
+                                const float dx = tx - px, dy = ty - py;
+                                acc[0] += (double)(pos * sc * (dx * dx + dy * dy));
+                                g0 = -2.f * S.lw[0] * pos * sc * dx * inv_n;
+                                g1 = -2.f * S.lw[0] * pos * sc * dy * inv_n;
+                                const float dlw = logf(fmaxf(tw / aw, kEpsF)) - lpw;
+                                const float dlh = logf(fmaxf(th / ah, kEpsF)) - lph;
+                                acc[1] += (double)(pos * sc * (dlw * dlw + dlh * dlh));
+                                g2 += -2.f * S.lw[1] * pos * sc * dlw / pw * inv_n;
+                                g3 += -2.f * S.lw[1] * pos * sc * dlh / ph * inv_n;
+                            }
+                            if (V == 3 && S.use_focal) {
+                                const float cc = fminf(fmaxf(c, kEpsF), 1.f - kEpsF);
+                                const float band = (c >= kEpsF && c <= 1.f - kEpsF) ? 1.f : 0.f;
+                                float fn, dfn;
+                                focal_term(cc, S.gamma, fn, dfn);
+                                float lcf = S.bw * neg * fn, gc = S.bw * neg * dfn;
+                                if (pos != 0.f) {
+                                    float fp, dfp;
+                                    focal_term(1.f - cc, S.gamma, fp, dfp);
+                                    lcf += pos * fp;
+                                    gc -= pos * dfp;
+                                }
+                                acc[2] += (double)lcf;
+                                g4 = S.lw[2] * gc * band * inv_n;
+                            } else {
+                                const float om = 1.f - c;
+                                acc[2] += (double)(pos * om * om + S.bw * neg * c * c);
+                                g4 = S.lw[2] * (-2.f * pos * om + 2.f * S.bw * neg * c) * inv_n;
+                            }
+                        }
+                    }
+                    if (write) {
+                        pc[0] = g0; pc[1] = g1; pc[2] = g2; pc[3] = g3; pc[4] = g4;
+                        // class scores of a non-responsible box get exactly zero gradient;
+                        // lanes are 85 (odd) floats apart -> bank-conflict-free stores
+                        if (V != 1 && pos == 0.f) {
+                            float* q = pc + 5;
+                            for (int k = 0; k < C; ++k) q[k] = 0.f;
+                        }
+                        if (V == 1 && lb == 0 && obj == 0.f) {
+                            float* q = sp + cell * S.pcf + 5 * B;
+                            for (int k = 0; k < C; ++k) q[k] = 0.f;
                         }
                     }
                 }
-                s_pos[j] = pos;
-                if (write) {
-                    pc[0] = g0;
-                    pc[1] = g1;
-                    pc[2] = g2;
-                    pc[3] = g3;
-                    pc[4] = g4;
-                }
-            }
-            bar_sync(1, kLossConsumers);
-
-            // ---- B: class term.  v2-v4: one row per (cell, box); v1: one row per cell.
-            const int n_rows = (V == 1) ? nc : nb;
-            for (int r = warp; r < n_rows; r += kLossConsumerWarps) {
-                float* q;
-                const float* t;
-                float m;
-                if (V == 1) {
-                    q = sp + r * S.pcf + 5 * B;
-                    t = st + r * S.tcf + 5;
-                    m = st[r * S.tcf + 4];
-                } else {
-                    const int cell = r / B, b = r - cell * B;
-                    q = sp + cell * S.pcf + b * bstride + 5;
-                    t = st + cell * S.tcf + 5;
-                    m = s_pos[r];
-                }
-                if (m == 0.f) {
-                    if (write)
-                        for (int k = lane; k < C; k += 32) q[k] = 0.f;
-                } else {
-                    const double lwc = (double)S.lw[(V == 4) ? 2 : 3] * (double)m * S.inv_n_d;
+                // class term of the (rare) responsible boxes: the whole warp takes one row at a time
+                const float rowm = (V == 1) ? ((lb == 0) ? obj : 0.f) : pos;
+                unsigned pm = __ballot_sync(0xffffffffu, valid && rowm != 0.f);
+                while (pm) {
+                    const int src = __ffs(pm) - 1;
+                    pm &= pm - 1;
+                    const int rc = __shfl_sync(0xffffffffu, cell, src);
+                    const int rb = __shfl_sync(0xffffffffu, lb, src);
+                    const float m = __shfl_sync(0xffffffffu, rowm, src);
+                    float* q = (V == 1) ? sp + rc * S.pcf + 5 * B : sp + rc * S.pcf + rb * bstride + 5;
+                    const float* t = st + rc * S.tcf + 5;
                     double part = 0.0;
-                    for (int k = lane; k < C; k += 32) {
-                        const double p = (double)q[k], tk = (double)t[k];
-                        const double pc = fmin(fmax(p, kEps), 1.0 - kEps);
-                        const double band = (p >= kEps && p <= 1.0 - kEps) ? 1.0 : 0.0;
-                        double l, g;
-                        if (V == 1 || V == 2) {
-                            l = tk * log(pc);
-                            g = -tk / pc;
-                        } else {
-                            l = tk * log(pc) + (1.0 - tk) * log(1.0 - pc);
-                            g = -(tk / pc - (1.0 - tk) / (1.0 - pc));
-                        }
-                        part -= (double)m * l;
-                        if (write) q[k] = (float)(lwc * g * band);
-                    }
-                    acc[3 - (V == 4)] += part;  // v4: term 2, others: term 3
+                    class_row<V>(q, t, m, C, lane, write, (double)S.lw[(V == 4) ? 2 : 3] * S.inv_n_d, part);
+                    acc[(V == 4) ? 2 : 3] += part;
                 }
             }
             fence_proxy_async();
             mbar_arrive(&done[stage]);
         }
-        flush(cur);
+        if (cur >= 0) flush(cur);
     }
 
     // ---- CTA partials -> global, last CTA reduces in a fixed order ------------
@@ -513,7 +517,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
     if (tid < n_vals) {
         const int s = tid / kTerms, k = tid - s * kTerms;
         double v = 0.0;
-        for (int w = 0; w < kLossConsumerWarps; ++w) v += s_acc[(w * YB_MAX_SCALES + s) * kTerms + k];
+        for (int w = 0; w < ncw; ++w) v += s_acc[(w * YB_MAX_SCALES + s) * kTerms + k];
         L.partials[(size_t)blockIdx.x * n_vals + tid] = v;
     }
     __threadfence();
@@ -523,7 +527,8 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
     if (!s_is_last) return;
     __threadfence();
     double* s_fin = s_acc;  // reuse: [n_vals]
-    for (int i = warp; i < n_vals; i += kLossThreads / 32) {
+    __syncthreads();
+    for (int i = warp; i < n_vals; i += (int)(blockDim.x >> 5)) {
         double v = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&L.partials[(size_t)b * n_vals + i]);
         v = warp_sum(v);
@@ -623,10 +628,10 @@ static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
 }
 
 template <int V>
-static int launch_loss(const LossLaunch& L, int grid, size_t smem, cudaStream_t stream) {
+static int launch_loss(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
     YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    loss_fwd_bwd_kernel<V><<<grid, kLossThreads, smem, stream>>>(L);
+    loss_fwd_bwd_kernel<V><<<grid, threads, smem, stream>>>(L);
     return (int)cudaGetLastError();
 }
 
@@ -661,17 +666,20 @@ extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float*
         cell_bytes_max = max(cell_bytes_max, (L.sc[s].pcf + L.sc[s].tcf) * 4);
     }
 
-    // Ring geometry: prefer 3 stages of ~22 KB (3 CTAs/SM); shrink for fat cells.
-    int n_stages = env_int("YB_LOSS_STAGES", 3);
+    // Ring geometry: by default 2 stages of ~27 KB and 4 CTAs per SM (for v3/v4 cells: 20 cells per
+    // tile = two consumer warps of 10 cells); fat cells get fewer CTAs per SM.
+    int n_stages = env_int("YB_LOSS_STAGES", 2);
     n_stages = max(2, min(kMaxStages, n_stages));
-    int ctas_per_sm = env_int("YB_LOSS_CTAS_PER_SM", 3);
+    int ctas_per_sm = max(1, min(8, env_int("YB_LOSS_CTAS_PER_SM", 4)));
     const int tile_env = env_int("YB_LOSS_TILE_CELLS", 0);
     const size_t smem_cap = 227 * 1024;
+    const size_t fixed_smem = sizeof(double) * kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms +
+                              2 * kMaxStages * sizeof(uint64_t) + 1024 /* per-CTA reservation */ + 256;
     int stage_budget = 0;
     for (;;) {
-        const size_t per_cta = smem_cap / ctas_per_sm - 2048;
-        stage_budget = (int)(per_cta / n_stages);
-        if (stage_budget >= 4 * cell_bytes_max + 64) break;
+        const size_t per_cta = smem_cap / ctas_per_sm - fixed_smem;
+        stage_budget = (int)(per_cta / n_stages) / 128 * 128;
+        if (stage_budget >= 4 * cell_bytes_max) break;
         if (ctas_per_sm > 1) {
             --ctas_per_sm;
         } else if (n_stages > 2) {
@@ -680,39 +688,42 @@ extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float*
             return YB_E_SHAPE;  // 4 cells do not fit a stage: B*(5+C) too large
         }
     }
-    int total_tiles = 0, stage_bytes = 0, max_rows = 0;
+    int total_tiles = 0, stage_bytes = 0, ncw = 1;
     for (int s = 0; s < n_scales; ++s) {
         LossScaleDev& d = L.sc[s];
         const int cb = (d.pcf + d.tcf) * 4;
-        int t = (stage_budget - 64) / cb / 4 * 4;
-        if (tile_env > 0) t = min(t, max(4, tile_env / 4 * 4));
-        t = max(4, min(t, 64));
+        const int cpw = 32 / d.B;                       // cells one consumer warp covers per pass
+        int t = stage_budget / cb / 4 * 4;
+        t = min(t, kLossMaxConsumerWarps * cpw / 4 * 4);  // one pass of the consumer warps
+        if (tile_env > 0) t = min(t, tile_env / 4 * 4);
+        t = max(4, t);
         d.tile_cells = t;
         d.n_tiles = (int)((d.n_cells + t - 1) / t);
         d.tile_base = total_tiles;
         total_tiles += d.n_tiles;
         stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
-        max_rows = max(max_rows, t * d.B);
+        ncw = max(ncw, min(kLossMaxConsumerWarps, (t + cpw - 1) / cpw));
     }
+    ncw = max(1, min(kLossMaxConsumerWarps, env_int("YB_LOSS_WARPS", ncw)));
     L.total_tiles = total_tiles;
     L.stage_bytes = stage_bytes;
-    L.max_rows = max_rows;
     L.n_stages = n_stages;
     L.partials = reinterpret_cast<double*>(workspace);
     L.counter = reinterpret_cast<unsigned int*>((char*)workspace + loss_partials_bytes(n_scales));
     L.loss_out = loss_out;
     L.terms_out = terms_out;
 
-    const size_t smem = align_up((size_t)n_stages * stage_bytes + 2 * sizeof(float) * max_rows, 16) +
-                        sizeof(double) * kLossConsumerWarps * YB_MAX_SCALES * kTerms +
+    const size_t smem = (size_t)n_stages * stage_bytes +
+                        sizeof(double) * kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms +
                         2 * kMaxStages * sizeof(uint64_t);
-    int grid = min(max(total_tiles, 1), kNumSMs * min(ctas_per_sm, 8));
+    const int threads = (ncw + 1) * 32;
+    int grid = min(max(total_tiles, 1), kNumSMs * ctas_per_sm);
     YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
     switch (version) {
-        case 1: return launch_loss<1>(L, grid, smem, stream);
-        case 2: return launch_loss<2>(L, grid, smem, stream);
-        case 3: return launch_loss<3>(L, grid, smem, stream);
-        default: return launch_loss<4>(L, grid, smem, stream);
+        case 1: return launch_loss<1>(L, grid, threads, smem, stream);
+        case 2: return launch_loss<2>(L, grid, threads, smem, stream);
+        case 3: return launch_loss<3>(L, grid, threads, smem, stream);
+        default: return launch_loss<4>(L, grid, threads, smem, stream);
     }
 }
 

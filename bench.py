@@ -36,9 +36,9 @@ UNIT = "images/s"
 CONFIG_NAME = "v4-608"
 CONF_THR, NMS_THR, NMS_MODE = 0.5, 0.45, 2
 ROW_CAPACITY_PER_IMG = 4096
-# my kernels per step: loss 1 | decode: count, 3 scan, emit | nms: classify, 3 scan,
-# scatter, small, big, 3 scan, emit
-LAUNCHES_PER_STEP = 1 + 5 + 12
+# my kernels per step: loss 1 | decode: count, 3-kernel scan, emit | nms: classify, scan,
+# scatter, small, big, scan, emit
+LAUNCHES_PER_STEP = 1 + 5 + 7
 
 
 def loss_algorithmic_bytes(cfg, batch):

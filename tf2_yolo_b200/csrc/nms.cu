@@ -138,14 +138,17 @@ nms_small_kernel(const double* __restrict__ rows, double thr, NmsWs W, unsigned 
         const long long start = W.seg_start[seg];
         const unsigned valid = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
 
-        // restore original order: sort the (atomically scattered) row ids
+        // restore original order: rank the (atomically scattered) row ids, permute by shuffle
         int m = (lane < n) ? W.members[start + lane] : INT_MAX;
-        int rk = 0;
-        for (int j = 0; j < n; ++j) rk += (__shfl_sync(0xffffffffu, m, j) < m) ? 1 : 0;
-        __syncwarp();
-        if (lane < n) W.members[start + rk] = m;
-        __syncwarp();
-        m = (lane < n) ? W.members[start + lane] : INT_MAX;
+        {
+            int rk = 0;
+            for (int j = 0; j < n; ++j) rk += (__shfl_sync(0xffffffffu, m, j) < m) ? 1 : 0;
+            int src = lane;
+            for (int j = 0; j < n; ++j)
+                if (__shfl_sync(0xffffffffu, rk, j) == lane) src = j;
+            m = __shfl_sync(0xffffffffu, m, src);
+            if (lane < n) W.members[start + lane] = m;
+        }
 
         double x = 0, y = 0, bw = 0, bh = 0, conf = 0;
         if (lane < n) {

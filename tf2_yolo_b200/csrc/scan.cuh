@@ -96,6 +96,36 @@ static __global__ void scan_apply(const unsigned int* __restrict__ in, long long
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[gridDim.x];
 }
 
+// small inputs (segment tables): the whole scan in one block, one launch
+static __global__ void scan_single_block(const unsigned int* __restrict__ in, long long n,
+                                         long long* __restrict__ out) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (long long base = 0; base < n; base += (long long)blockDim.x * kScanItems) {
+        const long long i0 = base + (long long)threadIdx.x * kScanItems;
+        unsigned int item[kScanItems];
+        long long v = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            item[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+            v += item[k];
+        }
+        long long total;
+        long long ex = block_exclusive_scan(v, s_warp, total) + s_carry;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < n) out[i0 + k] = ex;
+            ex += item[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
 static inline size_t scan_workspace_bytes(long long n) {
     const long long n_blocks = (n + kScanTile - 1) / kScanTile;
     return align_up((size_t)(n_blocks + 2) * sizeof(long long), 256);
@@ -104,6 +134,10 @@ static inline size_t scan_workspace_bytes(long long n) {
 // out has n+1 entries; out[n] = total.  n >= 1.
 static inline int exclusive_scan_u32(const unsigned int* in, long long n, long long* out,
                                      void* workspace, cudaStream_t stream) {
+    if (n <= 64 * 1024) {
+        scan_single_block<<<1, 1024, 0, stream>>>(in, n, out);
+        return (int)cudaGetLastError();
+    }
     const int n_blocks = (int)((n + kScanTile - 1) / kScanTile);
     long long* block_sums = reinterpret_cast<long long*>(workspace);
     scan_block_sums<<<n_blocks, kScanThreads, 0, stream>>>(in, n, block_sums);

@@ -203,6 +203,39 @@ int yb_map_match(const double* gt_rows, const int64_t* gt_offsets, const double*
                  int64_t det_capacity, double* best_iou, int32_t* best_gt,
                  int32_t* gt_class_counts, yb_stream_t stream);
 
+/* PR accumulation for one batch of images: utils/measurement.py:252-292 (PRfunc) and
+ * :104-130 (create_score_mat).  det_rows are NMS survivors grouped by (image, class) with
+ * det_seg_offsets (n_img*class_num+1, from yb_nms); best_iou / best_gt / gt_class_counts come
+ * from yb_map_match.  gt_base[c] = ground truths of class c in earlier batches (the running
+ * num_gts of measurement.py:256).  Outputs, grouped by class then image (capacity = number of
+ * det rows): conf = c*p, gt_id = best_gt + running count, flag = best_iou >= iou_threshold,
+ * cls; class_offsets has class_num+1 entries.  max_per_img > 0 keeps the top max_per_img
+ * detections per (image, class) in descending-confidence order (:285-289).  score_acc
+ * (3*class_num uint64, ADDED to): detections, flagged detections, distinct matched ground
+ * truths per class (PP, TPP, TP of create_score_mat). */
+size_t yb_map_accumulate_workspace_bytes(int64_t n_img, int class_num);
+
+int yb_map_accumulate(const double* det_rows, const int64_t* det_seg_offsets, const double* best_iou,
+                      const int32_t* best_gt, const int32_t* gt_class_counts, int64_t n_img,
+                      int class_num, double iou_threshold, int64_t max_per_img,
+                      const int64_t* gt_base, double* conf, int64_t* gt_id, uint8_t* flag,
+                      int32_t* cls, int64_t* class_offsets, uint64_t* score_acc, void* workspace,
+                      size_t workspace_bytes, yb_stream_t stream);
+
+/* Final PR pass, utils/measurement.py:297-321: sort all triples by (class asc, confidence
+ * desc, later position first), find the first occurrence of every matched ground truth and
+ * return running counts.  order[i] = input index of the i-th sorted record; tp_cum / tpp_cum
+ * (n_det+1 entries) = exclusive running counts of first-occurrence true positives / flagged
+ * detections over the whole sorted array (subtract the value at a class start to get the
+ * reference's per-prefix num_tp / num_tpp).  gt_table_base (class_num+1) = exclusive prefix of
+ * the total ground-truth count per class; n_gt_total its last entry. */
+size_t yb_pr_curve_workspace_bytes(int64_t n_det, int64_t n_gt_total);
+
+int yb_pr_curve(const double* conf, const int32_t* cls, const int64_t* gt_id, const uint8_t* flag,
+                int64_t n_det, const int64_t* gt_table_base, int64_t n_gt_total, int64_t* order,
+                int64_t* tp_cum, int64_t* tpp_cum, void* workspace, size_t workspace_bytes,
+                yb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 // (utils/measurement.py:252-283 PRfunc, :104-130 create_score_mat), float64 in the
 // reference's operation order (utils/tools.py:649-666; -fmad=false).
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace yb {
 
@@ -99,4 +100,335 @@ extern "C" int yb_map_match(const double* gt_rows, const int64_t* gt_offsets, co
         YB_CUDA_TRY(cudaGetLastError());
     }
     return YB_OK;
+}
+
+// ============================================================================
+// PR accumulation: detections -> (conf, gt_id, tp flag) triples grouped by class
+// (utils/measurement.py:252-292), per-class score-matrix counters (:104-130), and the
+// final per-class confidence sort + distinct-TP prefix (:297-321).
+// ============================================================================
+namespace yb {
+
+// ---- A: per (image, class) segment sizes, transposed to class-major ----------
+__global__ void map_segment_sizes_kernel(const long long* __restrict__ seg_off, const int* __restrict__ gt_counts,
+                                         long long n_img, int C, long long max_per_img,
+                                         unsigned int* __restrict__ kept_T, unsigned int* __restrict__ gt_T) {
+    const long long n_seg = n_img * C;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_seg;
+         s += (long long)gridDim.x * blockDim.x) {
+        const long long img = s / C;
+        const int c = (int)(s - img * C);
+        long long n = seg_off[s + 1] - seg_off[s];
+        if (max_per_img > 0 && n > max_per_img) n = max_per_img;
+        kept_T[(long long)c * n_img + img] = (unsigned)n;
+        gt_T[(long long)c * n_img + img] = (unsigned)gt_counts[s];
+    }
+}
+
+// ---- B: one warp per segment: triples, per-image top-k, score counters ----------
+__global__ void __launch_bounds__(256)
+map_triples_kernel(const double* __restrict__ det, const long long* __restrict__ seg_off,
+                   const double* __restrict__ best_iou, const int* __restrict__ best_gt,
+                   const int* __restrict__ gt_counts, long long n_img, int C, double iou_thr,
+                   long long max_per_img, const long long* __restrict__ gt_base,
+                   const long long* __restrict__ out_pos_T, const long long* __restrict__ gt_pos_T,
+                   double* __restrict__ conf_out, long long* __restrict__ gtid_out,
+                   unsigned char* __restrict__ flag_out, int* __restrict__ cls_out,
+                   long long* __restrict__ class_offsets, unsigned long long* __restrict__ acc /* [3][C] pp,tpp,tp */) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n_seg = n_img * C;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c <= C; c += (long long)gridDim.x * blockDim.x)
+        class_offsets[c] = out_pos_T[c * n_img];  // c == C -> total
+    for (long long s = warp; s < n_seg; s += n_warps) {
+        const long long img = s / C;
+        const int c = (int)(s - img * C);
+        const long long d0 = seg_off[s];
+        const int n = (int)(seg_off[s + 1] - d0);
+        if (n == 0) continue;
+        const int n_gt = gt_counts[s];
+        const long long tpos = (long long)c * n_img + img;
+        const long long out0 = out_pos_T[tpos];
+        // running ground-truth count of this class before this image (measurement.py:256-258)
+        const long long gbase = gt_base[c] + (gt_pos_T[tpos] - gt_pos_T[(long long)c * n_img]);
+        const bool trunc = max_per_img > 0 && n > max_per_img;
+        int tpp = 0, tp = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int j = j0 + lane;
+            double cf = 0.0;
+            long long gid = 0;
+            bool fl = false;
+            if (j < n) {
+                const double* r = det + (d0 + j) * 7;
+                cf = __dmul_rn(r[4], r[6]);
+                if (n_gt > 0) {
+                    fl = best_iou[d0 + j] >= iou_thr;
+                    gid = (long long)best_gt[d0 + j] + gbase;
+                }
+            }
+            // score-matrix counters: flagged detections and distinct matched ground truths
+            bool first = fl;
+            if (fl) {
+                const int g = best_gt[d0 + j];
+                for (int i = 0; i < j; ++i)
+                    if (best_iou[d0 + i] >= iou_thr && best_gt[d0 + i] == g) { first = false; break; }
+            }
+            tpp += __popc(__ballot_sync(0xffffffffu, fl));
+            tp += __popc(__ballot_sync(0xffffffffu, first));
+            if (j < n) {
+                long long dst;
+                if (!trunc) {
+                    dst = out0 + j;
+                } else {  // top max_per_img by confidence, in sorted order, ties: higher index first
+                    int rank = 0;
+                    for (int i = 0; i < n; ++i) {
+                        const double* q = det + (d0 + i) * 7;
+                        const double ci = __dmul_rn(q[4], q[6]);
+                        rank += (ci > cf || (ci == cf && i > j)) ? 1 : 0;
+                    }
+                    dst = (rank < max_per_img) ? out0 + rank : -1;
+                }
+                if (dst >= 0) {
+                    conf_out[dst] = cf;
+                    gtid_out[dst] = gid;
+                    flag_out[dst] = fl ? 1 : 0;
+                    cls_out[dst] = c;
+                }
+            }
+        }
+        if (lane == 0) {
+            atomicAdd(&acc[c], (unsigned long long)n);
+            if (n_gt > 0) {
+                atomicAdd(&acc[C + c], (unsigned long long)tpp);
+                atomicAdd(&acc[2 * C + c], (unsigned long long)tp);
+            }
+        }
+    }
+}
+
+// ---- C: sort records (class asc, confidence desc, position desc) -----------------------
+// record = two u64 compared lexicographically: A = class<<32 | hi32(~key), B = lo32(~key)<<32 | ~pos
+__device__ __forceinline__ unsigned long long orderable(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // ascending with value
+}
+__device__ __forceinline__ bool rec_less(const ulonglong2& a, const ulonglong2& b) {
+    return a.x < b.x || (a.x == b.x && a.y < b.y);
+}
+
+__global__ void pr_pack_kernel(const double* __restrict__ conf, const int* __restrict__ cls, long long n,
+                               long long P, ulonglong2* __restrict__ rec) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < P;
+         i += (long long)gridDim.x * blockDim.x) {
+        ulonglong2 r;
+        if (i < n) {
+            const unsigned long long k = ~orderable(conf[i]);  // ascending k == descending confidence
+            r.x = ((unsigned long long)(unsigned)cls[i] << 32) | (k >> 32);
+            r.y = (k << 32) | (unsigned long long)(~(unsigned)i);
+        } else {
+            r.x = ~0ull;  // padding sorts last
+            r.y = ~0ull;
+        }
+        rec[i] = r;
+    }
+}
+
+constexpr int kSortTile = 2048;  // records per CTA in the shared-memory stages (32 KB)
+
+// all (k, j) stages with j < kSortTile for k <= k_hi, starting from stage (k_lo, j_lo)
+__global__ void __launch_bounds__(512)
+bitonic_smem_kernel(ulonglong2* __restrict__ rec, long long k_lo, long long k_hi, long long j_start) {
+    __shared__ ulonglong2 s[kSortTile];
+    const long long base = (long long)blockIdx.x * kSortTile;
+    for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) s[t] = rec[base + t];
+    __syncthreads();
+    for (long long k = k_lo; k <= k_hi; k <<= 1) {
+        long long j = (k == k_lo) ? j_start : (k >> 1);
+        if (j >= kSortTile) j = kSortTile >> 1;
+        for (; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) {
+                const int u = t ^ (int)j;
+                if (u > t) {
+                    const bool up = ((base + t) & k) == 0;
+                    const ulonglong2 a = s[t], b = s[u];
+                    if (up ? rec_less(b, a) : rec_less(a, b)) {
+                        s[t] = b;
+                        s[u] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int t = threadIdx.x; t < kSortTile; t += blockDim.x) rec[base + t] = s[t];
+}
+
+__global__ void bitonic_global_kernel(ulonglong2* __restrict__ rec, long long P, long long k, long long j) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < P;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long u = t ^ j;
+        if (u > t) {
+            const bool up = (t & k) == 0;
+            const ulonglong2 a = rec[t], b = rec[u];
+            if (up ? rec_less(b, a) : rec_less(a, b)) {
+                rec[t] = b;
+                rec[u] = a;
+            }
+        }
+    }
+}
+
+// ---- D: first occurrence of every matched ground truth in sorted order ----------------
+__global__ void pr_first_pos_kernel(const ulonglong2* __restrict__ rec, long long n,
+                                    const long long* __restrict__ gtid, const unsigned char* __restrict__ flag,
+                                    const long long* __restrict__ gt_table_base,
+                                    unsigned long long* __restrict__ first_pos, long long* __restrict__ order) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const ulonglong2 r = rec[i];
+        const long long src = (long long)(unsigned)(~(unsigned)(r.y & 0xffffffffull));
+        order[i] = src;
+        if (flag[src]) {
+            const int c = (int)(r.x >> 32);
+            atomicMin(&first_pos[gt_table_base[c] + gtid[src]], (unsigned long long)i);
+        }
+    }
+}
+
+__global__ void pr_flags_kernel(const ulonglong2* __restrict__ rec, long long n, const long long* __restrict__ order,
+                                const long long* __restrict__ gtid, const unsigned char* __restrict__ flag,
+                                const long long* __restrict__ gt_table_base,
+                                const unsigned long long* __restrict__ first_pos,
+                                unsigned int* __restrict__ is_first, unsigned int* __restrict__ is_flag) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long src = order[i];
+        const bool fl = flag[src] != 0;
+        const int c = (int)(rec[i].x >> 32);
+        is_flag[i] = fl ? 1u : 0u;
+        is_first[i] = (fl && first_pos[gt_table_base[c] + gtid[src]] == (unsigned long long)i) ? 1u : 0u;
+    }
+}
+
+static long long next_pow2(long long n) {
+    long long p = kSortTile;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+}  // namespace yb
+
+extern "C" size_t yb_map_accumulate_workspace_bytes(int64_t n_img, int class_num) {
+    if (n_img < 0 || class_num <= 0) return 0;
+    const long long n = (long long)n_img * class_num;
+    return 4 * align_up((size_t)(n + 2) * sizeof(long long), 256) + scan_workspace_bytes(n + 1) + 1024;
+}
+
+extern "C" int yb_map_accumulate(const double* det_rows, const int64_t* det_seg_offsets, const double* best_iou,
+                                 const int32_t* best_gt, const int32_t* gt_class_counts, int64_t n_img,
+                                 int class_num, double iou_threshold, int64_t max_per_img,
+                                 const int64_t* gt_base, double* conf, int64_t* gt_id, uint8_t* flag,
+                                 int32_t* cls, int64_t* class_offsets, uint64_t* score_acc, void* workspace,
+                                 size_t workspace_bytes, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (det_seg_offsets == nullptr || gt_class_counts == nullptr || gt_base == nullptr ||
+        class_offsets == nullptr || score_acc == nullptr || workspace == nullptr)
+        return YB_E_NULL;
+    if (n_img <= 0 || class_num <= 0) return YB_E_SHAPE;
+    if (workspace_bytes < yb_map_accumulate_workspace_bytes(n_img, class_num) || ((uintptr_t)workspace & 255))
+        return YB_E_WORKSPACE;
+    const long long n = (long long)n_img * class_num;
+    const size_t slab = align_up((size_t)(n + 2) * sizeof(long long), 256);
+    char* w = reinterpret_cast<char*>(workspace);
+    unsigned int* kept_T = reinterpret_cast<unsigned int*>(w);
+    unsigned int* gt_T = reinterpret_cast<unsigned int*>(w + slab);
+    long long* out_pos_T = reinterpret_cast<long long*>(w + 2 * slab);
+    long long* gt_pos_T = reinterpret_cast<long long*>(w + 3 * slab);
+    void* scan_ws = w + 4 * slab;
+    const int threads = 256;
+    const int blocks = (int)min((long long)kNumSMs * 8, (n + threads - 1) / threads);
+    map_segment_sizes_kernel<<<blocks, threads, 0, stream>>>(
+        reinterpret_cast<const long long*>(det_seg_offsets), gt_class_counts, n_img, class_num, max_per_img, kept_T, gt_T);
+    YB_CUDA_TRY(cudaGetLastError());
+    int rc = exclusive_scan_u32(kept_T, n, out_pos_T, scan_ws, stream);
+    if (rc != 0) return rc;
+    rc = exclusive_scan_u32(gt_T, n, gt_pos_T, scan_ws, stream);
+    if (rc != 0) return rc;
+    const int wblocks = (int)min((long long)kNumSMs * 8, (n * 32 + threads - 1) / threads);
+    map_triples_kernel<<<wblocks, threads, 0, stream>>>(
+        det_rows, reinterpret_cast<const long long*>(det_seg_offsets), best_iou, best_gt, gt_class_counts, n_img,
+        class_num, iou_threshold, max_per_img, reinterpret_cast<const long long*>(gt_base), out_pos_T, gt_pos_T,
+        conf, reinterpret_cast<long long*>(gt_id), flag, cls, reinterpret_cast<long long*>(class_offsets),
+        reinterpret_cast<unsigned long long*>(score_acc));
+    return (int)cudaGetLastError();
+}
+
+extern "C" size_t yb_pr_curve_workspace_bytes(int64_t n_det, int64_t n_gt_total) {
+    if (n_det < 0 || n_gt_total < 0) return 0;
+    const long long P = next_pow2(n_det > 0 ? n_det : 1);
+    return align_up((size_t)P * sizeof(ulonglong2), 256) + align_up((size_t)(n_gt_total + 1) * 8, 256) +
+           2 * align_up((size_t)(n_det + 1) * 4, 256) + scan_workspace_bytes(n_det + 1) + 1024;
+}
+
+// order[i] = index (into conf/gt_id/flag/cls) of the i-th record after sorting by
+// (class asc, confidence desc, position desc); tp_cum / tpp_cum have n_det+1 entries:
+// exclusive running counts of first-occurrence true positives / flagged detections over the
+// WHOLE sorted array (the caller subtracts the value at each class start).
+extern "C" int yb_pr_curve(const double* conf, const int32_t* cls, const int64_t* gt_id, const uint8_t* flag,
+                           int64_t n_det, const int64_t* gt_table_base, int64_t n_gt_total, int64_t* order,
+                           int64_t* tp_cum, int64_t* tpp_cum, void* workspace, size_t workspace_bytes,
+                           yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_det < 0 || n_gt_total < 0) return YB_E_SHAPE;
+    if (tp_cum == nullptr || tpp_cum == nullptr || workspace == nullptr) return YB_E_NULL;
+    if (n_det == 0) {
+        YB_CUDA_TRY(cudaMemsetAsync(tp_cum, 0, 8, stream));
+        YB_CUDA_TRY(cudaMemsetAsync(tpp_cum, 0, 8, stream));
+        return YB_OK;
+    }
+    if (conf == nullptr || cls == nullptr || gt_id == nullptr || flag == nullptr || gt_table_base == nullptr ||
+        order == nullptr)
+        return YB_E_NULL;
+    if (n_det > 0xfffffff0ll) return YB_E_SHAPE;
+    if (workspace_bytes < yb_pr_curve_workspace_bytes(n_det, n_gt_total) || ((uintptr_t)workspace & 255))
+        return YB_E_WORKSPACE;
+    const long long P = next_pow2(n_det);
+    char* w = reinterpret_cast<char*>(workspace);
+    ulonglong2* rec = reinterpret_cast<ulonglong2*>(w);
+    w += align_up((size_t)P * sizeof(ulonglong2), 256);
+    unsigned long long* first_pos = reinterpret_cast<unsigned long long*>(w);
+    w += align_up((size_t)(n_gt_total + 1) * 8, 256);
+    unsigned int* is_first = reinterpret_cast<unsigned int*>(w);
+    w += align_up((size_t)(n_det + 1) * 4, 256);
+    unsigned int* is_flag = reinterpret_cast<unsigned int*>(w);
+    w += align_up((size_t)(n_det + 1) * 4, 256);
+    void* scan_ws = w;
+
+    const int threads = 256;
+    const int gblocks = (int)min((long long)kNumSMs * 8, (P + threads - 1) / threads);
+    pr_pack_kernel<<<gblocks, threads, 0, stream>>>(conf, cls, n_det, P, rec);
+    YB_CUDA_TRY(cudaGetLastError());
+    const int tiles = (int)(P / kSortTile);
+    bitonic_smem_kernel<<<tiles, 512, 0, stream>>>(rec, 2, kSortTile, 1);  // sorts every tile
+    YB_CUDA_TRY(cudaGetLastError());
+    for (long long k = 2 * kSortTile; k <= P; k <<= 1) {
+        for (long long j = k >> 1; j >= kSortTile; j >>= 1)
+            bitonic_global_kernel<<<gblocks, threads, 0, stream>>>(rec, P, k, j);
+        bitonic_smem_kernel<<<tiles, 512, 0, stream>>>(rec, k, k, kSortTile >> 1);
+        YB_CUDA_TRY(cudaGetLastError());
+    }
+    YB_CUDA_TRY(cudaMemsetAsync(first_pos, 0xff, (size_t)(n_gt_total + 1) * 8, stream));
+    const int dblocks = (int)min((long long)kNumSMs * 8, ((long long)n_det + threads - 1) / threads);
+    pr_first_pos_kernel<<<dblocks, threads, 0, stream>>>(rec, n_det, reinterpret_cast<const long long*>(gt_id), flag,
+                                                         reinterpret_cast<const long long*>(gt_table_base), first_pos,
+                                                         reinterpret_cast<long long*>(order));
+    pr_flags_kernel<<<dblocks, threads, 0, stream>>>(rec, n_det, reinterpret_cast<const long long*>(order),
+                                                     reinterpret_cast<const long long*>(gt_id), flag,
+                                                     reinterpret_cast<const long long*>(gt_table_base), first_pos,
+                                                     is_first, is_flag);
+    YB_CUDA_TRY(cudaGetLastError());
+    int rc = exclusive_scan_u32(is_first, n_det, reinterpret_cast<long long*>(tp_cum), scan_ws, stream);
+    if (rc != 0) return rc;
+    return exclusive_scan_u32(is_flag, n_det, reinterpret_cast<long long*>(tpp_cum), scan_ws, stream);
 }

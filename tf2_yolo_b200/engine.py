@@ -322,3 +322,46 @@ def map_match(gt_rows, gt_offsets, det_rows, det_offsets, class_num):
                                    class_num, gt_rows.shape[0], det_rows.shape[0], _ptr(best_iou),
                                    _ptr(best_gt), _ptr(counts), _stream()), "yb_map_match")
     return best_iou[:det_rows.shape[0]], best_gt[:det_rows.shape[0]], counts
+
+
+def map_accumulate(det_rows, seg_offsets, best_iou, best_gt, gt_counts, class_num, iou_threshold,
+                   max_per_img, gt_base, score_acc):
+    """Triples of one image batch grouped by class (see yb_map_accumulate).  Returns
+    (conf f64[D], gt_id i64[D], flag u8[D], cls i32[D], class_offsets i64[C+1]); entries past
+    class_offsets[-1] are unspecified.  ``score_acc`` (3*C int64 CUDA) is added to."""
+    require_cuda(det_rows, seg_offsets, best_iou, best_gt, gt_counts, gt_base, score_acc)
+    dev = seg_offsets.device
+    n_img = gt_counts.shape[0]
+    D = max(det_rows.shape[0], 1)
+    with torch.cuda.device(dev):
+        conf = torch.empty(D, dtype=_F64, device=dev)
+        gid = torch.empty(D, dtype=_I64, device=dev)
+        flag = torch.empty(D, dtype=torch.uint8, device=dev)
+        cls = torch.empty(D, dtype=torch.int32, device=dev)
+        coff = torch.empty(class_num + 1, dtype=_I64, device=dev)
+        ws_bytes = N.lib.yb_map_accumulate_workspace_bytes(n_img, class_num)
+        ws = workspaces.get("map_acc", ws_bytes, dev)
+        N.check(N.lib.yb_map_accumulate(_ptr(det_rows), _ptr(seg_offsets), _ptr(best_iou), _ptr(best_gt),
+                                        _ptr(gt_counts), n_img, class_num, float(iou_threshold),
+                                        int(max_per_img) if max_per_img else 0, _ptr(gt_base), _ptr(conf),
+                                        _ptr(gid), _ptr(flag), _ptr(cls), _ptr(coff), _ptr(score_acc), _ptr(ws),
+                                        ws_bytes, _stream()), "yb_map_accumulate")
+    return conf, gid, flag, cls, coff
+
+
+def pr_curve(conf, cls, gt_id, flag, gt_table_base, n_gt_total):
+    """Sort by (class, confidence desc, later position first) and count distinct true positives.
+    Returns (order i64[D], tp_cum i64[D+1], tpp_cum i64[D+1])."""
+    require_cuda(conf, cls, gt_id, flag, gt_table_base)
+    dev = conf.device
+    D = conf.shape[0]
+    with torch.cuda.device(dev):
+        order = torch.empty(max(D, 1), dtype=_I64, device=dev)
+        tp = torch.empty(D + 1, dtype=_I64, device=dev)
+        tpp = torch.empty(D + 1, dtype=_I64, device=dev)
+        ws_bytes = N.lib.yb_pr_curve_workspace_bytes(D, int(n_gt_total))
+        ws = workspaces.get("pr_curve", ws_bytes, dev)
+        N.check(N.lib.yb_pr_curve(_ptr(conf), _ptr(cls), _ptr(gt_id), _ptr(flag), D, _ptr(gt_table_base),
+                                  int(n_gt_total), _ptr(order), _ptr(tp), _ptr(tpp), _ptr(ws), ws_bytes,
+                                  _stream()), "yb_pr_curve")
+    return order[:D], tp, tpp

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 from numpy.random import rand
 
+from .. import dist as dist_util
 from .. import engine
 from .._native import YB_DIST_EUCLID, YB_DIST_IOU, YoloB200Error
 
@@ -66,12 +67,7 @@ def kmeans(data, n_cluster, dist_func, stop_dist, max_iternum=10000, verbose=Tru
     dev_data = dev_data.reshape(-1, n_dim)
     mm = engine.minmax(dev_data)
     if process_group is not None:
-        import torch.distributed as dist
-        lo = mm[0:1].clone()
-        hi = mm[1:2].clone()
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=process_group)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=process_group)
-        mm = torch.cat([lo, hi])
+        mm = dist_util.allreduce_minmax(mm, process_group)
     data_min, data_max = (float(v) for v in mm.cpu().numpy())
     data_min, data_max = np.float64(data_min), np.float64(data_max)
 
@@ -84,11 +80,7 @@ def kmeans(data, n_cluster, dist_func, stop_dist, max_iternum=10000, verbose=Tru
         dev_center = torch.from_numpy(np.ascontiguousarray(center.reshape(n_cluster, n_dim))).to(dev_data.device)
         assign, sums, counts = engine.kmeans_assign(dev_data, dev_center, kind, want_assign=return_assignments)
         if process_group is not None:
-            import torch.distributed as dist
-            packed = torch.cat([sums.reshape(-1), counts.to(torch.float64)])
-            dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=process_group)
-            sums = packed[:n_cluster * n_dim].reshape(n_cluster, n_dim)
-            counts = packed[n_cluster * n_dim:].round().to(torch.int64)
+            sums, counts = dist_util.allreduce_kmeans(sums, counts, process_group)
         sums = sums.cpu().numpy()
         counts = counts.cpu().numpy()
         new_center = np.copy(center)

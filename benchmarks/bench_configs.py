@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Kernel-level measurements of the other BASELINE.json configs (not the driver's bench contract):
+
+    python benchmarks/bench_configs.py [v2 v3 v4 nms kmeans map] [--json out.json]
+
+CUDA-event timings after warm-up, inputs resident in HBM; every number is printed with the
+algorithmic bytes / work it is measured against.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tf2_yolo_b200 import engine, synth  # noqa: E402
+from tf2_yolo_b200._native import YB_DIST_IOU  # noqa: E402
+from tf2_yolo_b200.grid_loss import fused_losses  # noqa: E402
+
+PEAK = 6549.8
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+
+
+def timed(fn, warm=3, reps=10, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def wrap(version):
+    import importlib
+    pkg = {2: "yolov2", 3: "yolov3", 4: "yolov4"}[version]
+    return importlib.import_module(f"tf2_yolo_b200.{pkg}.losses").wrap_yolo_loss
+
+
+def grid_config(name, version, out):
+    cfg = synth.make_config(name, seed=version)
+    B, C, batch = cfg["bbox_num"], cfg["class_num"], cfg["batch"]
+    fns = []
+    for si, S in enumerate(cfg["grids"]):
+        kw = dict(anchors=cfg["anchors"][si * B:(si + 1) * B])
+        kw["loss_weight"] = [1, 5, 1] if version == 4 else [1, 1, 5, 1]
+        fns.append(wrap(version)((S, S), B, C, **kw))
+    yt = [torch.from_numpy(a).cuda() for a in cfg["y_trues"]]
+    yp = [torch.from_numpy(a).cuda() for a in cfg["y_preds"]]
+    dp = [torch.empty_like(a) for a in yp]
+    ch = 5 + C
+    loss_bytes = sum(4 * batch * s * s * (2 * B * ch + ch) for s in cfg["grids"])
+    dec_bytes = sum(4 * batch * s * s * B * ch for s in cfg["grids"])
+    small = loss_bytes < 126e6
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
+    rows = torch.empty((4096 * batch, 7), dtype=torch.float64, device="cuda")
+    t_loss, t_loss_min = timed(lambda: fused_losses(fns, yt, yp, dpreds=dp), flush=flush)
+    t_dec, _ = timed(lambda: engine.decode_batch(yp, C, 0.5, version, rows=rows), flush=flush)
+    _, offs = engine.decode_batch(yp, C, 0.5, version, rows=rows)
+    t_nms, _ = timed(lambda: engine.nms_batch(rows, offs, C, 0.45, 2 if version == 4 else 1))
+    out[name] = {
+        "batch": batch, "loss_ms": t_loss, "loss_GBps": loss_bytes / t_loss / 1e6,
+        "loss_frac_of_measured_hbm": loss_bytes / t_loss / 1e6 / PEAK, "loss_bytes": loss_bytes,
+        "decode_ms": t_dec, "decode_GBps": dec_bytes / t_dec / 1e6, "decode_frac": dec_bytes / t_dec / 1e6 / PEAK,
+        "nms_ms": t_nms, "rows_per_image": int(offs[-1]) / batch,
+        "images_per_s_loss_decode_nms": batch / ((t_loss + t_dec + t_nms) * 1e-3),
+        "l2": "flushed between iterations (working set < L2)" if small else "inputs larger than L2",
+    }
+    print(name, json.dumps(out[name]))
+
+
+def nms_stress(out, n_img=16, per_img=100_000, C=80):
+    rng = np.random.default_rng(4)
+    rows = np.concatenate([synth.make_dense_candidates(rng, per_img, C) for _ in range(n_img)])
+    offs = torch.arange(0, (n_img + 1) * per_img, per_img, dtype=torch.int64, device="cuda")
+    dev = torch.from_numpy(rows).cuda()
+    for mode in (1, 2):
+        t, tmin = timed(lambda: engine.nms_batch(dev, offs, C, 0.45, mode), warm=1, reps=3)
+        res = engine.nms_batch(dev, offs, C, 0.45, mode)
+        pairs = n_img * C * (per_img / C) ** 2 / 2
+        out[f"nms_dense_mode{mode}"] = {"images": n_img, "candidates_per_image": per_img, "ms": t,
+                                        "images_per_s": n_img / (t * 1e-3),
+                                        "upper_bound_pair_iou_per_s": pairs / (t * 1e-3),
+                                        "kept_per_image": int(res["out_offsets"][-1]) / n_img}
+        print(f"nms_dense_mode{mode}", json.dumps(out[f"nms_dense_mode{mode}"]))
+
+
+def kmeans_bench(out, n=50_000_000, k=9):
+    rng = np.random.default_rng(4)
+    data = torch.from_numpy(synth.make_kmeans_boxes(rng, n, k)).cuda()
+    centers = torch.from_numpy(np.sort(rng.uniform(0.02, 0.8, (k, 2)), axis=0)).cuda()
+    t, tmin = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU))
+    t2, _ = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU, want_assign=True))
+    out["kmeans_50M"] = {"boxes": n, "k": k, "ms_per_iteration": t, "GBps": 16 * n / t / 1e6,
+                         "frac_of_measured_hbm": 16 * n / t / 1e6 / PEAK, "ms_with_assignments": t2}
+    print("kmeans_50M", json.dumps(out["kmeans_50M"]))
+    from tf2_yolo_b200.utils import kmeans as km
+    np.random.seed(4)
+    t0 = time.perf_counter()
+    c = km.kmeans(data[:5_000_000], k, km.iou_dist, 1e-5, verbose=False)
+    out["kmeans_5M_full_run_s"] = time.perf_counter() - t0
+    print("kmeans full run on 5M boxes:", out["kmeans_5M_full_run_s"], "s", c[:3].tolist())
+
+
+def map_bench(out, n_img=512):
+    from tf2_yolo_b200.utils import measurement as meas
+    cfg = synth.make_config("v4-608", batch=n_img, seed=5)
+    names = [str(i) for i in range(80)]
+    yt = cfg["y_trues"][-1]
+    t0 = time.perf_counter()
+    pr = meas.PRfunc(yt, *cfg["y_preds"], class_names=names, conf_threshold=0.05, version=4)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["prfunc_v4_608"] = {"images": n_img, "seconds_host_inputs": dt, "images_per_s": n_img / dt,
+                            "mAP_voc2012": float(pr.get_map()["ap"].iloc[-1])}
+    print("prfunc", json.dumps(out["prfunc_v4_608"]))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", nargs="*", default=["v2", "v3", "v4", "nms", "kmeans", "map"])
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    out = {"peak_hbm_GBps": PEAK}
+    if "v2" in a.what:
+        grid_config("v2-416", 2, out)
+    if "v3" in a.what:
+        grid_config("v3-416", 3, out)
+    if "v4" in a.what:
+        grid_config("v4-608", 4, out)
+    if "nms" in a.what:
+        nms_stress(out)
+    if "kmeans" in a.what:
+        kmeans_bench(out)
+    if "map" in a.what:
+        map_bench(out)
+    if a.json:
+        json.dump(out, open(a.json, "w"), indent=1)

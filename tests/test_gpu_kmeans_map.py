@@ -45,6 +45,8 @@ def test_large_assign_vs_oracle_and_ties():
     centers = rng.uniform(0.02, 0.8, (9, 2))
     centers[4] = centers[2]                                 # duplicate centre: first minimum wins
     data[:9] = centers                                      # zero distances
+    data[10:20] = 1e-4                                      # area ratio < 2^-20: per-point exact fallback
+    data[20:30] = [0.999, 1.0]                              # larger than every centroid
     ref = okm.assign(data, centers, okm.iou_dist)
     a, sums, counts = engine.kmeans_assign(torch.from_numpy(data).cuda(), torch.from_numpy(centers).cuda(),
                                            YB_DIST_IOU, want_assign=True)
@@ -54,6 +56,17 @@ def test_large_assign_vs_oracle_and_ties():
     assert a2 is None and torch.equal(s2, sums) and torch.equal(c2, counts)   # deterministic reduction
     mm = engine.minmax(torch.from_numpy(data).cuda()).cpu().numpy()
     assert mm[0] == data.min() and mm[1] == data.max()
+    # well-separated centroids (the bracketed two-division fast path), incl. boxes on a centroid area
+    c2 = np.array([[0.03, 0.05], [0.6, 0.5], [0.1, 0.12], [0.3, 0.2], [0.9, 0.95], [0.05, 0.08], [0.2, 0.1],
+                   [0.15, 0.3], [0.4, 0.45]])
+    data[100:109] = c2
+    data[110:119] = c2[:, ::-1]                             # same area, swapped sides
+    ref2 = okm.assign(data, c2, okm.iou_dist)
+    a3, s3, n3 = engine.kmeans_assign(torch.from_numpy(data).cuda(), torch.from_numpy(c2).cuda(), YB_DIST_IOU, True)
+    assert np.array_equal(a3.cpu().numpy(), ref2)
+    assert np.array_equal(n3.cpu().numpy(), np.bincount(ref2, minlength=9))
+    for c in range(9):
+        assert np.allclose(s3[c].cpu().numpy(), data[ref2 == c].sum(axis=0), rtol=1e-12, atol=0)
     for d in (1, 3, 4):
         x = rng.uniform(0, 1, (5000, d))
         c = rng.uniform(0, 1, (6, d))

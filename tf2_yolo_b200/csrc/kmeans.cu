@@ -9,13 +9,14 @@
 // bulk-async copies (TMA); every thread keeps k*(d+1) accumulators in registers
 // (compile-time k bound, predicated adds - no atomics in the hot loop), reduced
 // warp -> CTA -> global partials -> last CTA in a fixed order (deterministic).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace yb {
 
 constexpr int kKmThreads = 256;
-constexpr int kKmStages = 3;
-constexpr int kKmTilePts = 2048;  // points per stage (32 KB at d=2)
+constexpr int kKmMaxStages = 3;
 
 struct KmLaunch {
     const double* data;
@@ -23,52 +24,108 @@ struct KmLaunch {
     const double* centers;
     int k, d, kind;
     int bulk_ok;
+    int tile_pts, n_stages;
     int* assign;
     double* sums;       // [k][d]
     long long* counts;  // [k]
-    double* partials;   // [grid][k*(d+1)]
+    double* partials;   // [grid][K*(D+1)]
     unsigned int* counter;
 };
 
-template <int KMAX, int D>
-__global__ void __launch_bounds__(kKmThreads)
+// Per-bracket table entry: box area a with j centroid areas <= a lies in [lo, hi).
+struct __align__(16) KmBracket {
+    double lo, hi;     // sorted neighbours (0 below the smallest, 1e300 above the largest)
+    double gm2;        // lo * hi: a*a < gm2  <=>  lo is the closer centroid
+    int idx_lo, idx_hi;  // original cluster indices of lo / hi
+};
+
+// Shared memory: [ring: n_stages x tile_pts x D doubles][acc: K x 256 x D doubles][cnt: K x 256 ints]
+// Every thread owns one column of the accumulator planes, so the per-box update is a plain
+// load / add / store at a dynamic cluster index (no atomics, no k-way predicated adds).
+template <int K, int D, bool kIou, bool kAssign>
+__global__ void __launch_bounds__(kKmThreads, 2)
 kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     extern __shared__ __align__(128) unsigned char smem[];
-    double* ring = reinterpret_cast<double*>(smem);  // [stages][tile*D]
-    __shared__ uint64_t full[kKmStages];
-    __shared__ double s_center[KMAX * D];
-    __shared__ double s_carea[KMAX];
-    __shared__ double s_red[(kKmThreads / 32) * KMAX * (D + 1)];
+    double* ring = reinterpret_cast<double*>(smem);
+    double* s_acc = ring + (size_t)L.n_stages * L.tile_pts * D;               // [K][256][D]
+    int* s_cnt = reinterpret_cast<int*>(s_acc + (size_t)K * D * kKmThreads);  // [K][256]
+    __shared__ uint64_t full[kKmMaxStages];
+    __shared__ double s_center[K * D];
+    __shared__ double s_carea[K];
+    __shared__ double s_sarea[K + 1];      // centroid areas, ascending
+    __shared__ int s_sidx[K + 1];          // original index of the j-th smallest area
+    __shared__ KmBracket s_br[K + 1];
+    __shared__ int s_exact_all;            // 1: degenerate centroid set -> every box takes the exact loop
+    __shared__ double s_red[(kKmThreads / 32) * K * (D + 1)];
     __shared__ int s_is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = L.k;
+    const int k = L.k;  // <= K
+    const int n_stages = L.n_stages, tile_pts = L.tile_pts;
 
     if (tid == 0) {
-        for (int i = 0; i < kKmStages; ++i) mbar_init(&full[i], 1);
+        for (int i = 0; i < kKmMaxStages; ++i) mbar_init(&full[i], 1);
         mbar_fence_init();
     }
-    if (tid < KMAX * D) s_center[tid] = (tid < k * D) ? L.centers[tid] : 0.0;
+    if (tid < K * D) s_center[tid] = (tid < k * D) ? L.centers[tid] : 0.0;
+    for (int i = tid; i < K * D * kKmThreads; i += kKmThreads) s_acc[i] = 0.0;
+    for (int i = tid; i < K * kKmThreads; i += kKmThreads) s_cnt[i] = 0;
     __syncthreads();
-    if (tid < KMAX) s_carea[tid] = (tid < k && D >= 2) ? __dmul_rn(s_center[tid * D], s_center[tid * D + 1]) : 0.0;
+    if (tid < K) s_carea[tid] = (tid < k && D >= 2) ? __dmul_rn(s_center[tid * D], s_center[tid * D + 1]) : 0.0;
     __syncthreads();
-
-    double acc[KMAX][D];
-    int cnt[KMAX];
-#pragma unroll
-    for (int c = 0; c < KMAX; ++c) {
-        cnt[c] = 0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) acc[c][j] = 0.0;
+    // iou_dist is a function of the AREA only and monotone in it on either side of the box's
+    // area a, so the nearest centroid is one of the two sorted areas lo <= a < hi bracketing
+    // the box, and lo/a > a/hi  <=>  lo*hi > a*a: sort the k areas once, bracket the box,
+    // compare a*a with the precomputed lo*hi - no division at all.  The shortcut is taken only
+    // when it provably agrees with NumPy's first-minimum argmin over the ROUNDED distances
+    // fl(1 - fl(min/max)):
+    //   * |lo*hi - a*a| > 1e-15 * a*hi  => the two ratios differ by > 7e-16, more than the
+    //     rounding of the ratios and of 1 - r can hide, so the rounded distances are ordered
+    //     like the exact ones;
+    //   * neighbouring areas differ by > 1e-6 relative and the winning ratio is >= 2^-20, so
+    //     every farther centroid's rounded distance is strictly larger (no tie to break).
+    // Anything else (duplicate / non-finite centroids, near ties, boxes 2^20 times smaller or
+    // larger than every centroid) takes the exact k-way loop with IEEE divisions.
+    if (tid == 0) {
+        int bad = 0;
+        for (int c = 0; c < k; ++c) {
+            const double a = s_carea[c];
+            if (!(a > 0.0) || !(a < 1e100)) bad = 1;
+            int r = 0;
+            for (int q = 0; q < k; ++q) r += (s_carea[q] < a || (s_carea[q] == a && q < c)) ? 1 : 0;
+            s_sarea[r] = a;
+            s_sidx[r] = c;
+        }
+        for (int j = k; j <= K; ++j) {
+            s_sarea[j] = INFINITY;
+            s_sidx[j] = 0;
+        }
+        for (int j = 0; j <= K; ++j) {
+            KmBracket b;
+            b.lo = (j > 0 && j <= k) ? s_sarea[j - 1] : 0.0;
+            b.hi = (j < k) ? s_sarea[j] : 1e300;
+            b.gm2 = __dmul_rn(b.lo, b.hi);
+            b.idx_lo = (j > 0 && j <= k) ? s_sidx[j - 1] : 0;
+            b.idx_hi = (j < k) ? s_sidx[j] : 0;
+            s_br[j] = b;
+        }
+        for (int j = 0; j + 1 < k && !bad; ++j)
+            if (!(s_sarea[j + 1] - s_sarea[j] > 1e-6 * s_sarea[j + 1])) bad = 1;
+        s_exact_all = bad;
     }
+    __syncthreads();
+    const bool exact_all = (s_exact_all != 0) || D < 2;
+    double sarea[K];  // sorted areas in registers: the bracket index is a count of K compares
+#pragma unroll
+    for (int c = 0; c < K; ++c) sarea[c] = s_sarea[c];
 
-    const long long n_tiles = (L.n + kKmTilePts - 1) / kKmTilePts;
+    const long long n_tiles = (L.n + tile_pts - 1) / tile_pts;
     const long long n_my = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto issue = [&](long long t) {
         const long long tile = blockIdx.x + t * gridDim.x;
-        const long long p0 = tile * kKmTilePts;
-        const int np = (int)min((long long)kKmTilePts, L.n - p0);
-        const int stage = (int)(t % kKmStages);
-        double* dst = ring + (size_t)stage * kKmTilePts * D;
+        const long long p0 = tile * tile_pts;
+        const int np = (int)min((long long)tile_pts, L.n - p0);
+        const int stage = (int)(t % n_stages);
+        double* dst = ring + (size_t)stage * tile_pts * D;
         const uint32_t bytes = (uint32_t)np * D * 8u;
         if (L.bulk_ok && (bytes & 15u) == 0u) {
             mbar_arrive_expect_tx(&full[stage], bytes);
@@ -78,28 +135,48 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         }
     };
     if (tid == 0)
-        for (long long t = 0; t < min((long long)(kKmStages - 1), n_my); ++t) issue(t);
+        for (long long t = 0; t < min((long long)(n_stages - 1), n_my); ++t) issue(t);
 
+    double* my_acc = s_acc + tid * D;
+    int* my_cnt = s_cnt + tid;
     for (long long it = 0; it < n_my; ++it) {
-        if (tid == 0 && it + kKmStages - 1 < n_my) issue(it + kKmStages - 1);
+        if (tid == 0 && it + n_stages - 1 < n_my) issue(it + n_stages - 1);
         const long long tile = blockIdx.x + it * gridDim.x;
-        const long long p0 = tile * kKmTilePts;
-        const int np = (int)min((long long)kKmTilePts, L.n - p0);
-        const int stage = (int)(it % kKmStages);
+        const long long p0 = tile * tile_pts;
+        const int np = (int)min((long long)tile_pts, L.n - p0);
+        const int stage = (int)(it % n_stages);
         const bool staged = L.bulk_ok && ((((uint32_t)np * D * 8u) & 15u) == 0u);
-        const double* src = staged ? ring + (size_t)stage * kKmTilePts * D : L.data + p0 * D;
-        mbar_wait(&full[stage], (uint32_t)((it / kKmStages) & 1));
+        const double* src = staged ? ring + (size_t)stage * tile_pts * D : L.data + p0 * D;
+        mbar_wait(&full[stage], (uint32_t)((it / n_stages) & 1));
+#pragma unroll 2
         for (int i = tid; i < np; i += kKmThreads) {
             double v[D];
+            if (D == 2) {
+                const double2 t2 = *reinterpret_cast<const double2*>(src + (size_t)i * 2);
+                v[0] = t2.x;
+                v[D - 1] = t2.y;
+            } else {
 #pragma unroll
-            for (int j = 0; j < D; ++j) v[j] = src[(size_t)i * D + j];
+                for (int j = 0; j < D; ++j) v[j] = src[(size_t)i * D + j];
+            }
             int best = 0;
-            double bd = 0.0;
-            if (L.kind == YB_DIST_IOU) {
-                const double a = __dmul_rn(v[0], v[1]);
+            if (kIou) {
+                const double a = __dmul_rn(v[0], v[D > 1 ? 1 : 0]);
+                int j = 0;  // number of centroid areas <= a
 #pragma unroll
-                for (int c = 0; c < KMAX; ++c) {
-                    if (c < k) {
+                for (int c = 0; c < K; ++c) j += (sarea[c] <= a) ? 1 : 0;
+                const KmBracket b = s_br[j];
+                const double tiny = 9.5367431640625e-07;  // 2^-20
+                const double q = __dmul_rn(a, a);
+                const double band = __dmul_rn(1e-15, __dmul_rn(a, b.hi));
+                const bool take_lo = b.gm2 > q;  // lo/a > a/hi: the smaller centroid is closer
+                best = take_lo ? b.idx_lo : b.idx_hi;
+                const bool far_enough = take_lo ? (b.lo >= tiny * a) : (a >= tiny * b.hi);
+                const bool sure = (fabs(b.gm2 - q) > band) && far_enough && !exact_all;
+                if (!sure) {
+                    double bd = 0.0;
+                    best = 0;
+                    for (int c = 0; c < k; ++c) {
                         const double ca = s_carea[c];
                         const double dist = 1.0 - fmin(ca, a) / fmax(ca, a);
                         if (c == 0 || dist < bd) {
@@ -109,52 +186,53 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
                     }
                 }
             } else {
+                double bd = 0.0;
+                for (int c = 0; c < k; ++c) {
+                    double sq = 0.0;
 #pragma unroll
-                for (int c = 0; c < KMAX; ++c) {
-                    if (c < k) {
-                        double s = 0.0;
-#pragma unroll
-                        for (int j = 0; j < D; ++j) {
-                            const double df = s_center[c * D + j] - v[j];
-                            s = __dadd_rn(s, __dmul_rn(df, df));
-                        }
-                        const double dist = sqrt(s);
-                        if (c == 0 || dist < bd) {
-                            bd = dist;
-                            best = c;
-                        }
+                    for (int j = 0; j < D; ++j) {
+                        const double df = s_center[c * D + j] - v[j];
+                        sq = __dadd_rn(sq, __dmul_rn(df, df));
+                    }
+                    const double dist = sqrt(sq);
+                    if (c == 0 || dist < bd) {
+                        bd = dist;
+                        best = c;
                     }
                 }
             }
-            if (L.assign != nullptr) L.assign[p0 + i] = best;
+            if (kAssign) L.assign[p0 + i] = best;
+            double* slot = my_acc + best * (D * kKmThreads);
+            if (D == 2) {
+                double2 t2 = *reinterpret_cast<double2*>(slot);
+                t2.x += v[0];
+                t2.y += v[D - 1];
+                *reinterpret_cast<double2*>(slot) = t2;
+            } else {
 #pragma unroll
-            for (int c = 0; c < KMAX; ++c) {
-                const bool hit = (best == c);
-                cnt[c] += hit ? 1 : 0;
-#pragma unroll
-                for (int j = 0; j < D; ++j) acc[c][j] += hit ? v[j] : 0.0;
+                for (int j = 0; j < D; ++j) slot[j] += v[j];
             }
+            my_cnt[best * kKmThreads] += 1;
         }
         __syncthreads();  // stage free for the next bulk load
     }
 
-    // ---- reduction: thread -> warp -> CTA -> global partials -> last CTA ----
-    constexpr int NV = KMAX * (D + 1);
-#pragma unroll
-    for (int c = 0; c < KMAX; ++c) {
+    // ---- reduction: thread columns -> warp -> CTA -> global partials -> last CTA ----
+    constexpr int NV = K * (D + 1);
+    for (int c = 0; c < K; ++c) {
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            const double s = warp_sum(acc[c][j]);
-            if (lane == 0) s_red[warp * NV + c * (D + 1) + j] = s;
+            const double sres = warp_sum(my_acc[c * (D * kKmThreads) + j]);
+            if (lane == 0) s_red[warp * NV + c * (D + 1) + j] = sres;
         }
-        const int cs = warp_sum(cnt[c]);
+        const int cs = warp_sum(my_cnt[c * kKmThreads]);
         if (lane == 0) s_red[warp * NV + c * (D + 1) + D] = (double)cs;  // exact below 2^53
     }
     __syncthreads();
     if (tid < NV) {
-        double s = 0.0;
-        for (int w = 0; w < kKmThreads / 32; ++w) s += s_red[w * NV + tid];
-        L.partials[(size_t)blockIdx.x * NV + tid] = s;
+        double sres = 0.0;
+        for (int w = 0; w < kKmThreads / 32; ++w) sres += s_red[w * NV + tid];
+        L.partials[(size_t)blockIdx.x * NV + tid] = sres;
     }
     __threadfence();
     __syncthreads();
@@ -163,14 +241,14 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     if (!s_is_last) return;
     __threadfence();
     for (int i = warp; i < NV; i += kKmThreads / 32) {
-        double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&L.partials[(size_t)b * NV + i]);
-        s = warp_sum(s);
+        double sres = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) sres += __ldcg(&L.partials[(size_t)b * NV + i]);
+        sres = warp_sum(sres);
         if (lane == 0) {
             const int c = i / (D + 1), j = i - c * (D + 1);
             if (c < k) {
-                if (j < D) L.sums[c * D + j] = s;
-                else L.counts[c] = (long long)s;
+                if (j < D) L.sums[c * D + j] = sres;
+                else L.counts[c] = (long long)sres;
             }
         }
     }
@@ -215,15 +293,48 @@ __global__ void minmax_kernel(const double* __restrict__ x, long long n, double*
     *counter = 0u;
 }
 
-constexpr int kKmGrid = kNumSMs * 2;
+constexpr int kKmGrid = kNumSMs * 4;  // upper bound of the launch grid (partials sizing)
 
-template <int KMAX, int D>
-static int launch_km(const KmLaunch& L, cudaStream_t stream) {
-    const size_t smem = (size_t)kKmStages * kKmTilePts * D * sizeof(double);
-    YB_CUDA_TRY(cudaFuncSetAttribute(kmeans_assign_kernel<KMAX, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long n_tiles = (L.n + kKmTilePts - 1) / kKmTilePts;
-    const int grid = (int)max(1LL, min((long long)kKmGrid, n_tiles));
-    kmeans_assign_kernel<KMAX, D><<<grid, kKmThreads, smem, stream>>>(L);
+template <int K, int D>
+static int launch_km(KmLaunch L, cudaStream_t stream) {
+    // accumulator planes + ring must fit: prefer 2 stages of 2048 boxes and 2 CTAs per SM (measured best:
+    // the per-tile barrier cost is amortised over 8 boxes per thread, see benchmarks/km_sweep.sh)
+    const size_t acc = (size_t)K * kKmThreads * (D * sizeof(double) + sizeof(int));
+    const size_t budget2 = (227 * 1024) / 2 - 5 * 1024;   // per CTA with 2 CTAs/SM (static smem + reservation)
+    const size_t budget1 = 227 * 1024 - 8 * 1024;
+    int tile = 2048, stages = 2;
+    auto need = [&](int t, int st) { return acc + (size_t)st * t * D * sizeof(double); };
+    while (need(tile, stages) > budget2 && tile > 512) tile >>= 1;
+    if (need(tile, stages) > budget2) {   // fat k*d: one CTA per SM
+        tile = 1024;
+        while (need(tile, stages) > budget1 && tile > 128) tile >>= 1;
+        if (need(tile, stages) > budget1) return YB_E_SHAPE;
+    }
+    int ctas = (need(tile, stages) <= budget2) ? 2 : 1;
+    {   // tuning hooks (debug): YB_KM_TILE / YB_KM_STAGES / YB_KM_CTAS
+        const char* e;
+        if ((e = getenv("YB_KM_TILE")) && atoi(e) >= 128) tile = atoi(e) / 128 * 128;
+        if ((e = getenv("YB_KM_STAGES")) && atoi(e) >= 2 && atoi(e) <= kKmMaxStages) stages = atoi(e);
+        if ((e = getenv("YB_KM_CTAS")) && atoi(e) >= 1 && atoi(e) <= 4) ctas = atoi(e);
+        if (need(tile, stages) > budget1) return YB_E_SHAPE;
+    }
+    L.tile_pts = tile;
+    L.n_stages = stages;
+    const size_t smem = need(tile, stages);
+    const long long n_tiles = (L.n + tile - 1) / tile;
+    const int grid = (int)max(1LL, min((long long)kNumSMs * ctas, n_tiles));
+#define YB_KM_LAUNCH(IOU, ASSIGN)                                                                          \
+    do {                                                                                                   \
+        YB_CUDA_TRY(cudaFuncSetAttribute(kmeans_assign_kernel<K, D, IOU, ASSIGN>,                          \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        kmeans_assign_kernel<K, D, IOU, ASSIGN><<<grid, kKmThreads, smem, stream>>>(L);                    \
+    } while (0)
+    const bool iou = L.kind == YB_DIST_IOU, asg = L.assign != nullptr;
+    if (iou && asg) YB_KM_LAUNCH(true, true);
+    else if (iou) YB_KM_LAUNCH(true, false);
+    else if (asg) YB_KM_LAUNCH(false, true);
+    else YB_KM_LAUNCH(false, false);
+#undef YB_KM_LAUNCH
     return (int)cudaGetLastError();
 }
 
@@ -233,6 +344,28 @@ static int launch_km_d(const KmLaunch& L, cudaStream_t stream) {
     if (L.k <= 8) return launch_km<8, D>(L, stream);
     if (L.k <= 12) return launch_km<12, D>(L, stream);
     return launch_km<16, D>(L, stream);
+}
+
+// (w, h) boxes - the anchor case: exact k so the register accumulators are not padded
+static int launch_km_boxes(const KmLaunch& L, cudaStream_t stream) {
+    switch (L.k) {
+        case 1: return launch_km<1, 2>(L, stream);
+        case 2: return launch_km<2, 2>(L, stream);
+        case 3: return launch_km<3, 2>(L, stream);
+        case 4: return launch_km<4, 2>(L, stream);
+        case 5: return launch_km<5, 2>(L, stream);
+        case 6: return launch_km<6, 2>(L, stream);
+        case 7: return launch_km<7, 2>(L, stream);
+        case 8: return launch_km<8, 2>(L, stream);
+        case 9: return launch_km<9, 2>(L, stream);
+        case 10: return launch_km<10, 2>(L, stream);
+        case 11: return launch_km<11, 2>(L, stream);
+        case 12: return launch_km<12, 2>(L, stream);
+        case 13: return launch_km<13, 2>(L, stream);
+        case 14: return launch_km<14, 2>(L, stream);
+        case 15: return launch_km<15, 2>(L, stream);
+        default: return launch_km<16, 2>(L, stream);
+    }
 }
 
 }  // namespace yb
@@ -274,7 +407,7 @@ extern "C" int yb_kmeans_assign(const double* data, int64_t n_points, int n_dim,
     YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
     switch (n_dim) {
         case 1: return launch_km_d<1>(L, stream);
-        case 2: return launch_km_d<2>(L, stream);
+        case 2: return launch_km_boxes(L, stream);
         case 3: return launch_km_d<3>(L, stream);
         default: return launch_km_d<4>(L, stream);
     }

@@ -158,6 +158,16 @@ int yb_nms(const double* rows, const int64_t* row_offsets, int64_t n_rows, int64
            double* out_rows, int64_t* out_offsets, int64_t* out_seg_offsets,
            void* workspace, size_t workspace_bytes, yb_stream_t stream);
 
+/* Gaussian soft-NMS: utils/tools.py:736-786 (soft_nms).  Same layout and outputs as yb_nms
+ * (same workspace size).  Every visited box - deleted or not - multiplies the confidence c*p
+ * of each not-yet-visited box it overlaps (IoU >= nms_threshold) by exp(-IoU^2/sigma); a box is
+ * dropped once that pushes it below conf_threshold.  The visit order is fixed by the initial
+ * confidences, so each box's fate is an independent product over the boxes before it. */
+int yb_soft_nms(const double* rows, const int64_t* row_offsets, int64_t n_rows, int64_t n_img,
+                int class_num, double nms_threshold, double conf_threshold, double sigma,
+                uint8_t* keep, double* out_rows, int64_t* out_offsets, int64_t* out_seg_offsets,
+                void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
 /* Pairwise IoU / DIoU matrix, utils/tools.py:630-684 on (g,1,.) x (1,d,.):
  * a: (na, stride_a) doubles, b: (nb, stride_b) doubles, out (na, nb). */
 int yb_pairwise_iou(const double* a, int64_t na, int stride_a, const double* b, int64_t nb,

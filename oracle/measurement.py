@@ -22,15 +22,15 @@ import numpy as np
 from . import tools
 
 
-def _detect(per_image_preds, class_num, conf_threshold, nms_mode, nms_threshold, version):
+def _detect(per_image_preds, class_num, conf_threshold, nms_mode, nms_threshold, version, nms_sigma=0.5):
     det = tools.decode(*per_image_preds, class_num=class_num, threshold=conf_threshold, version=version)
     if nms_mode > 0 and len(det) > 0:
         if nms_mode == 1:
             det = tools.nms(det, class_num, nms_threshold)
         elif nms_mode == 3:
             det = tools.nms(det, class_num, nms_threshold, 2)
-        else:
-            raise NotImplementedError("soft-NMS path is not part of the oracle")
+        elif nms_mode == 2:
+            det = tools.soft_nms(det, class_num, nms_threshold, conf_threshold, nms_sigma)
     return det.reshape(-1, 7)
 
 
@@ -63,7 +63,7 @@ class PRfunc:
         dets = [[] for _ in range(C)]
         for i, y_true in enumerate(y_trues):
             gt = tools.decode(y_true, class_num=C, version=version).reshape(-1, 7)
-            det = _detect([p[i] for p in y_preds], C, conf_threshold, nms_mode, nms_threshold, version)
+            det = _detect([p[i] for p in y_preds], C, conf_threshold, nms_mode, nms_threshold, version, nms_sigma)
             for k, (conf, arg, flag, n_gt) in enumerate(match_image(gt, det, C, iou_threshold)):
                 if len(conf):
                     gid = arg + gts[k] if n_gt > 0 else np.zeros(len(conf))
@@ -139,7 +139,7 @@ def score_table(y_trues, *y_preds, class_names=[], conf_threshold=0.5, nms_mode=
     det_counts = np.zeros(C, dtype="int")
     for i, y_true in enumerate(y_trues):
         gt = tools.decode(y_true, class_num=C, version=version).reshape(-1, 7)
-        det = _detect([p[i] for p in y_preds], C, conf_threshold, nms_mode, nms_threshold, version)
+        det = _detect([p[i] for p in y_preds], C, conf_threshold, nms_mode, nms_threshold, version, nms_sigma)
         for k, (conf, arg, flag, n_gt) in enumerate(match_image(gt, det, C, iou_threshold)):
             denom[k] += (len(conf), n_gt)
             det_counts[k] += len(conf)

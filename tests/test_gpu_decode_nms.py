@@ -129,3 +129,18 @@ def test_nms_edge_cases():
     for i, p in enumerate(parts):
         if len(p):
             assert np.array_equal(keep[offs[i]:offs[i + 1]], ot.nms_keep(p, 3, 0.45, 2))
+
+
+def test_soft_nms(golden):
+    """Gaussian soft-NMS (nms_mode=2): keep sets equal the reference fixtures and the oracle."""
+    z = golden("decode_nms")
+    for thr in (0.5, 0.3):
+        for i in range(3):
+            rows = z[f"m/rows_t{thr}_i{i}"]
+            assert np.array_equal(tools.soft_nms(rows, 5, 0.45, thr, 0.5), z[f"m/soft_t{thr}_i{i}"])
+    rng = np.random.default_rng(12)
+    rows = synth.make_dense_candidates(rng, 4000, 6)      # warp path and CTA path
+    for sigma, cthr in ((0.5, 0.5), (0.3, 0.6), (1.0, 0.3)):
+        assert np.array_equal(tools.soft_nms(rows, 6, 0.45, cthr, sigma), ot.soft_nms(rows, 6, 0.45, cthr, sigma))
+    rows = synth.make_dense_candidates(rng, 9000, 3)      # > 2048 per class: global-scratch path
+    assert np.array_equal(tools.soft_nms(rows, 3, 0.5, 0.5, 0.5), ot.soft_nms(rows, 3, 0.5, 0.5, 0.5))

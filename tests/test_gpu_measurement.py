@@ -57,7 +57,8 @@ def test_prfunc_larger_vs_oracle():
     yt = y_trues[-1].astype(np.float64)
     for kw in (dict(conf_threshold=0.05, nms_mode=1, max_per_img=100),
                dict(conf_threshold=0.2, nms_mode=3, nms_threshold=0.45, max_per_img=4, precision_mode=0),
-               dict(conf_threshold=0.2, nms_mode=0, max_per_img=None, precision_mode=1)):
+               dict(conf_threshold=0.2, nms_mode=0, max_per_img=None, precision_mode=1),
+               dict(conf_threshold=0.3, nms_mode=2, nms_threshold=0.45, nms_sigma=0.5, max_per_img=100)):
         ref = om.PRfunc(yt, *y_preds, class_names=names, version=4, **kw)
         got = meas.PRfunc(yt, *y_preds, class_names=names, version=4, **kw)
         for k in range(C):

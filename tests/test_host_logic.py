@@ -73,6 +73,8 @@ def test_no_cpu_fallback_anywhere():
     with pytest.raises(YoloB200Error):
         tools.nms(np.zeros((3, 7)), 2)
     with pytest.raises(YoloB200Error):
+        tools.soft_nms(np.zeros((3, 7)), 2)
+    with pytest.raises(YoloB200Error):
         km.kmeans(np.random.rand(10, 2), 2, km.iou_dist, 1e-3, verbose=False)
     with pytest.raises(YoloB200Error):
         meas.PRfunc(np.zeros((1, 4, 4, 7)), yp, class_names=["a", "b"])
@@ -81,8 +83,8 @@ def test_no_cpu_fallback_anywhere():
 def test_error_behaviour_matches_the_reference():
     with pytest.raises(ValueError, match="Invalid version"):
         tools.decode(np.zeros((2, 2, 14), np.float32), class_num=2, version=7)
-    with pytest.raises(NotImplementedError):
-        tools.soft_nms(np.zeros((1, 7)))
+    with pytest.raises(IndexError):
+        tools.soft_nms(np.zeros(0))
     with pytest.raises(YoloB200Error):
         km.kmeans(np.random.rand(10, 2), 2, lambda a, b: a, 1e-3)     # arbitrary Python distance
     with pytest.raises(YoloB200Error):

@@ -19,6 +19,8 @@ HOT_PATH = {
     ("utils.tools", "decode"): ("tf2_yolo_b200.utils.tools", "decode"),
     ("utils.tools", "nms"): ("tf2_yolo_b200.utils.tools", "nms"),
     ("utils.tools", "cal_iou"): ("tf2_yolo_b200.utils.tools", "cal_iou"),
+    ("utils.tools", "soft_nms"): ("tf2_yolo_b200.utils.tools", "soft_nms"),
+    ("utils.measurement", "soft_nms"): ("tf2_yolo_b200.utils.tools", "soft_nms"),
     ("utils.kmeans", "kmeans"): ("tf2_yolo_b200.utils.kmeans", "kmeans"),
     ("utils.kmeans", "iou_dist"): ("tf2_yolo_b200.utils.kmeans", "iou_dist"),
     ("utils.kmeans", "euclidean_dist"): ("tf2_yolo_b200.utils.kmeans", "euclidean_dist"),

@@ -80,6 +80,7 @@ SIGNATURES = {
     "yb_decode": (C.c_int, [C.POINTER(_vp), _i64, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _sz, _vp]),
     "yb_nms_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "yb_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "yb_soft_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_pairwise_iou": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _vp, _vp]),
     "yb_elementwise_iou": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
     "yb_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),

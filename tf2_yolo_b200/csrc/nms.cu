@@ -50,6 +50,47 @@ __device__ __forceinline__ double pair_iou(double tx, double ty, double tw, doub
     return iou - rho2 / c2;
 }
 
+// Does box t suppress box p, i.e. is fl(IoU) (MODE 1) / fl(fl(IoU) - fl(rho2/c2)) (MODE 2) >= thr ?
+// Same truth value as comparing pair_iou<MODE>() with thr, but decided WITHOUT a division
+// whenever the cross-multiplied inequality holds with a margin wider than every rounding
+// error involved; only pairs inside that margin (and non-finite cases) evaluate the exact
+// expression.  fp64 division is the latency of this kernel, the margin test is ~10 multiplies.
+template <int MODE>
+__device__ __forceinline__ bool suppresses(double tx, double ty, double tw, double th, double px,
+                                           double py, double pw, double ph, double thr) {
+    const double thw = tw / 2.0, thh = th / 2.0, phw = pw / 2.0, phh = ph / 2.0;
+    const double t0x = tx - thw, t0y = ty - thh, t1x = tx + thw, t1y = ty + thh;
+    const double p0x = px - phw, p0y = py - phh, p1x = px + phw, p1y = py + phh;
+    const double iw = fmax(fmin(p1x, t1x) - fmax(p0x, t0x), 0.0);
+    const double ih = fmax(fmin(p1y, t1y) - fmax(p0y, t0y), 0.0);
+    const double inter = iw * ih;
+    const double den = (pw * ph + tw * th - inter) + kIouEps;
+    if (MODE == 1) {
+        if (thr > 0.0) {
+            // x = inter/den (real).  x >= thr => fl(x) >= thr;  x < thr(1-2^-51) => fl(x) < thr.
+            const double P = thr * den;
+            if (inter >= P * (1.0 + 4.5e-16)) return true;
+            if (inter <= P * (1.0 - 9.0e-16)) return false;
+        }
+        return inter / den >= thr;
+    }
+    const double ew = fmax(p1x, t1x) - fmin(p0x, t0x), eh = fmax(p1y, t1y) - fmin(p0y, t0y);
+    const double c2 = ew * ew + eh * eh;
+    const double dx = tx - px, dy = ty - py;
+    const double rho2 = dx * dx + dy * dy;
+    {
+        // y = inter/den - rho2/c2 (real); the computed value differs from y by < 4e-16 for
+        // |terms| <= 1, so |y - thr| > 1e-15 decides.  y - thr = (A - B - thr*S) / S with
+        // A = inter*c2, B = rho2*den, S = den*c2 > 0; every product carries 2^-53 relative error.
+        const double A = inter * c2, B = rho2 * den, S = den * c2;
+        const double lhs = A - B, rhs = thr * S;
+        const double slack = 4.5e-16 * (A + B + fabs(rhs)) + 2.0e-15 * S;
+        if (lhs - rhs > slack && inter <= den && rho2 <= c2) return true;
+        if (rhs - lhs > slack && inter <= den && rho2 <= c2) return false;
+    }
+    return (inter / den - rho2 / c2) >= thr;
+}
+
 struct NmsWs {
     int* row_seg;            // [R]
     unsigned int* seg_count; // [n_seg + 1]
@@ -126,7 +167,8 @@ __global__ void nms_scatter_kernel(const long long* __restrict__ row_offsets, lo
 // ---- small segments: one warp each ---------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(256)
-nms_small_kernel(const double* __restrict__ rows, double thr, NmsWs W, unsigned char* __restrict__ keep) {
+nms_small_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W,
+                 unsigned char* __restrict__ keep) {
     const int lane = threadIdx.x & 31;
     for (;;) {
         unsigned w = 0;
@@ -159,22 +201,45 @@ nms_small_kernel(const double* __restrict__ rows, double thr, NmsWs W, unsigned 
         // visit rank: descending confidence, ties -> higher original index first
         int vis = 0;
         unsigned sup = 0;
+#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const double cj = __shfl_sync(0xffffffffu, conf, j);
             vis += (cj > conf || (cj == conf && j > lane)) ? 1 : 0;
             const double xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
             const double wj = __shfl_sync(0xffffffffu, bw, j), hj = __shfl_sync(0xffffffffu, bh, j);
-            if (pair_iou<MODE>(x, y, bw, bh, xj, yj, wj, hj) >= thr) sup |= 1u << j;
+            if (MODE != 3 && suppresses<(MODE == 3 ? 1 : MODE)>(x, y, bw, bh, xj, yj, wj, hj, thr)) sup |= 1u << j;
         }
-        // greedy sweep, state replicated in every lane
         unsigned dead = 0, seen = 0;
-        for (int v = 0; v < n; ++v) {
-            const unsigned who = __ballot_sync(0xffffffffu, lane < n && vis == v);
-            if (who == 0u) continue;  // only with NaN confidences
-            const int src = __ffs(who) - 1;
-            const unsigned s = __shfl_sync(0xffffffffu, sup, src);
-            seen |= 1u << src;
-            if (!((dead >> src) & 1u)) dead |= s & ~seen & valid;
+        if (MODE == 3) {
+            // soft-NMS (utils/tools.py:736-786): the visit order is fixed up front and deleted boxes keep
+            // decaying others, so box j's final confidence is its own product over the boxes visited
+            // before it, taken in visit order - independent of every other box.
+            bool decayed = false;
+            for (int v = 0; v < n; ++v) {
+                const unsigned who = __ballot_sync(0xffffffffu, lane < n && vis == v);
+                if (who == 0u) continue;
+                const int src = __ffs(who) - 1;
+                const double xs = __shfl_sync(0xffffffffu, x, src), ys = __shfl_sync(0xffffffffu, y, src);
+                const double ws = __shfl_sync(0xffffffffu, bw, src), hs = __shfl_sync(0xffffffffu, bh, src);
+                if (lane < n && vis > v) {
+                    const double iou = pair_iou<1>(xs, ys, ws, hs, x, y, bw, bh);
+                    if (iou >= thr) {
+                        conf = conf * exp(-1.0 * (iou * iou) / sigma);
+                        decayed = true;
+                    }
+                }
+            }
+            dead = __ballot_sync(0xffffffffu, lane < n && decayed && conf < conf_thr);
+        } else {
+            // greedy sweep, state replicated in every lane
+            for (int v = 0; v < n; ++v) {
+                const unsigned who = __ballot_sync(0xffffffffu, lane < n && vis == v);
+                if (who == 0u) continue;  // only with NaN confidences
+                const int src = __ffs(who) - 1;
+                const unsigned s = __shfl_sync(0xffffffffu, sup, src);
+                seen |= 1u << src;
+                if (!((dead >> src) & 1u)) dead |= s & ~seen & valid;
+            }
         }
         const unsigned alive = valid & ~dead;
         if (lane < n) {
@@ -209,7 +274,7 @@ __device__ __forceinline__ void block_bitonic(int* h, int P, Less less) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kBigThreads)
-nms_big_kernel(const double* __restrict__ rows, double thr, NmsWs W, long long R,
+nms_big_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W, long long R,
                unsigned char* __restrict__ keep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* s_box = reinterpret_cast<double*>(smem_raw);                 // [5][kBigCap]
@@ -268,8 +333,26 @@ nms_big_kernel(const double* __restrict__ rows, double thr, NmsWs W, long long R
             rem[v] = 0;
         }
         __syncthreads();
+        if (MODE == 3) {
+            // soft-NMS: every box multiplies its confidence by exp(-IoU^2/sigma) for each earlier-visited
+            // box it overlaps (in visit order); deleted <=> it was decayed below conf_thr.
+            for (int v = tid; v < n; v += kBigThreads) {
+                double c = cf[ord[v]];
+                const double x = bx[v], y = by[v], w = bwd[v], h = bht[v];
+                bool decayed = false;
+                for (int i = 0; i < v; ++i) {
+                    const double iou = pair_iou<1>(bx[i], by[i], bwd[i], bht[i], x, y, w, h);
+                    if (iou >= thr) {
+                        c = c * exp(-1.0 * (iou * iou) / sigma);
+                        decayed = true;
+                    }
+                }
+                rem[v] = (decayed && c < conf_thr) ? 1 : 0;
+            }
+            __syncthreads();
+        }
         // 3. blocked greedy sweep
-        for (int blk = 0; blk < n; blk += kSweep) {
+        for (int blk = 0; MODE != 3 && blk < n; blk += kSweep) {
             const int m = min(kSweep, n - blk);
             if (tid < kSweep) s_mask[tid] = 0ull;
             __syncthreads();
@@ -279,8 +362,9 @@ nms_big_kernel(const double* __restrict__ rows, double thr, NmsWs W, long long R
                     const double x = bx[blk + i], y = by[blk + i], w = bwd[blk + i], h = bht[blk + i];
                     unsigned long long bits = 0ull;
                     const int j0 = max(part * 16, i + 1), j1 = min(part * 16 + 16, m);
+#pragma unroll 4
                     for (int j = j0; j < j1; ++j)
-                        if (pair_iou<MODE>(x, y, w, h, bx[blk + j], by[blk + j], bwd[blk + j], bht[blk + j]) >= thr)
+                        if (suppresses<(MODE == 3 ? 1 : MODE)>(x, y, w, h, bx[blk + j], by[blk + j], bwd[blk + j], bht[blk + j], thr))
                             bits |= 1ull << j;
                     if (bits) atomicOr(&s_mask[i], bits);
                 }
@@ -306,7 +390,7 @@ nms_big_kernel(const double* __restrict__ rows, double thr, NmsWs W, long long R
                 const double x = bx[j], y = by[j], w = bwd[j], h = bht[j];
                 for (int q = 0; q < nk; ++q) {
                     const int i = s_kept[q];
-                    if (pair_iou<MODE>(bx[i], by[i], bwd[i], bht[i], x, y, w, h) >= thr) {
+                    if (suppresses<(MODE == 3 ? 1 : MODE)>(bx[i], by[i], bwd[i], bht[i], x, y, w, h, thr)) {
                         rem[j] = 1;
                         break;
                     }
@@ -431,17 +515,17 @@ extern "C" size_t yb_nms_workspace_bytes(int64_t n_rows, int64_t n_img, int clas
     return nms_layout(n_rows, n_img * class_num, nullptr, nullptr);
 }
 
-extern "C" int yb_nms(const double* rows, const int64_t* row_offsets_, int64_t n_rows, int64_t n_img,
-                      int class_num, double nms_threshold, int iou_mode, uint8_t* keep, double* out_rows,
-                      int64_t* out_offsets_, int64_t* out_seg_offsets_, void* workspace,
-                      size_t workspace_bytes, yb_stream_t stream_) {
+static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_rows, int64_t n_img,
+                    int class_num, double nms_threshold, int iou_mode, double conf_thr, double sigma,
+                    uint8_t* keep, double* out_rows, int64_t* out_offsets_, int64_t* out_seg_offsets_,
+                    void* workspace, size_t workspace_bytes, yb_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     const long long* row_offsets = reinterpret_cast<const long long*>(row_offsets_);
     long long* out_offsets = reinterpret_cast<long long*>(out_offsets_);
     long long* out_seg_offsets = reinterpret_cast<long long*>(out_seg_offsets_);
     if (row_offsets == nullptr || workspace == nullptr) return YB_E_NULL;
     if (n_rows < 0 || n_img < 0 || class_num <= 0) return YB_E_SHAPE;
-    if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
+    if (iou_mode != 1 && iou_mode != 2 && iou_mode != 3) return YB_E_PARAM;
     if (n_rows > 0 && (rows == nullptr || keep == nullptr)) return YB_E_NULL;
     if (n_rows > (int64_t)INT_MAX / 2) return YB_E_SHAPE;
     if (workspace_bytes < yb_nms_workspace_bytes(n_rows, n_img, class_num) || ((uintptr_t)workspace & 255))
@@ -472,15 +556,18 @@ extern "C" int yb_nms(const double* rows, const int64_t* row_offsets_, int64_t n
     const int small_blocks = (int)min((long long)kNumSMs * 4, (n_seg * 32 + threads - 1) / threads);
     const size_t big_smem = sizeof(double) * 5 * kBigCap + sizeof(int) * 2 * kBigCap + kBigCap;
     const int big_blocks = (int)min((long long)kNumSMs * 2, n_seg);
-    if (iou_mode == 1) {
-        nms_small_kernel<1><<<small_blocks, threads, 0, stream>>>(rows, nms_threshold, W, keep);
-        YB_CUDA_TRY(cudaFuncSetAttribute(nms_big_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
-        nms_big_kernel<1><<<big_blocks, kBigThreads, big_smem, stream>>>(rows, nms_threshold, W, n_rows, keep);
-    } else {
-        nms_small_kernel<2><<<small_blocks, threads, 0, stream>>>(rows, nms_threshold, W, keep);
-        YB_CUDA_TRY(cudaFuncSetAttribute(nms_big_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem));
-        nms_big_kernel<2><<<big_blocks, kBigThreads, big_smem, stream>>>(rows, nms_threshold, W, n_rows, keep);
-    }
+#define YB_NMS_LAUNCH(M)                                                                                       \
+    do {                                                                                                       \
+        nms_small_kernel<M><<<small_blocks, threads, 0, stream>>>(rows, nms_threshold, conf_thr, sigma, W, keep); \
+        YB_CUDA_TRY(cudaFuncSetAttribute(nms_big_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int)big_smem));                                                      \
+        nms_big_kernel<M><<<big_blocks, kBigThreads, big_smem, stream>>>(rows, nms_threshold, conf_thr, sigma, W, \
+                                                                        n_rows, keep);                         \
+    } while (0)
+    if (iou_mode == 1) YB_NMS_LAUNCH(1);
+    else if (iou_mode == 2) YB_NMS_LAUNCH(2);
+    else YB_NMS_LAUNCH(3);
+#undef YB_NMS_LAUNCH
     YB_CUDA_TRY(cudaGetLastError());
     rc = exclusive_scan_u32(W.seg_kept, n_seg, W.out_start, W.scan_ws, stream);
     if (rc != 0) return rc;
@@ -490,6 +577,24 @@ extern "C" int yb_nms(const double* rows, const int64_t* row_offsets_, int64_t n
         YB_CUDA_TRY(cudaGetLastError());
     }
     return YB_OK;
+}
+
+extern "C" int yb_nms(const double* rows, const int64_t* row_offsets, int64_t n_rows, int64_t n_img,
+                      int class_num, double nms_threshold, int iou_mode, uint8_t* keep, double* out_rows,
+                      int64_t* out_offsets, int64_t* out_seg_offsets, void* workspace, size_t workspace_bytes,
+                      yb_stream_t stream) {
+    if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
+    return nms_impl(rows, row_offsets, n_rows, n_img, class_num, nms_threshold, iou_mode, 0.0, 1.0, keep,
+                    out_rows, out_offsets, out_seg_offsets, workspace, workspace_bytes, stream);
+}
+
+extern "C" int yb_soft_nms(const double* rows, const int64_t* row_offsets, int64_t n_rows, int64_t n_img,
+                           int class_num, double nms_threshold, double conf_threshold, double sigma,
+                           uint8_t* keep, double* out_rows, int64_t* out_offsets, int64_t* out_seg_offsets,
+                           void* workspace, size_t workspace_bytes, yb_stream_t stream) {
+    if (!(sigma != 0.0)) return YB_E_PARAM;
+    return nms_impl(rows, row_offsets, n_rows, n_img, class_num, nms_threshold, 3, conf_threshold, sigma, keep,
+                    out_rows, out_offsets, out_seg_offsets, workspace, workspace_bytes, stream);
 }
 
 extern "C" int yb_pairwise_iou(const double* a, int64_t na, int stride_a, const double* b, int64_t nb,

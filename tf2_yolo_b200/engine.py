@@ -225,7 +225,7 @@ def decode_batch_exact(preds, class_num=1, threshold=0.5, version=1, capacity=No
 
 
 def nms_batch(rows, row_offsets, class_num=1, nms_threshold=0.45, iou_mode=1, want_rows=True,
-              want_seg_offsets=False):
+              want_seg_offsets=False, soft=None):
     """Batched per-class NMS.  rows (R,7) f64 CUDA (R = capacity), row_offsets (n_img+1) i64
     CUDA.  Returns dict(keep u8[R], out_rows (R,7), out_offsets (n_img+1), seg_offsets)."""
     require_cuda(rows, row_offsets)
@@ -241,9 +241,14 @@ def nms_batch(rows, row_offsets, class_num=1, nms_threshold=0.45, iou_mode=1, wa
         seg = torch.empty(n_img * class_num + 1, dtype=_I64, device=dev) if want_seg_offsets else None
         ws_bytes = N.lib.yb_nms_workspace_bytes(R, n_img, class_num)
         ws = workspaces.get("nms", ws_bytes, dev)
-        N.check(N.lib.yb_nms(_ptr(rows), _ptr(row_offsets), R, n_img, class_num, float(nms_threshold),
-                             int(iou_mode), _ptr(keep), _ptr(out_rows), _ptr(out_offsets), _ptr(seg),
-                             _ptr(ws), ws_bytes, _stream()), "yb_nms")
+        if soft is not None:   # (conf_threshold, sigma): Gaussian soft-NMS
+            N.check(N.lib.yb_soft_nms(_ptr(rows), _ptr(row_offsets), R, n_img, class_num, float(nms_threshold),
+                                      float(soft[0]), float(soft[1]), _ptr(keep), _ptr(out_rows),
+                                      _ptr(out_offsets), _ptr(seg), _ptr(ws), ws_bytes, _stream()), "yb_soft_nms")
+        else:
+            N.check(N.lib.yb_nms(_ptr(rows), _ptr(row_offsets), R, n_img, class_num, float(nms_threshold),
+                                 int(iou_mode), _ptr(keep), _ptr(out_rows), _ptr(out_offsets), _ptr(seg),
+                                 _ptr(ws), ws_bytes, _stream()), "yb_nms")
     return dict(keep=keep[:R], out_rows=out_rows, out_offsets=out_offsets, seg_offsets=seg)
 
 

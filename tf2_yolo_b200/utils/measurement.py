@@ -51,12 +51,10 @@ def _to_dev(a, sl, dev, keep_f64):
 def _nms_args(nms_mode, nms_threshold):
     if nms_mode == 0:
         return math.inf, 1          # nothing is suppressed: pure grouping by class
-    if nms_mode == 1:
+    if nms_mode in (1, 2):
         return float(nms_threshold), 1
     if nms_mode == 3:
         return float(nms_threshold), 2
-    if nms_mode == 2:
-        raise NotImplementedError("Soft-NMS (nms_mode=2) is not on the CUDA path yet; no CPU fallback")
     raise ValueError(f"Invalid nms_mode: {nms_mode}")
 
 
@@ -65,7 +63,7 @@ class _Accumulated:
 
 
 def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold, iou_threshold,
-                max_per_img, version, process_group=None):
+                max_per_img, version, process_group=None, nms_sigma=0.5):
     if not torch.cuda.is_available():
         raise YoloB200Error("no CUDA device: tf2_yolo_b200 has no CPU fallback")
     if len(y_preds) == 0:
@@ -99,7 +97,8 @@ def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_thres
         preds = [_to_dev(p, sl, dev, False) for p in y_preds]
         gt_rows, gt_off = engine.decode_batch_exact([yt], C, 0.5, version)
         det_rows, det_off = engine.decode_batch_exact(preds, C, conf_threshold, version)
-        res = engine.nms_batch(det_rows, det_off, C, thr, iou_mode, want_seg_offsets=True)
+        res = engine.nms_batch(det_rows, det_off, C, thr, iou_mode, want_seg_offsets=True,
+                               soft=(conf_threshold, nms_sigma) if nms_mode == 2 else None)
         n_keep = int(res["out_offsets"][-1].item())
         dets = res["out_rows"][:n_keep].contiguous()
         best_iou, best_gt, counts = engine.map_match(gt_rows, gt_off, dets, res["out_offsets"], C)
@@ -143,7 +142,7 @@ def create_score_mat(y_trues, *y_preds,
     """Score matrix table: precision, recall, F1-score, gts and dets per class."""
     class_num = len(class_names)
     acc = _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold,
-                      iou_threshold, None, version, process_group)
+                      iou_threshold, None, version, process_group, nms_sigma)
     sc = acc.score.cpu().numpy().reshape(3, class_num)
     pp, tpp, tp = sc[0].astype(np.float64), sc[1].astype(np.float64), sc[2].astype(np.float64)
     denom_array = np.zeros((class_num, 2))
@@ -194,7 +193,7 @@ class PRfunc(object):
         self.class_names = class_names
 
         acc = _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold,
-                          iou_threshold, max_per_img, version, process_group)
+                          iou_threshold, max_per_img, version, process_group, nms_sigma)
         gts = [int(g) for g in acc.gts]
         dev = acc.conf.device
         table = np.concatenate([[0], np.cumsum(acc.gts)]).astype(np.int64)

@@ -95,7 +95,15 @@ def nms(xywhcp, class_num=1, nms_threshold=0.45, iou_mode=1):
     return r["out_rows"][:n].cpu().numpy()
 
 
-def soft_nms(xywhcp, class_num=1, nms_threshold=0.45, conf_threshold=0.5, sigma=0.5):
-    raise NotImplementedError(
-        "soft_nms (nms_mode=2) is not on the CUDA path yet (SURVEY.md 8f row 4); "
-        "there is deliberately no CPU fallback")
+def soft_nms(xywhcp, class_num=1,
+        nms_threshold=0.45, conf_threshold=0.5, sigma=0.5):
+    """Gaussian Soft-NMS of one image's rows (utils/tools.py:736-786)."""
+    xywhcp = np.asarray(xywhcp, dtype=np.float64)
+    if xywhcp.ndim != 2:
+        raise IndexError("too many indices for array: soft_nms needs (K, 7) rows from decode()")
+    dev = _device()
+    rows = torch.from_numpy(np.ascontiguousarray(xywhcp)).to(dev)
+    offsets = torch.tensor([0, rows.shape[0]], dtype=torch.int64, device=dev)
+    r = engine.nms_batch(rows, offsets, class_num, nms_threshold, 1, soft=(conf_threshold, sigma))
+    n = int(r["out_offsets"][-1].item())
+    return r["out_rows"][:n].cpu().numpy()

@@ -36,9 +36,9 @@ UNIT = "images/s"
 CONFIG_NAME = "v4-608"
 CONF_THR, NMS_THR, NMS_MODE = 0.5, 0.45, 2
 ROW_CAPACITY_PER_IMG = 4096
-# my kernels per step: loss 1 | decode: count, 3-kernel scan, emit | nms: classify, scan,
-# scatter, small, big, scan, emit
-LAUNCHES_PER_STEP = 1 + 5 + 7
+# my kernels per step: fused loss+decode-count 1 | decode: 3-kernel scan, emit | nms: classify,
+# scan, scatter, small, big, scan, emit   (--unfused: one more, the separate decode count)
+LAUNCHES_PER_STEP = 1 + 4 + 7
 
 
 def loss_algorithmic_bytes(cfg, batch):
@@ -218,6 +218,7 @@ def run_ours(args):
                           wh_reg_weight=0.01, ignore_thresh=0.6)
            for si, S in enumerate(cfg["grids"])]
     global_batch = batch * world
+    params = [f.params for f in fns]
     host_t = [torch.from_numpy(a).pin_memory() for a in cfg["y_trues"]]
     host_p = [torch.from_numpy(a).pin_memory() for a in cfg["y_preds"]]
     dev_t = [a.to(dev) for a in host_t]
@@ -231,12 +232,21 @@ def run_ours(args):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        loss, _, _ = fused_losses(fns, y_t, y_p, global_batch=global_batch, dpreds=dpreds)
-        if record:
+        if args.unfused:
+            loss, _, _ = fused_losses(fns, y_t, y_p, global_batch=global_batch, dpreds=dpreds)
+        else:   # loss fwd+grad and the decode counting pass share one read of y_pred
+            def mark():
+                if record:
+                    e1.record()
+                    loss_ev.append((e0, e1))
+            loss, _, _, _, offs = engine.loss_decode_fused(params, y_t, y_p, CONF_THR, global_batch=global_batch,
+                                                           dpreds=dpreds, rows=rows, split_hook=mark)
+        if record and args.unfused:
             e1.record()
             loss_ev.append((e0, e1))
         work = dist.all_reduce(loss, async_op=True) if world > 1 else None   # the only collective: 3 scalars
-        _, offs = engine.decode_batch(y_p, C, CONF_THR, 4, rows=rows)
+        if args.unfused:
+            _, offs = engine.decode_batch(y_p, C, CONF_THR, 4, rows=rows)
         res = engine.nms_batch(rows, offs, C, NMS_THR, NMS_MODE)
         if work is not None:
             work.wait()                       # NCCL ran beside decode/NMS; join it to this stream
@@ -319,6 +329,9 @@ def run_ours(args):
                 "workload": f"YOLOv4-608 (BASELINE configs[2]): 3 scales (19/38/76) x 3 anchors, 80 classes, "
                             f"batch {batch} per GPU; fused CIoU loss fwd+grad + decode(thr {CONF_THR}) + "
                             f"per-class DIoU-NMS(thr {NMS_THR})",
+                "fusion": "separate loss and decode launches" if args.unfused else
+                          "loss fwd+grad and the decode counting pass share one read of y_pred (yb_loss_decode_fused); "
+                          "roofline counts only the loss's algorithmic bytes",
                 "global_batch": batch * world, "per_gpu_batch": batch,
                 "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB read + {sum(d.numel() * 4 for d in dpreds) / 1e6:.0f} MB "
                              "written per step vs 126 MB L2",
@@ -331,8 +344,10 @@ def run_ours(args):
             "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h[0], "ms_per_step": e2e_ms,
                     "note": "pinned H2D of labels+heads, loss scalars + NMS survivors D2H; gradient stays on device"},
-            "gpu_launches": LAUNCHES_PER_STEP * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "loss_fwd_bwd_kernel<4>", "achieved": achieved, "peak": peak,
+            "gpu_launches": (LAUNCHES_PER_STEP + (1 if args.unfused else 0)) * args.steps,
+            "roofline": {"bound": "hbm",
+                         "kernel": "loss_fwd_bwd_kernel<4,false,%s>" % ("false" if args.unfused else "true"),
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(),
                          "algorithmic_bytes_per_launch": algo, "ms_per_launch": loss_ms, "peak_source": peak_src,
                          "kernel_share_of_step": loss_ms / ms},
@@ -352,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="separate loss and decode launches (y_pred read twice)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -27,6 +27,7 @@ typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
 #define YB_MAX_BOXES 16  /* anchors per cell */
 #define YB_MAX_SCALES 4  /* FPN outputs per fused loss launch */
 #define YB_LOSS_TERMS 8  /* doubles per scale in terms_out */
+#define YB_LOSS_METRICS 10 /* doubles per scale in metrics_out */
 
 enum {
     YB_OK = 0,
@@ -88,6 +89,17 @@ int yb_loss_fwd_bwd(const yb_loss_scale* scales_host, int n_scales, float* loss_
                     double* terms_out, void* workspace, size_t workspace_bytes,
                     yb_stream_t stream);
 
+/* Same launch, plus the in-training metrics of yolov{2,3,4}/metrics/yolo_metrics.py:9-115
+ * (wrap_obj_acc / wrap_mean_iou / wrap_class_acc / wrap_recall; v1 variant
+ * yolov1_5/metrics/yolo_metrics.py) computed in the SAME pass over the tensors (zero extra HBM
+ * traffic).  metrics_out: YB_LOSS_METRICS doubles per scale =
+ * [obj_acc, mean_iou, class_acc, recall,  cells with correct objectness, sum of best IoU over
+ * object cells, sum of obj, sum of class-argmax matches, recall true positives, n_cells]
+ * (the raw sums let a sharded batch combine ranks). */
+int yb_loss_fwd_bwd_metrics(const yb_loss_scale* scales_host, int n_scales, float* loss_out,
+                            double* terms_out, double* metrics_out, double recall_iou_threshold,
+                            void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
 /* Single-scale conveniences, one per reference package. */
 int yb_loss_v1_fwd_bwd(const float* y_true, const float* y_pred, int64_t n_cells,
                        float* loss_out, float* dpred, const yb_loss_params* p,
@@ -136,6 +148,23 @@ int yb_decode(const void* const* preds_host /* n_scales device pointers */,
               int64_t n_img, const yb_decode_params* p, double* rows,
               int64_t row_capacity, int64_t* row_offsets, void* workspace,
               size_t workspace_bytes, yb_stream_t stream);
+
+/* Fused evaluate-while-training step: the loss forward+gradient of yb_loss_fwd_bwd AND the
+ * decode of the same head outputs (yb_decode on scales[i].y_pred, float32, all scales holding the
+ * same images).  y_pred is streamed from HBM once for both: the decode counting pass runs on the
+ * tiles the loss kernel already staged in shared memory; only cells with hits are touched again
+ * to emit rows.  Results are identical to calling the two entry points separately.
+ * With row_offsets == NULL only the counting pass runs (the counts stay in decode_workspace);
+ * yb_decode_finish then scans them and emits the rows. */
+int yb_loss_decode_fused(const yb_loss_scale* scales_host, int n_scales, float* loss_out,
+                         double* terms_out, double decode_threshold, double* rows,
+                         int64_t row_capacity, int64_t* row_offsets, void* loss_workspace,
+                         size_t loss_workspace_bytes, void* decode_workspace,
+                         size_t decode_workspace_bytes, yb_stream_t stream);
+
+int yb_decode_finish(const void* const* preds_host, int64_t n_img, const yb_decode_params* p,
+                     double* rows, int64_t row_capacity, int64_t* row_offsets, void* workspace,
+                     size_t workspace_bytes, yb_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Per-class greedy NMS / DIoU-NMS: utils/tools.py:687-733 (nms) with the

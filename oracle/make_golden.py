@@ -205,9 +205,34 @@ def gen_map():
     print("map.npz ok")
 
 
+def gen_metrics():
+    rng = np.random.default_rng(505)
+    pack = {}
+    names = []
+    plan = [("v4", 4, [4, 8], 3, 6, synth.ANCHORS_V4[3:9]), ("v3", 3, [4, 8], 3, 6, synth.ANCHORS_V3[3:9]),
+            ("v2", 2, [6], 5, 4, synth.ANCHORS_V2), ("v1", 1, [7], 2, 5, None)]
+    for name, ver, grids, B, C, anchors in plan:
+        y_trues, y_preds = small_grid_case(rng, ver, 4, grids, B, C, anchors if anchors is not None else synth.ANCHORS_V4)
+        if ver == 1:   # make some class predictions right
+            obj = y_trues[0][..., 4] == 1
+            y_preds[0][obj, -C:] = 0.5 * y_preds[0][obj, -C:] + 0.5 * y_trues[0][obj, 5:]
+        for si, s in enumerate(grids):
+            for thr in (0.5, 0.25):
+                n = f"{name}_s{s}_t{thr}"
+                names.append(n)
+                pack[n + "/meta"] = np.array(json.dumps(dict(version=ver, grid=s, B=B, C=C, thr=thr)))
+                pack[n + "/y_true"] = y_trues[si]
+                pack[n + "/y_pred"] = y_preds[si]
+                pack[n + "/metrics"] = refexec.reference_metrics(ver, y_trues[si], y_preds[si], (s, s), B, C, thr)
+    pack["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **pack)
+    print("metrics.npz:", len(names), "cases")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_losses()
     gen_decode_nms()
     gen_kmeans()
     gen_map()
+    gen_metrics()

@@ -194,3 +194,56 @@ def reference_loss(version, y_true, y_pred, dtype=torch.float64, **wrap_kwargs):
     loss = loss.reshape(()) if loss.numel() == 1 else loss
     loss.backward()
     return loss.detach().numpy().copy(), yp.grad.detach().numpy().copy()
+
+
+def load_metrics_module(version, dtype=torch.float64):
+    """Load yolov{1_5,2,3,4}/metrics/yolo_metrics.py verbatim over the TF shim (its
+    ``binary_accuracy`` import and ``from yolovX.losses import cal_iou`` are satisfied by shim
+    modules; cal_iou is the reference's own, from the verbatim loss file)."""
+    if not available():
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    _install_stubs()
+    pkg = {1: "yolov1_5", 2: "yolov2", 3: "yolov3", 4: "yolov4"}[version]
+    loss_mod = load_loss_module(version, dtype)
+    tf = make_tf_shim()
+    tf.reduce_max = lambda x, axis=None, keepdims=False: (x.max() if axis is None
+                                                          else x.max(dim=axis, keepdim=keepdims).values)
+    km = types.ModuleType("tensorflow.keras.metrics")
+    km.binary_accuracy = lambda y_true, y_pred, threshold=0.5: (
+        (y_true == (y_pred > threshold).to(y_pred.dtype)).to(y_pred.dtype).mean(dim=-1))
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "tensorflow.keras.metrics", pkg, pkg + ".losses")}
+    sys.modules["tensorflow"] = tf
+    sys.modules["tensorflow.keras.metrics"] = km
+    fake_pkg = types.ModuleType(pkg)
+    fake_pkg.__path__ = []
+    fake_losses = types.ModuleType(pkg + ".losses")
+    fake_losses.cal_iou = loss_mod.cal_iou
+    sys.modules[pkg] = fake_pkg
+    sys.modules[pkg + ".losses"] = fake_losses
+    try:
+        path = os.path.join(REFERENCE_ROOT, pkg, "metrics", "yolo_metrics.py")
+        spec = importlib.util.spec_from_file_location(f"yb_ref_{pkg}_metrics", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    mod.tf = tf
+    return mod
+
+
+def reference_metrics(version, y_true, y_pred, grid_shape, bbox_num, class_num, iou_threshold=0.5,
+                      dtype=torch.float64):
+    """[obj_acc, mean_iou, class_acc, recall] of the verbatim reference closures (Keras reduces a
+    per-sample metric tensor by its mean, which is what obj_acc needs)."""
+    mod = load_metrics_module(version, dtype)
+    yt = torch.as_tensor(np.asarray(y_true), dtype=dtype)
+    yp = torch.as_tensor(np.asarray(y_pred), dtype=dtype)
+    fns = [mod.wrap_obj_acc(grid_shape, bbox_num, class_num),
+           mod.wrap_mean_iou(grid_shape, bbox_num, class_num),
+           mod.wrap_class_acc(grid_shape, class_num) if version == 1 else mod.wrap_class_acc(grid_shape, bbox_num, class_num),
+           mod.wrap_recall(grid_shape, bbox_num, class_num, iou_threshold=iou_threshold)]
+    return np.array([float(torch.as_tensor(f(yt, yp), dtype=dtype).mean()) for f in fns])

@@ -183,3 +183,25 @@ def test_grid_iou_entry():
     assert np.allclose(iou.cpu().numpy(), ri.numpy(), rtol=1e-5, atol=1e-6)
     obj = cfg["y_trues"][0][..., 4] == 1      # CIoU is only defined where a label box exists
     assert np.allclose(ciou.cpu().numpy()[obj], rc.numpy()[obj], rtol=1e-5, atol=1e-6)
+
+
+def test_fused_loss_decode_equals_separate_calls():
+    """yb_loss_decode_fused: y_pred read once; loss, gradient and decoded rows identical to the two calls."""
+    for name, ver, thr in (("v4-608", 4, 0.5), ("v3-416", 3, 0.3), ("v2-416", 2, 0.4)):
+        cfg = synth.make_config(name, batch=5, seed=61)
+        B, C = cfg["bbox_num"], cfg["class_num"]
+        fns = []
+        for si, S in enumerate(cfg["grids"]):
+            kw = dict(anchors=cfg["anchors"][si * B:(si + 1) * B])
+            kw["loss_weight"] = [1, 5, 1] if ver == 4 else [1, 1, 5, 1]
+            fns.append(wrap(ver)((S, S), B, C, **kw))
+        yts = [torch.from_numpy(a).cuda() for a in cfg["y_trues"]]
+        yps = [torch.from_numpy(a).cuda() for a in cfg["y_preds"]]
+        loss0, d0, _ = fused_losses(fns, yts, yps)
+        rows0, off0 = engine.decode_batch(yps, C, thr, ver, capacity=5 * 4096)
+        loss1, d1, _, rows1, off1 = engine.loss_decode_fused([f.params for f in fns], yts, yps, thr, capacity=5 * 4096)
+        assert torch.equal(loss0, loss1)
+        assert all(torch.equal(a, b) for a, b in zip(d0, d1))
+        assert torch.equal(off0, off1)
+        n = int(off0[-1])
+        assert n > 0 and torch.equal(rows0[:n], rows1[:n])

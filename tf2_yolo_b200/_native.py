@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libyolo_b200.so")
 YB_MAX_BOXES = 16
 YB_MAX_SCALES = 4
 YB_LOSS_TERMS = 8
+YB_LOSS_METRICS = 10
 YB_DIST_IOU, YB_DIST_EUCLID = 0, 1
 
 
@@ -71,6 +72,7 @@ SIGNATURES = {
     "yb_status_string": (C.c_char_p, [C.c_int]),
     "yb_loss_workspace_bytes": (_sz, [_i32]),
     "yb_loss_fwd_bwd": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _vp, _sz, _vp]),
+    "yb_loss_fwd_bwd_metrics": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _vp, _dbl, _vp, _sz, _vp]),
     "yb_loss_v1_fwd_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.POINTER(LossParams), _vp, _sz, _vp]),
     "yb_loss_v2_fwd_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.POINTER(LossParams), _vp, _sz, _vp]),
     "yb_loss_v3_fwd_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp, C.POINTER(LossParams), _vp, _sz, _vp]),
@@ -78,6 +80,9 @@ SIGNATURES = {
     "yb_grid_iou": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "yb_decode_workspace_bytes": (_sz, [C.POINTER(DecodeParams), _i64]),
     "yb_decode": (C.c_int, [C.POINTER(_vp), _i64, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _sz, _vp]),
+    "yb_loss_decode_fused": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _dbl, _vp, _i64, _vp, _vp, _sz,
+                                       _vp, _sz, _vp]),
+    "yb_decode_finish": (C.c_int, [C.POINTER(_vp), _i64, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _sz, _vp]),
     "yb_nms_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "yb_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_soft_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -16,26 +16,10 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "decode_internal.cuh"
 #include "scan.cuh"
 
 namespace yb {
-
-struct DecodeLaunch {
-    const void* preds[YB_MAX_SCALES];
-    int gh[YB_MAX_SCALES], gw[YB_MAX_SCALES], B[YB_MAX_SCALES];
-    int pcf[YB_MAX_SCALES];            // values per cell
-    long long cells[YB_MAX_SCALES];    // gh*gw
-    long long cell_base[YB_MAX_SCALES + 1];  // prefix of cells over scales (per image)
-    long long scale_base[YB_MAX_SCALES + 1]; // prefix of n_img*cells over scales
-    int n_scales, C, version;
-    long long n_img;
-    double thr;
-    // K1 tiling
-    int tile_cells[YB_MAX_SCALES];
-    int tile_base[YB_MAX_SCALES + 1];
-    int bulk_ok[YB_MAX_SCALES];
-    int stage_bytes;
-};
 
 template <typename T>
 __device__ __forceinline__ T mul_rn(T a, T b);
@@ -276,38 +260,71 @@ extern "C" size_t yb_decode_workspace_bytes(const yb_decode_params* p, int64_t n
            scan_workspace_bytes(total > 0 ? total : 1);
 }
 
+namespace yb {
+
+int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params* p, void* workspace,
+                 size_t workspace_bytes, DecodeLaunch& L, DecodeWs& ws) {
+    int rc = fill_decode(preds, n_img, p, L);
+    if (rc != YB_OK) return rc;
+    if (workspace == nullptr) return YB_E_NULL;
+    if (workspace_bytes < yb_decode_workspace_bytes(p, n_img) || ((uintptr_t)workspace & 255))
+        return YB_E_WORKSPACE;
+    const long long total = L.n_img * L.cell_base[L.n_scales];
+    ws.total_cells = total;
+    ws.n_hot = reinterpret_cast<unsigned int*>(workspace);
+    ws.counts = reinterpret_cast<unsigned int*>((char*)workspace + 256);
+    ws.offsets = reinterpret_cast<long long*>((char*)ws.counts + decode_counts_bytes(total));
+    ws.hot = reinterpret_cast<long long*>((char*)ws.offsets + decode_offsets_bytes(total));
+    ws.scan_ws = (char*)ws.hot + decode_hot_bytes(total);
+    return YB_OK;
+}
+
+int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double* rows, long long cap,
+                  long long* row_offsets, cudaStream_t stream) {
+    int rc = exclusive_scan_u32(ws.counts, ws.total_cells, ws.offsets, ws.scan_ws, stream);
+    if (rc != 0) return rc;
+    const size_t esz = is_f64 ? 8 : 4;
+    const int threads = 256;
+    const int blocks2 = kNumSMs * 8;
+    int max_pcf = 0;
+    for (int s = 0; s < L.n_scales; ++s) max_pcf = max(max_pcf, L.pcf[s]);
+    int buf_elems = (max_pcf + 3) / 4 * 4;
+    if ((size_t)buf_elems * esz * (threads / 32) > 24 * 1024) buf_elems = 0;  // fat cells: read in place
+    const size_t smem2 = (size_t)buf_elems * esz * (threads / 32);
+    if (is_f64)
+        decode_emit_kernel<double><<<blocks2, threads, smem2, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
+                                                                        row_offsets, buf_elems);
+    else
+        decode_emit_kernel<float><<<blocks2, threads, smem2, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
+                                                                       row_offsets, buf_elems);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace yb
+
 extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decode_params* p, double* rows,
                          int64_t row_capacity, int64_t* row_offsets, void* workspace,
                          size_t workspace_bytes, yb_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    DecodeLaunch L;
-    int rc = fill_decode(preds, n_img, p, L);
-    if (rc != YB_OK) return rc;
-    if (row_offsets == nullptr || workspace == nullptr) return YB_E_NULL;
+    if (row_offsets == nullptr) return YB_E_NULL;
     if (rows == nullptr && row_capacity > 0) return YB_E_NULL;
     if (row_capacity < 0) return YB_E_CAPACITY;
-    if (workspace_bytes < yb_decode_workspace_bytes(p, n_img) || ((uintptr_t)workspace & 255))
-        return YB_E_WORKSPACE;
-    const long long total = L.n_img * L.cell_base[L.n_scales];
-    if (total == 0) {
+    DecodeLaunch L;
+    DecodeWs ws;
+    int rc = decode_setup(preds, n_img, p, workspace, workspace_bytes, L, ws);
+    if (rc != YB_OK) return rc;
+    if (ws.total_cells == 0) {
         YB_CUDA_TRY(cudaMemsetAsync(row_offsets, 0, sizeof(int64_t) * (n_img + 1), stream));
         return YB_OK;
     }
-    unsigned int* n_hot = reinterpret_cast<unsigned int*>(workspace);
-    unsigned int* counts = reinterpret_cast<unsigned int*>((char*)workspace + 256);
-    long long* offsets = reinterpret_cast<long long*>((char*)counts + decode_counts_bytes(total));
-    long long* hot = reinterpret_cast<long long*>((char*)offsets + decode_offsets_bytes(total));
-    void* scan_ws = (char*)hot + decode_hot_bytes(total);
-
     // K1 geometry: 3 stages of <= 24 KB, 3 CTAs per SM
     const size_t esz = p->is_f64 ? 8 : 4;
     const int stage_budget = 24 * 1024;
-    int ncw = 1, n_tiles = 0, stage_bytes = 0;
+    int ncw = 1, stage_bytes = 0;
     for (int s = 0; s < L.n_scales; ++s) {
         const int cb = (int)(L.pcf[s] * esz);
         if (4 * cb > 72 * 1024) return YB_E_SHAPE;
-        const int cpw = 32 / min(L.B[s], 32);
-        if (cpw < 1) return YB_E_SHAPE;
+        const int cpw = 32 / L.B[s];
         int t = stage_budget / cb / 4 * 4;
         t = min(t, kDecMaxConsumerWarps * cpw / 4 * 4);
         t = max(4, t);
@@ -317,35 +334,40 @@ extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decod
         stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
         ncw = max(ncw, min(kDecMaxConsumerWarps, (t + cpw - 1) / cpw));
     }
-    n_tiles = L.tile_base[L.n_scales];
+    const int n_tiles = L.tile_base[L.n_scales];
     L.stage_bytes = stage_bytes;
     const size_t smem = (size_t)kDecStages * stage_bytes;
     const int ctas_per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 2048))));
     const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
     const int threads1 = (ncw + 1) * 32;
-    YB_CUDA_TRY(cudaMemsetAsync(n_hot, 0, sizeof(unsigned int), stream));
+    YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, sizeof(unsigned int), stream));
     if (p->is_f64) {
         YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot);
+        decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, ws.counts, ws.n_hot, ws.hot);
     } else {
         YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot);
+        decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, ws.counts, ws.n_hot, ws.hot);
     }
     YB_CUDA_TRY(cudaGetLastError());
-    rc = exclusive_scan_u32(counts, total, offsets, scan_ws, stream);
-    if (rc != 0) return rc;
-    const int threads = 256;
-    const int blocks2 = kNumSMs * 8;
-    int max_pcf = 0;
-    for (int s = 0; s < L.n_scales; ++s) max_pcf = max(max_pcf, L.pcf[s]);
-    int buf_elems = (max_pcf + 3) / 4 * 4;
-    if ((size_t)buf_elems * esz * (threads / 32) > 24 * 1024) buf_elems = 0;  // fat cells: read in place
-    const size_t smem2 = (size_t)buf_elems * esz * (threads / 32);
-    if (p->is_f64)
-        decode_emit_kernel<double><<<blocks2, threads, smem2, stream>>>(
-            L, n_hot, hot, offsets, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), buf_elems);
-    else
-        decode_emit_kernel<float><<<blocks2, threads, smem2, stream>>>(
-            L, n_hot, hot, offsets, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), buf_elems);
-    return (int)cudaGetLastError();
+    return decode_finish(L, ws, p->is_f64 != 0, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream);
+}
+
+// Second half of a split decode: the per-cell counts and the hot-cell list are already in
+// `workspace` (left there by yb_loss_decode_fused called with row_offsets == NULL).
+extern "C" int yb_decode_finish(const void* const* preds, int64_t n_img, const yb_decode_params* p, double* rows,
+                                int64_t row_capacity, int64_t* row_offsets, void* workspace,
+                                size_t workspace_bytes, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (row_offsets == nullptr) return YB_E_NULL;
+    if (rows == nullptr && row_capacity > 0) return YB_E_NULL;
+    if (row_capacity < 0) return YB_E_CAPACITY;
+    DecodeLaunch L;
+    DecodeWs ws;
+    int rc = decode_setup(preds, n_img, p, workspace, workspace_bytes, L, ws);
+    if (rc != YB_OK) return rc;
+    if (ws.total_cells == 0) {
+        YB_CUDA_TRY(cudaMemsetAsync(row_offsets, 0, sizeof(int64_t) * (n_img + 1), stream));
+        return YB_OK;
+    }
+    return decode_finish(L, ws, p->is_f64 != 0, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream);
 }

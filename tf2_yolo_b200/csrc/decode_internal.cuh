@@ -1,0 +1,41 @@
+// Internal (not part of the C ABI): pieces of the decode pipeline shared with the fused
+// loss+decode launch in loss.cu.
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+struct DecodeLaunch {
+    const void* preds[YB_MAX_SCALES];
+    int gh[YB_MAX_SCALES], gw[YB_MAX_SCALES], B[YB_MAX_SCALES];
+    int pcf[YB_MAX_SCALES];            // values per cell
+    long long cells[YB_MAX_SCALES];    // gh*gw
+    long long cell_base[YB_MAX_SCALES + 1];  // prefix of cells over scales (per image)
+    long long scale_base[YB_MAX_SCALES + 1]; // prefix of n_img*cells over scales
+    int n_scales, C, version;
+    long long n_img;
+    double thr;
+    // K1 tiling
+    int tile_cells[YB_MAX_SCALES];
+    int tile_base[YB_MAX_SCALES + 1];
+    int bulk_ok[YB_MAX_SCALES];
+    int stage_bytes;
+};
+
+struct DecodeWs {          // carved out of the caller's decode workspace
+    unsigned int* n_hot;   // number of cells with hits
+    unsigned int* counts;  // hits per cell, OUTPUT order (image, scale, y, x)
+    long long* offsets;    // exclusive scan of counts (+ total)
+    long long* hot;        // work list of cells with hits
+    void* scan_ws;
+    long long total_cells;
+};
+
+// validate + fill L and ws (no launches).  Returns YB_OK / YB_E_*.
+int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params* p, void* workspace,
+                 size_t workspace_bytes, DecodeLaunch& L, DecodeWs& ws);
+// scan of the per-cell counts + emission of the rows (after counts / hot list are complete)
+int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double* rows, long long cap,
+                  long long* row_offsets, cudaStream_t stream);
+
+}  // namespace yb

@@ -26,13 +26,15 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "decode_internal.cuh"
 
 namespace yb {
 
 constexpr int kLossMaxConsumerWarps = 8;
 constexpr int kLossMaxThreads = (kLossMaxConsumerWarps + 1) * 32;
 constexpr int kMaxStages = 4;
-constexpr int kTerms = 5;
+constexpr int kTerms = 10;     // 5 loss terms + 5 in-training metric sums
+constexpr int kLossTerms = 5;
 constexpr float kEpsF = 1e-07f;
 constexpr double kEps = 1e-07;
 
@@ -55,7 +57,8 @@ struct LossScaleDev {
     float ignore_thr, truth_thr, label_smooth, gamma;
     int use_focal, use_scale;
     float inv_n;
-    double term_w[kTerms];  // weights combining the raw terms into the loss
+    float recall_thr;       // IoU threshold of the recall metric
+    double term_w[kLossTerms];  // weights combining the raw terms into the loss
     double inv_n_d;
 };
 
@@ -69,6 +72,15 @@ struct LossLaunch {
     unsigned int* counter;
     float* loss_out;       // [n_scales]
     double* terms_out;     // [n_scales][YB_LOSS_TERMS] or null
+    double* metrics_out;   // [n_scales][YB_LOSS_METRICS] or null
+    // fused decode counting (yb_loss_decode_fused): per-cell hit counts in decode OUTPUT order
+    unsigned int* dec_counts;
+    unsigned int* dec_n_hot;
+    long long* dec_hot;
+    long long dec_per_img;                   // cells per image over all scales
+    long long dec_cell_base[YB_MAX_SCALES];  // first cell of a scale inside an image
+    long long dec_cells[YB_MAX_SCALES];      // grid_h * grid_w
+    float dec_thr;
 };
 
 // ---- box geometry ------------------------------------------------------------
@@ -206,9 +218,33 @@ __device__ __forceinline__ void class_row(float* q, const float* t, float m, int
     }
 }
 
-template <int V>
+// first-index argmax of C floats by one warp (tf.argmax semantics)
+__device__ __forceinline__ int warp_argmax(const float* v, int C, int lane) {
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+    for (int k = lane; k < C; k += 32) {
+        const float x = v[k];
+        if (x > best || arg == 0x7fffffff) {
+            best = x;
+            arg = k;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (oa != 0x7fffffff && (arg == 0x7fffffff || ob > best || (ob == best && oa < arg))) {
+            best = ob;
+            arg = oa;
+        }
+    }
+    return arg;
+}
+
+template <int V, bool kMetrics, bool kDecode>
 __global__ void __launch_bounds__(kLossMaxThreads)
 loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
+    constexpr int kAcc = kMetrics ? kTerms : kLossTerms;  // per-thread accumulators
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -217,8 +253,9 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
 
     unsigned char* ring = smem;
     double* s_acc = reinterpret_cast<double*>(smem + (size_t)n_stages * L.stage_bytes);
-    // s_acc: [kLossMaxConsumerWarps][YB_MAX_SCALES][kTerms]
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms);
+    // s_acc: [ncw][n_scales][kTerms]
+    const int n_sc = L.n_scales;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + ncw * n_sc * kTerms);
     uint64_t* done = full + kMaxStages;
     __shared__ int s_is_last;
 
@@ -229,7 +266,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms; i += blockDim.x) s_acc[i] = 0.0;
+    for (int i = tid; i < ncw * n_sc * kTerms; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
 
     const int n_my = (L.total_tiles > (int)blockIdx.x)
@@ -293,18 +330,18 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
         if (lane == 0) bulk_wait_all<0>();
     } else {
         // ===================== consumer warps =====================
-        double acc[kTerms];
+        double acc[kAcc];
 #pragma unroll
-        for (int k = 0; k < kTerms; ++k) acc[k] = 0.0;
+        for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
         int cur = -1;
         int cpw = 0, lc = 0, lb = 0;  // cells per warp, this lane's local cell / box
         bool lane_on = false;
         float aw = 1.f, ah = 1.f;
         auto flush = [&](int s) {
 #pragma unroll
-            for (int k = 0; k < kTerms; ++k) {
+            for (int k = 0; k < kAcc; ++k) {
                 const double v = warp_sum(acc[k]);
-                if (lane == 0) s_acc[(warp * YB_MAX_SCALES + s) * kTerms + k] += v;
+                if (lane == 0) s_acc[(warp * n_sc + s) * kTerms + k] += v;
                 acc[k] = 0.0;
             }
         };
@@ -360,6 +397,55 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     }
                 }
                 const float resp = (lb == amax) ? 1.f : 0.f;
+                if (kDecode) {
+                    // head decode, counting pass (utils/tools.py:411-412), on the tile that is already in
+                    // shared memory: hits of c*p_k >= thr per cell, stored in decode OUTPUT order, cells
+                    // with hits appended to the emit work list.  Must precede the in-place gradient writes.
+                    int n = 0;
+                    if (valid) {
+                        const float* prob = (V == 1) ? sp + cell * S.pcf + 5 * B : pc + 5;
+#pragma unroll 4
+                        for (int k = 0; k < C; ++k) n += (__fmul_rn(c, prob[k]) >= L.dec_thr) ? 1 : 0;
+                    }
+                    int tot = 0;
+                    for (int q = 0; q < B; ++q) tot += __shfl_sync(0xffffffffu, n, lc * B + q);
+                    if (valid && lb == 0) {
+                        const long long g = cell0 + cell;
+                        const long long img = g / L.dec_cells[s];
+                        const long long o = img * L.dec_per_img + L.dec_cell_base[s] + (g - img * L.dec_cells[s]);
+                        L.dec_counts[o] = (unsigned)tot;
+                        if (tot > 0) L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = o;
+                    }
+                }
+                if (kMetrics) {
+                    // In-training metrics of yolov*/metrics/yolo_metrics.py folded into this pass (they
+                    // read the same tensors): objectness accuracy, mean best IoU, class accuracy, recall.
+                    float cmax = __shfl_sync(0xffffffffu, c, lc * B);
+                    for (int q = 1; q < B; ++q) cmax = fmaxf(cmax, __shfl_sync(0xffffffffu, c, lc * B + q));
+                    if (valid && lb == 0) {
+                        acc[kAcc - 5] += (obj == ((cmax > 0.5f) ? 1.f : 0.f)) ? 1.0 : 0.0;
+                        acc[kAcc - 4] += (double)(best * obj);
+                        acc[kAcc - 3] += (double)obj;
+                    }
+                    float eq = 0.f;  // argmax(class scores) agrees with the label's class
+                    unsigned om = __ballot_sync(0xffffffffu, valid && obj != 0.f && (V != 1 || lb == 0));
+                    while (om) {
+                        const int src = __ffs(om) - 1;
+                        om &= om - 1;
+                        const int rc = __shfl_sync(0xffffffffu, cell, src);
+                        const int rb = __shfl_sync(0xffffffffu, lb, src);
+                        const float* q = (V == 1) ? sp + rc * S.pcf + 5 * B : sp + rc * S.pcf + rb * bstride + 5;
+                        const int ap = warp_argmax(q, C, lane);
+                        const int at = warp_argmax(st + rc * S.tcf + 5, C, lane);
+                        if (lane == src) eq = (ap == at) ? 1.f : 0.f;
+                    }
+                    if (V == 1) eq = __shfl_sync(0xffffffffu, eq, lc * B);  // per-cell class scores
+                    if (valid && (V != 1 || lb == 0)) acc[kAcc - 2] += (double)(eq * obj);
+                    float hit = iou * (eq * obj);
+                    float hmax = __shfl_sync(0xffffffffu, hit, lc * B);
+                    for (int q = 1; q < B; ++q) hmax = fmaxf(hmax, __shfl_sync(0xffffffffu, hit, lc * B + q));
+                    if (valid && lb == 0) acc[kAcc - 1] += (hmax >= S.recall_thr) ? 1.0 : 0.0;
+                }
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
                 float pos = 0.f;
                 if (valid) {
@@ -513,11 +599,11 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
 
     // ---- CTA partials -> global, last CTA reduces in a fixed order ------------
     __syncthreads();
-    const int n_vals = L.n_scales * kTerms;
+    const int n_vals = L.n_scales * kAcc;
     if (tid < n_vals) {
-        const int s = tid / kTerms, k = tid - s * kTerms;
+        const int s = tid / kAcc, k = tid - s * kAcc;
         double v = 0.0;
-        for (int w = 0; w < ncw; ++w) v += s_acc[(w * YB_MAX_SCALES + s) * kTerms + k];
+        for (int w = 0; w < ncw; ++w) v += s_acc[(w * n_sc + s) * kTerms + k];
         L.partials[(size_t)blockIdx.x * n_vals + tid] = v;
     }
     __threadfence();
@@ -526,27 +612,51 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
-    double* s_fin = s_acc;  // reuse: [n_vals]
+    double* s_fin = s_acc;  // reuse: [n_scales][kTerms]
     __syncthreads();
     for (int i = warp; i < n_vals; i += (int)(blockDim.x >> 5)) {
+        // each lane owns blocks lane, lane+32, ...: independent loads first (latency overlapped),
+        // then a fixed-order sum -> deterministic
         double v = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(&L.partials[(size_t)b * n_vals + i]);
+        for (int b0 = lane; b0 < (int)gridDim.x; b0 += 32 * 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int b = b0 + 32 * u;
+                t[u] = (b < (int)gridDim.x) ? __ldcg(&L.partials[(size_t)b * n_vals + i]) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += t[u];
+        }
         v = warp_sum(v);
-        if (lane == 0) s_fin[i] = v;
+        const int s = i / kAcc, k = i - s * kAcc;
+        if (lane == 0) s_fin[s * kTerms + k] = v;
     }
     __syncthreads();
     if (tid < L.n_scales) {
         const LossScaleDev& S = L.sc[tid];
         double total = 0.0;
-        for (int k = 0; k < kTerms; ++k) total += S.term_w[k] * s_fin[tid * kTerms + k];
+        for (int k = 0; k < kLossTerms; ++k) total += S.term_w[k] * s_fin[tid * kTerms + k];
         total *= S.inv_n_d;
         L.loss_out[tid] = (float)total;
         if (L.terms_out != nullptr) {
             double* o = L.terms_out + tid * YB_LOSS_TERMS;
             o[0] = total;
-            for (int k = 0; k < kTerms; ++k) o[1 + k] = s_fin[tid * kTerms + k] * S.inv_n_d;
+            for (int k = 0; k < kLossTerms; ++k) o[1 + k] = s_fin[tid * kTerms + k] * S.inv_n_d;
             o[6] = 0.0;
             o[7] = 0.0;
+        }
+        if (L.metrics_out != nullptr) {
+            const double* m = s_fin + tid * kTerms + kLossTerms;  // hits, sum best-IoU, sum obj, sum equal, tp
+            double* o = L.metrics_out + tid * YB_LOSS_METRICS;
+            const double cells = (double)S.n_cells;
+            const double eps = 1e-07;
+            o[0] = cells > 0 ? m[0] / cells : 0.0;                      // obj_acc
+            o[1] = m[1] / (m[2] + eps);                                // mean_iou
+            o[2] = m[3] / (m[2] * ((V == 1) ? 1.0 : (double)S.B) + eps);  // class_acc
+            o[3] = m[4] / (m[2] + eps);                                // recall
+            for (int k = 0; k < 5; ++k) o[4 + k] = m[k];               // raw sums (for sharded batches)
+            o[9] = cells;
         }
     }
     if (tid == 0) *L.counter = 0u;  // leave the workspace reusable
@@ -612,7 +722,8 @@ static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
     d.use_scale = (p.version == 2) ? 1 : p.use_scale;
     d.inv_n = (float)p.inv_batch;
     d.inv_n_d = p.inv_batch;
-    for (int k = 0; k < kTerms; ++k) d.term_w[k] = 0.0;
+    for (int k = 0; k < kLossTerms; ++k) d.term_w[k] = 0.0;
+    d.recall_thr = 0.5f;
     if (p.version == 4) {
         d.whw = p.wh_reg_weight;
         d.term_w[0] = p.loss_weight[0];
@@ -627,12 +738,21 @@ static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
     return YB_OK;
 }
 
+template <int V, bool kMetrics, bool kDecode>
+static int launch_loss_variant(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
+    YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V, kMetrics, kDecode>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loss_fwd_bwd_kernel<V, kMetrics, kDecode><<<grid, threads, smem, stream>>>(L);
+    return (int)cudaGetLastError();
+}
+
 template <int V>
 static int launch_loss(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
-    YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    loss_fwd_bwd_kernel<V><<<grid, threads, smem, stream>>>(L);
-    return (int)cudaGetLastError();
+    const bool m = L.metrics_out != nullptr, d = L.dec_counts != nullptr;
+    if (m && d) return launch_loss_variant<V, true, true>(L, grid, threads, smem, stream);
+    if (m) return launch_loss_variant<V, true, false>(L, grid, threads, smem, stream);
+    if (d) return launch_loss_variant<V, false, true>(L, grid, threads, smem, stream);
+    return launch_loss_variant<V, false, false>(L, grid, threads, smem, stream);
 }
 
 }  // namespace yb
@@ -645,9 +765,14 @@ extern "C" size_t yb_loss_workspace_bytes(int n_scales) {
     return loss_partials_bytes(n_scales) + 256;
 }
 
-extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float* loss_out,
-                               double* terms_out, void* workspace, size_t workspace_bytes,
-                               yb_stream_t stream_) {
+struct FusedDecode {   // optional: count decode hits inside the loss pass
+    const DecodeLaunch* L;
+    const DecodeWs* ws;
+};
+
+static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out, double* terms_out,
+                     double* metrics_out, double recall_iou_threshold, void* workspace,
+                     size_t workspace_bytes, yb_stream_t stream_, const FusedDecode* fd = nullptr) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (scales == nullptr || loss_out == nullptr || workspace == nullptr) return YB_E_NULL;
     if (n_scales < 1 || n_scales > YB_MAX_SCALES) return YB_E_SHAPE;
@@ -666,45 +791,51 @@ extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float*
         cell_bytes_max = max(cell_bytes_max, (L.sc[s].pcf + L.sc[s].tcf) * 4);
     }
 
-    // Ring geometry: by default 2 stages of ~27 KB and 4 CTAs per SM (for v3/v4 cells: 20 cells per
-    // tile = two consumer warps of 10 cells); fat cells get fewer CTAs per SM.
+    // Ring geometry: by default 2 stages and 4 CTAs per SM (for v3/v4 cells: 20 cells = 27.2 KB per
+    // stage, two consumer warps of 10 cells); fat cells get fewer CTAs per SM.  An SM has 228 KB of
+    // shared memory, every resident CTA costs its static + dynamic bytes + 1 KB.
     int n_stages = env_int("YB_LOSS_STAGES", 2);
     n_stages = max(2, min(kMaxStages, n_stages));
     int ctas_per_sm = max(1, min(8, env_int("YB_LOSS_CTAS_PER_SM", 4)));
     const int tile_env = env_int("YB_LOSS_TILE_CELLS", 0);
-    const size_t smem_cap = 227 * 1024;
-    const size_t fixed_smem = sizeof(double) * kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms +
-                              2 * kMaxStages * sizeof(uint64_t) + 1024 /* per-CTA reservation */ + 256;
-    int stage_budget = 0;
-    for (;;) {
-        const size_t per_cta = smem_cap / ctas_per_sm - fixed_smem;
-        stage_budget = (int)(per_cta / n_stages) / 128 * 128;
-        if (stage_budget >= 4 * cell_bytes_max) break;
-        if (ctas_per_sm > 1) {
-            --ctas_per_sm;
-        } else if (n_stages > 2) {
-            --n_stages;
-        } else {
-            return YB_E_SHAPE;  // 4 cells do not fit a stage: B*(5+C) too large
+    const size_t sm_smem = 228 * 1024, static_smem = 192;
+    auto acc_bytes = [&](int warps) { return sizeof(double) * warps * n_scales * kTerms; };
+    const size_t bar_bytes = 2 * kMaxStages * sizeof(uint64_t);
+    int total_tiles = 0, stage_bytes = 0, ncw = kLossMaxConsumerWarps;
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0 assumes the maximum warp count, pass 1 the real one
+        int stage_budget = 0;
+        for (;;) {
+            const size_t per_cta = sm_smem / ctas_per_sm - 1024 - static_smem - acc_bytes(ncw) - bar_bytes;
+            stage_budget = (int)(per_cta / n_stages) / 128 * 128;
+            if (stage_budget >= 4 * cell_bytes_max) break;
+            if (ctas_per_sm > 1) {
+                --ctas_per_sm;
+            } else if (n_stages > 2) {
+                --n_stages;
+            } else {
+                return YB_E_SHAPE;  // 4 cells do not fit a stage: B*(5+C) too large
+            }
         }
+        total_tiles = 0;
+        stage_bytes = 0;
+        int warps = 1;
+        for (int s = 0; s < n_scales; ++s) {
+            LossScaleDev& d = L.sc[s];
+            const int cb = (d.pcf + d.tcf) * 4;
+            const int cpw = 32 / d.B;                        // cells one consumer warp covers per pass
+            int t = stage_budget / cb / 4 * 4;
+            t = min(t, kLossMaxConsumerWarps * cpw / 4 * 4);  // one pass of the consumer warps
+            if (tile_env > 0) t = min(t, tile_env / 4 * 4);
+            t = max(4, t);
+            d.tile_cells = t;
+            d.n_tiles = (int)((d.n_cells + t - 1) / t);
+            d.tile_base = total_tiles;
+            total_tiles += d.n_tiles;
+            stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));  // 128 B-aligned stages
+            warps = max(warps, min(kLossMaxConsumerWarps, (t + cpw - 1) / cpw));
+        }
+        ncw = max(1, min(kLossMaxConsumerWarps, env_int("YB_LOSS_WARPS", warps)));
     }
-    int total_tiles = 0, stage_bytes = 0, ncw = 1;
-    for (int s = 0; s < n_scales; ++s) {
-        LossScaleDev& d = L.sc[s];
-        const int cb = (d.pcf + d.tcf) * 4;
-        const int cpw = 32 / d.B;                       // cells one consumer warp covers per pass
-        int t = stage_budget / cb / 4 * 4;
-        t = min(t, kLossMaxConsumerWarps * cpw / 4 * 4);  // one pass of the consumer warps
-        if (tile_env > 0) t = min(t, tile_env / 4 * 4);
-        t = max(4, t);
-        d.tile_cells = t;
-        d.n_tiles = (int)((d.n_cells + t - 1) / t);
-        d.tile_base = total_tiles;
-        total_tiles += d.n_tiles;
-        stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
-        ncw = max(ncw, min(kLossMaxConsumerWarps, (t + cpw - 1) / cpw));
-    }
-    ncw = max(1, min(kLossMaxConsumerWarps, env_int("YB_LOSS_WARPS", ncw)));
     L.total_tiles = total_tiles;
     L.stage_bytes = stage_bytes;
     L.n_stages = n_stages;
@@ -712,10 +843,21 @@ extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float*
     L.counter = reinterpret_cast<unsigned int*>((char*)workspace + loss_partials_bytes(n_scales));
     L.loss_out = loss_out;
     L.terms_out = terms_out;
+    L.metrics_out = metrics_out;
+    for (int s = 0; s < n_scales; ++s) L.sc[s].recall_thr = (float)recall_iou_threshold;
+    if (fd != nullptr) {
+        L.dec_counts = fd->ws->counts;
+        L.dec_n_hot = fd->ws->n_hot;
+        L.dec_hot = fd->ws->hot;
+        L.dec_per_img = fd->L->cell_base[n_scales];
+        for (int s = 0; s < n_scales; ++s) {
+            L.dec_cell_base[s] = fd->L->cell_base[s];
+            L.dec_cells[s] = fd->L->cells[s];
+        }
+        L.dec_thr = (float)fd->L->thr;
+    }
 
-    const size_t smem = (size_t)n_stages * stage_bytes +
-                        sizeof(double) * kLossMaxConsumerWarps * YB_MAX_SCALES * kTerms +
-                        2 * kMaxStages * sizeof(uint64_t);
+    const size_t smem = (size_t)n_stages * stage_bytes + acc_bytes(ncw) + bar_bytes;
     const int threads = (ncw + 1) * 32;
     int grid = min(max(total_tiles, 1), kNumSMs * ctas_per_sm);
     YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
@@ -725,6 +867,72 @@ extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float*
         case 3: return launch_loss<3>(L, grid, threads, smem, stream);
         default: return launch_loss<4>(L, grid, threads, smem, stream);
     }
+}
+
+extern "C" int yb_loss_fwd_bwd(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                               double* terms_out, void* workspace, size_t workspace_bytes,
+                               yb_stream_t stream) {
+    return loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, workspace, workspace_bytes, stream);
+}
+
+extern "C" int yb_loss_fwd_bwd_metrics(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                                       double* terms_out, double* metrics_out, double recall_iou_threshold,
+                                       void* workspace, size_t workspace_bytes, yb_stream_t stream) {
+    if (metrics_out == nullptr) return YB_E_NULL;
+    return loss_impl(scales, n_scales, loss_out, terms_out, metrics_out, recall_iou_threshold, workspace,
+                     workspace_bytes, stream);
+}
+
+// Loss fwd+grad AND head decode of the same head outputs: y_pred is read from HBM once for both.
+extern "C" int yb_loss_decode_fused(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                                    double* terms_out, double decode_threshold, double* rows,
+                                    int64_t row_capacity, int64_t* row_offsets, void* loss_workspace,
+                                    size_t loss_workspace_bytes, void* decode_workspace,
+                                    size_t decode_workspace_bytes, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (scales == nullptr) return YB_E_NULL;
+    if (n_scales < 1 || n_scales > YB_MAX_SCALES) return YB_E_SHAPE;
+    if (rows == nullptr && row_capacity > 0) return YB_E_NULL;
+    const bool count_only = row_offsets == nullptr;  // rows are emitted later by yb_decode_finish
+    if (row_capacity < 0) return YB_E_CAPACITY;
+    yb_decode_params dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.version = scales[0].p.version;
+    dp.class_num = scales[0].p.class_num;
+    dp.n_scales = n_scales;
+    dp.is_f64 = 0;
+    dp.threshold = decode_threshold;
+    const void* preds[YB_MAX_SCALES];
+    int64_t n_img = -1;
+    for (int s = 0; s < n_scales; ++s) {
+        const yb_loss_params& p = scales[s].p;
+        if (p.grid_h <= 0 || p.grid_w <= 0) return YB_E_SHAPE;
+        const int64_t cells = (int64_t)p.grid_h * p.grid_w;
+        if (scales[s].n_cells % cells != 0) return YB_E_SHAPE;
+        const int64_t n = scales[s].n_cells / cells;
+        if (n_img >= 0 && n != n_img) return YB_E_SHAPE;  // every scale must hold the same images
+        n_img = n;
+        if (p.class_num != dp.class_num || p.version != dp.version) return YB_E_PARAM;
+        dp.grid_h[s] = p.grid_h;
+        dp.grid_w[s] = p.grid_w;
+        dp.bbox_num[s] = p.bbox_num;
+        preds[s] = scales[s].y_pred;
+    }
+    DecodeLaunch DL;
+    DecodeWs ws;
+    int rc = decode_setup(preds, n_img, &dp, decode_workspace, decode_workspace_bytes, DL, ws);
+    if (rc != YB_OK) return rc;
+    if (ws.total_cells == 0) {
+        if (!count_only) YB_CUDA_TRY(cudaMemsetAsync(row_offsets, 0, sizeof(int64_t) * (n_img + 1), stream));
+        return loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes,
+                         stream_);
+    }
+    YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, sizeof(unsigned int), stream));
+    FusedDecode fd{&DL, &ws};
+    rc = loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes,
+                   stream_, &fd);
+    if (rc != YB_OK || count_only) return rc;
+    return decode_finish(DL, ws, false, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream);
 }
 
 static int loss_single(int version, const float* y_true, const float* y_pred, int64_t n_cells,

@@ -98,7 +98,7 @@ def make_loss_params(version, grid_shape, bbox_num, class_num, anchors=None, bin
 
 
 def loss_fwd_bwd(params, y_trues, y_preds, global_batch=None, want_grad=True, want_terms=False,
-                 dpreds=None):
+                 dpreds=None, want_metrics=False, recall_iou_threshold=0.5):
     """One fused launch over the scales in ``params``.
 
     y_trues[i]: (N, gh, gw, 5+C) fp32 CUDA; y_preds[i]: (N, gh, gw, B*(5+C)) fp32 CUDA.
@@ -140,9 +140,69 @@ def loss_fwd_bwd(params, y_trues, y_preds, global_batch=None, want_grad=True, wa
         terms = torch.empty((n, N.YB_LOSS_TERMS), dtype=_F64, device=dev) if want_terms else None
         ws_bytes = N.lib.yb_loss_workspace_bytes(n)
         ws = workspaces.get("loss", ws_bytes, dev)
+        if want_metrics:
+            metrics = torch.empty((n, N.YB_LOSS_METRICS), dtype=_F64, device=dev)
+            N.check(N.lib.yb_loss_fwd_bwd_metrics(scales, n, _ptr(loss), _ptr(terms), _ptr(metrics),
+                                                  float(recall_iou_threshold), _ptr(ws), ws_bytes, _stream()),
+                    "yb_loss_fwd_bwd_metrics")
+            return loss, (outs if want_grad else None), terms, metrics
         N.check(N.lib.yb_loss_fwd_bwd(scales, n, _ptr(loss), _ptr(terms), _ptr(ws), ws_bytes, _stream()),
                 "yb_loss_fwd_bwd")
     return loss, (outs if want_grad else None), terms
+
+
+def loss_decode_fused(params, y_trues, y_preds, threshold=0.5, global_batch=None, dpreds=None,
+                      capacity=None, rows=None, want_terms=False, split_hook=None):
+    """Loss forward+gradient and decode of the same head outputs, y_pred read from HBM once
+    (yb_loss_decode_fused).  Returns (loss [n], dpreds, terms, rows (capacity,7) f64, row_offsets)."""
+    n = len(params)
+    require_cuda(*y_trues, *y_preds)
+    dev = y_preds[0].device
+    scales = (N.LossScale * n)()
+    outs = []
+    n_img = y_preds[0].shape[0]
+    for i, (p, yt, yp) in enumerate(zip(params, y_trues, y_preds)):
+        if yt.dtype != torch.float32 or yp.dtype != torch.float32:
+            raise N.YoloB200Error("loss tensors must be float32")
+        cells_per_img = p.grid_h * p.grid_w
+        pcf = (5 * p.bbox_num + p.class_num) if p.version == 1 else p.bbox_num * (5 + p.class_num)
+        if yp.numel() != n_img * cells_per_img * pcf or yt.numel() != n_img * cells_per_img * (5 + p.class_num):
+            raise ValueError("every scale must hold the same images with matching grid / info sizes")
+        q = N.LossParams.from_buffer_copy(p)
+        q.inv_batch = 1.0 / float(global_batch if global_batch is not None else max(n_img, 1))
+        d = dpreds[i] if dpreds is not None else torch.empty_like(yp)
+        outs.append(d)
+        scales[i].y_true, scales[i].y_pred, scales[i].dpred = yt.data_ptr(), yp.data_ptr(), d.data_ptr()
+        scales[i].n_cells = n_img * cells_per_img
+        scales[i].p = q
+    dparams, _ = make_decode_params(y_preds, params[0].class_num, threshold, params[0].version)
+    if rows is not None:
+        capacity = rows.shape[0]
+    if capacity is None:
+        capacity = max(1024, 512 * n_img)
+    with torch.cuda.device(dev):
+        if rows is None:
+            rows = torch.empty((capacity, 7), dtype=_F64, device=dev)
+        offsets = torch.empty(n_img + 1, dtype=_I64, device=dev)
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        terms = torch.empty((n, N.YB_LOSS_TERMS), dtype=_F64, device=dev) if want_terms else None
+        lws_bytes = N.lib.yb_loss_workspace_bytes(n)
+        lws = workspaces.get("loss", lws_bytes, dev)
+        dws_bytes = N.lib.yb_decode_workspace_bytes(C.byref(dparams), n_img)
+        dws = workspaces.get("decode", dws_bytes, dev)
+        if split_hook is None:
+            N.check(N.lib.yb_loss_decode_fused(scales, n, _ptr(loss), _ptr(terms), float(threshold), _ptr(rows),
+                                               capacity, _ptr(offsets), _ptr(lws), lws_bytes, _ptr(dws), dws_bytes,
+                                               _stream()), "yb_loss_decode_fused")
+        else:   # two calls so that a timer can bracket the fused kernel alone (bench.py roofline)
+            N.check(N.lib.yb_loss_decode_fused(scales, n, _ptr(loss), _ptr(terms), float(threshold), None, 0, None,
+                                               _ptr(lws), lws_bytes, _ptr(dws), dws_bytes, _stream()),
+                    "yb_loss_decode_fused(count)")
+            split_hook()
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in y_preds])
+            N.check(N.lib.yb_decode_finish(ptrs, n_img, C.byref(dparams), _ptr(rows), capacity, _ptr(offsets),
+                                           _ptr(dws), dws_bytes, _stream()), "yb_decode_finish")
+    return loss, outs, terms, rows, offsets
 
 
 def grid_iou(box_true, box_pred, grid_shape, want_ciou=False):

@@ -103,13 +103,16 @@ class GridLoss:
 
 
 def fused_losses(loss_fns, y_trues, y_preds, global_batch=None, want_grad=True, want_terms=False,
-                 dpreds=None):
+                 dpreds=None, want_metrics=False, recall_iou_threshold=0.5):
     """All FPN scales of one train step in ONE launch (what Keras does with
     ``loss=[f0, f1, f2]`` in three).  Tensors must already be fp32 CUDA.
-    Returns (loss per scale [n] fp32 CUDA, dpreds, terms)."""
+    Returns (loss per scale [n] fp32 CUDA, dpreds, terms[, metrics]); with ``want_metrics`` the
+    in-training metrics (obj_acc, mean_iou, class_acc, recall + raw sums, per scale) come out of
+    the same pass."""
     return engine.loss_fwd_bwd([f.params for f in loss_fns], list(y_trues), list(y_preds),
                                global_batch=global_batch, want_grad=want_grad,
-                               want_terms=want_terms, dpreds=dpreds)
+                               want_terms=want_terms, dpreds=dpreds, want_metrics=want_metrics,
+                               recall_iou_threshold=recall_iou_threshold)
 
 
 def cal_iou_grid(xywh_true, xywh_pred, grid_shape, return_ciou=False):

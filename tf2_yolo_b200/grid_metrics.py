@@ -1,0 +1,87 @@
+"""Host-side mirror of the reference's in-training metrics
+(yolov{2,3,4}/metrics/yolo_metrics.py:9-115, yolov1_5/metrics/yolo_metrics.py):
+``wrap_obj_acc``, ``wrap_mean_iou``, ``wrap_class_acc``, ``wrap_recall``.
+
+All four are sums over the same ``y_true`` / ``y_pred`` the loss reads, so the CUDA loss kernel
+accumulates them in its own pass (yb_loss_fwd_bwd_metrics): use
+``fused_losses(..., want_metrics=True)`` in a train step for zero extra HBM traffic.  The
+closures below keep the reference's ``metric(y_true, y_pred)`` signature; the four metrics of
+one (y_true, y_pred) pair share a single forward-only launch (cached on tensor identity).
+
+``obj_acc`` returns the mean over all cells (the reference returns the per-cell tensor that
+Keras then averages).
+"""
+import numpy as np
+import torch
+
+from . import engine
+
+_KINDS = {"obj_acc": 0, "mean_iou": 1, "class_acc": 2, "recall": 3}
+_cache = {}
+
+
+def _key(t):
+    return (t.data_ptr(), t._version, tuple(t.shape), t.device.index)
+
+
+def _as_cuda(a):
+    if torch.is_tensor(a):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
+    if not t.is_cuda:
+        if not torch.cuda.is_available():
+            raise engine.N.YoloB200Error("no CUDA device: tf2_yolo_b200 has no CPU fallback")
+        t = t.cuda()
+    return t.detach().float().contiguous()
+
+
+def grid_metrics(version, y_true, y_pred, grid_shape, bbox_num, class_num, iou_threshold=0.5):
+    """[obj_acc, mean_iou, class_acc, recall, 5 raw sums, n_cells] float64 CUDA (one launch)."""
+    yt, yp = _as_cuda(y_true), _as_cuda(y_pred)
+    key = (version, tuple(grid_shape), bbox_num, class_num, float(iou_threshold), _key(yt), _key(yp))
+    hit = _cache.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    params = engine.make_loss_params(version, grid_shape, bbox_num, class_num)
+    _, _, _, metrics = engine.loss_fwd_bwd([params], [yt], [yp], want_grad=False, want_metrics=True,
+                                           recall_iou_threshold=iou_threshold)
+    _cache["last"] = (key, metrics[0])
+    return metrics[0]
+
+
+def _wrap(version, kind, grid_shape, bbox_num, class_num, iou_threshold=0.5):
+    def metric(y_true, y_pred):
+        host_in = not torch.is_tensor(y_pred)
+        m = grid_metrics(version, y_true, y_pred, grid_shape, bbox_num, class_num, iou_threshold)
+        out = m[_KINDS[kind]].float()
+        return out.cpu().numpy() if host_in else out
+    metric.__name__ = kind
+    return metric
+
+
+def make_module_functions(version):
+    def wrap_obj_acc(grid_shape, bbox_num, class_num):
+        """Wrapped objectness accuracy."""
+        return _wrap(version, "obj_acc", grid_shape, bbox_num, class_num)
+
+    def wrap_mean_iou(grid_shape, bbox_num, class_num):
+        """Wrapped mean IoU."""
+        return _wrap(version, "mean_iou", grid_shape, bbox_num, class_num)
+
+    def wrap_recall(grid_shape, bbox_num, class_num, iou_threshold=0.5):
+        """Wrapped bounding box recall."""
+        return _wrap(version, "recall", grid_shape, bbox_num, class_num, iou_threshold)
+
+    if version == 1:
+        def wrap_class_acc(grid_shape, class_num, bbox_num=None):
+            """Wrapped class accuracy (v1: per cell; ``bbox_num`` is inferred at call time)."""
+            def class_acc(y_true, y_pred):
+                b = bbox_num if bbox_num is not None else (np.shape(y_pred)[-1] - class_num) // 5
+                return _wrap(1, "class_acc", grid_shape, b, class_num)(y_true, y_pred)
+            return class_acc
+    else:
+        def wrap_class_acc(grid_shape, bbox_num, class_num):
+            """Wrapped class accuracy."""
+            return _wrap(version, "class_acc", grid_shape, bbox_num, class_num)
+    return wrap_obj_acc, wrap_mean_iou, wrap_class_acc, wrap_recall

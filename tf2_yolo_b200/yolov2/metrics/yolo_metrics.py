@@ -1,0 +1,7 @@
+"""In-training metrics of yolov2 -- mirrors /root/reference/yolov2/metrics/yolo_metrics.py; computed by
+the fused CUDA loss kernel's metric accumulators (see tf2_yolo_b200/grid_metrics.py)."""
+from ...grid_metrics import make_module_functions
+
+EPSILON = 1e-07
+
+wrap_obj_acc, wrap_mean_iou, wrap_class_acc, wrap_recall = make_module_functions(2)

@@ -275,6 +275,23 @@ int yb_pr_curve(const double* conf, const int32_t* cls, const int64_t* gt_id, co
                 int64_t* tp_cum, int64_t* tpp_cum, void* workspace, size_t workspace_bytes,
                 yb_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Label-side helpers.
+ * yb_down2x_labels: utils/tools.py:342-367 (down2xlabel): (n_img, gh, gw, channels) labels,
+ * float32 or float64, -> (n_img, gh/2, gw/2, channels) float64; a 2x2 block whose maximum obj
+ * flag equals 1 keeps its largest-area entry (first maximum, areas in the input dtype) with
+ * xy re-expressed in the coarser cell.  Odd grids are rejected (the reference raises).
+ * yb_column_sums: per-column sums of a (rows, cols) matrix in fp64 - the data-sized part of
+ * utils/tools.py:592-627 (get_class_weight).
+ * ---------------------------------------------------------------------- */
+int yb_down2x_labels(const void* labels, int is_f64, int64_t n_img, int grid_h, int grid_w,
+                     int channels, double* out, yb_stream_t stream);
+
+size_t yb_column_sums_workspace_bytes(int cols);
+
+int yb_column_sums(const void* data, int is_f64, int64_t rows, int cols, double* out,
+                   void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

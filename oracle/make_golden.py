@@ -229,6 +229,18 @@ def gen_metrics():
     print("metrics.npz:", len(names), "cases")
 
 
+def gen_labels():
+    """down2xlabel / get_class_weight fixtures (utils/tools.py:342-367, :592-627)."""
+    tools, _, _ = refexec.load_numpy_half()
+    rng = np.random.default_rng(606)
+    lab = synth.make_labels(rng, 3, [12], 5, synth.ANCHORS_V4, mean_boxes=14.0, dtype=np.float64)[0]
+    pack = {"lab": lab, "down64": tools.down2xlabel(lab), "down32": tools.down2xlabel(lab.astype(np.float32))}
+    for m in ("alpha", "log", "effective", "binary"):
+        pack["cw_" + m] = tools.get_class_weight(lab[..., 5:], method=m)
+    np.savez_compressed(os.path.join(OUT, "labels.npz"), **pack)
+    print("labels.npz ok")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_losses()
@@ -236,3 +248,4 @@ if __name__ == "__main__":
     gen_kmeans()
     gen_map()
     gen_metrics()
+    gen_labels()

@@ -74,4 +74,4 @@ def test_host_side_argument_validation_needs_no_gpu(lib):
     assert N.lib.yb_kmeans_assign(None, 10, 2, None, 9, 0, None, None, None, None, 0, None) == -1
     p = N.DecodeParams()
     p.version, p.class_num, p.n_scales = 9, 80, 1
-    assert N.lib.yb_decode((ctypes.c_void_p * 1)(1), 1, ctypes.byref(p), None, 0, None, None, 0, None) == -3
+    assert N.lib.yb_decode((ctypes.c_void_p * 1)(1), 1, ctypes.byref(p), None, 0, ctypes.c_void_p(8), None, 0, None) == -3

@@ -144,3 +144,20 @@ def test_soft_nms(golden):
         assert np.array_equal(tools.soft_nms(rows, 6, 0.45, cthr, sigma), ot.soft_nms(rows, 6, 0.45, cthr, sigma))
     rows = synth.make_dense_candidates(rng, 9000, 3)      # > 2048 per class: global-scratch path
     assert np.array_equal(tools.soft_nms(rows, 3, 0.5, 0.5, 0.5), ot.soft_nms(rows, 3, 0.5, 0.5, 0.5))
+
+
+def test_label_helpers(golden):
+    """down2xlabel and get_class_weight vs the reference fixtures (bit-exact / 1e-15)."""
+    z = golden("labels")
+    lab = z["lab"]
+    assert np.array_equal(tools.down2xlabel(lab), z["down64"])
+    assert np.array_equal(tools.down2xlabel(lab.astype(np.float32)), z["down32"])
+    assert np.array_equal(tools.down2xlabel(lab), synth.halve_labels(lab))
+    with pytest.raises(IndexError):
+        tools.down2xlabel(lab[:, :11])
+    for m in ("alpha", "log", "effective", "binary"):
+        assert np.allclose(tools.get_class_weight(lab[..., 5:], method=m), z["cw_" + m], rtol=1e-14, atol=0), m
+    big = synth.make_labels(np.random.default_rng(2), 16, [76], 80, synth.ANCHORS_V4)[0]   # fp32 labels
+    ref = big.astype(np.float64).reshape(-1, 85)[:, 5:].sum(axis=0)
+    got = engine.column_sums(torch.from_numpy(big[..., 5:].reshape(-1, 80).copy()).cuda()).cpu().numpy()
+    assert np.array_equal(got, ref)

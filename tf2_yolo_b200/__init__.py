@@ -20,6 +20,8 @@ HOT_PATH = {
     ("utils.tools", "nms"): ("tf2_yolo_b200.utils.tools", "nms"),
     ("utils.tools", "cal_iou"): ("tf2_yolo_b200.utils.tools", "cal_iou"),
     ("utils.tools", "soft_nms"): ("tf2_yolo_b200.utils.tools", "soft_nms"),
+    ("utils.tools", "down2xlabel"): ("tf2_yolo_b200.utils.tools", "down2xlabel"),
+    ("utils.tools", "get_class_weight"): ("tf2_yolo_b200.utils.tools", "get_class_weight"),
     ("utils.measurement", "soft_nms"): ("tf2_yolo_b200.utils.tools", "soft_nms"),
     ("utils.kmeans", "kmeans"): ("tf2_yolo_b200.utils.kmeans", "kmeans"),
     ("utils.kmeans", "iou_dist"): ("tf2_yolo_b200.utils.kmeans", "iou_dist"),

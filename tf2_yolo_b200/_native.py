@@ -91,6 +91,9 @@ SIGNATURES = {
     "yb_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "yb_kmeans_assign": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_minmax_f64": (C.c_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    "yb_down2x_labels": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "yb_column_sums_workspace_bytes": (_sz, [_i32]),
+    "yb_column_sums": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _sz, _vp]),
     "yb_map_match": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _vp]),
     "yb_map_accumulate_workspace_bytes": (_sz, [_i64, _i32]),
     "yb_map_accumulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i64, _vp, _vp, _vp, _vp, _vp,

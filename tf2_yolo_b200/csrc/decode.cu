@@ -285,7 +285,7 @@ int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double
     if (rc != 0) return rc;
     const size_t esz = is_f64 ? 8 : 4;
     const int threads = 256;
-    const int blocks2 = kNumSMs * 8;
+    const int blocks2 = kNumSMs * 32;  // ~one hot cell per warp; idle warps exit at once
     int max_pcf = 0;
     for (int s = 0; s < L.n_scales; ++s) max_pcf = max(max_pcf, L.pcf[s]);
     int buf_elems = (max_pcf + 3) / 4 * 4;

@@ -97,33 +97,38 @@ static __global__ void scan_apply(const unsigned int* __restrict__ in, long long
 }
 
 // small inputs (segment tables): the whole scan in one block, one launch
-static __global__ void scan_single_block(const unsigned int* __restrict__ in, long long n,
-                                         long long* __restrict__ out) {
+constexpr int kScanSmallItems = 16;
+static __global__ void __launch_bounds__(1024)
+scan_single_block(const unsigned int* __restrict__ in, long long n, long long* __restrict__ out) {
     __shared__ long long s_warp[32];
-    __shared__ long long s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (long long base = 0; base < n; base += (long long)blockDim.x * kScanItems) {
-        const long long i0 = base + (long long)threadIdx.x * kScanItems;
-        unsigned int item[kScanItems];
+    long long carry = 0;
+    for (long long base = 0; base < n; base += (long long)blockDim.x * kScanSmallItems) {
+        const long long i0 = base + (long long)threadIdx.x * kScanSmallItems;
+        unsigned int item[kScanSmallItems];
         long long v = 0;
+        if (i0 + kScanSmallItems <= n) {   // 64-byte aligned run: four 128-bit loads
+            const uint4* p = reinterpret_cast<const uint4*>(in + i0);
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
-            item[k] = (i0 + k < n) ? in[i0 + k] : 0u;
-            v += item[k];
+            for (int q = 0; q < kScanSmallItems / 4; ++q) {
+                const uint4 t = p[q];
+                item[4 * q] = t.x; item[4 * q + 1] = t.y; item[4 * q + 2] = t.z; item[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanSmallItems; ++k) item[k] = (i0 + k < n) ? in[i0 + k] : 0u;
         }
-        long long total;
-        long long ex = block_exclusive_scan(v, s_warp, total) + s_carry;
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) {
+        for (int k = 0; k < kScanSmallItems; ++k) v += item[k];
+        long long total;
+        long long ex = block_exclusive_scan(v, s_warp, total) + carry;
+#pragma unroll
+        for (int k = 0; k < kScanSmallItems; ++k) {
             if (i0 + k < n) out[i0 + k] = ex;
             ex += item[k];
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_carry += total;
-        __syncthreads();
+        carry += total;   // every thread tracks the same running total
     }
-    if (threadIdx.x == 0) out[n] = s_carry;
+    if (threadIdx.x == 0) out[n] = carry;
 }
 
 static inline size_t scan_workspace_bytes(long long n) {

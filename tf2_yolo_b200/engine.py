@@ -430,3 +430,35 @@ def pr_curve(conf, cls, gt_id, flag, gt_table_base, n_gt_total):
                                   int(n_gt_total), _ptr(order), _ptr(tp), _ptr(tpp), _ptr(ws), ws_bytes,
                                   _stream()), "yb_pr_curve")
     return order[:D], tp, tpp
+
+
+# --------------------------------------------------------------------------
+# label-side helpers
+# --------------------------------------------------------------------------
+def down2x_labels(labels):
+    """(N, gh, gw, ch) f32/f64 CUDA -> (N, gh/2, gw/2, ch) f64 CUDA (utils/tools.py:342-367)."""
+    require_cuda(labels)
+    if labels.dtype not in (torch.float32, _F64) or labels.dim() != 4:
+        raise N.YoloB200Error("labels must be a (N, gh, gw, ch) float32/float64 tensor")
+    n, gh, gw, ch = labels.shape
+    if gh % 2 or gw % 2:
+        raise IndexError("index out of bounds: down2xlabel needs even grid sizes (the reference raises here too)")
+    out = torch.empty((n, gh // 2, gw // 2, ch), dtype=_F64, device=labels.device)
+    with torch.cuda.device(labels.device):
+        N.check(N.lib.yb_down2x_labels(_ptr(labels), int(labels.dtype == _F64), n, gh, gw, ch, _ptr(out), _stream()),
+                "yb_down2x_labels")
+    return out
+
+
+def column_sums(data2d):
+    """(rows, cols) f32/f64 CUDA -> (cols,) f64 CUDA."""
+    require_cuda(data2d)
+    rows, cols = data2d.shape
+    dev = data2d.device
+    with torch.cuda.device(dev):
+        out = torch.empty(cols, dtype=_F64, device=dev)
+        ws_bytes = N.lib.yb_column_sums_workspace_bytes(cols)
+        ws = workspaces.get("colsum", ws_bytes, dev)
+        N.check(N.lib.yb_column_sums(_ptr(data2d), int(data2d.dtype == _F64), rows, cols, _ptr(out), _ptr(ws),
+                                     ws_bytes, _stream()), "yb_column_sums")
+    return out

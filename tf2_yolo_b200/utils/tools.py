@@ -36,6 +36,55 @@ decode_batch = engine.decode_batch_exact
 nms_batch = engine.nms_batch
 
 
+def down2xlabel(label_data):
+    """Downsample label by 2x (utils/tools.py:342-367): ndarray in, float64 ndarray out."""
+    dev = _device()
+    a = np.asarray(label_data)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return engine.down2x_labels(t).cpu().numpy()
+
+
+def get_class_weight(label_data, method="alpha"):
+    """Weight of every category (utils/tools.py:592-627).  The per-class sums over the label
+    tensor run on the GPU; the arithmetic on the C sums follows the reference on the host."""
+    dev = _device()
+    a = label_data if torch.is_tensor(label_data) else np.asarray(label_data)
+    n_cls = a.shape[-1]
+    if torch.is_tensor(a):
+        t = a.to(dev)
+        t = t if t.dtype in (torch.float32, torch.float64) else t.double()
+    else:
+        a = a if a.dtype in (np.float32, np.float64) else a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sums = engine.column_sums(t.reshape(-1, n_cls).contiguous()).cpu().numpy()
+    class_weight = []
+    if method != "alpha":
+        total = 1
+        for i in a.shape[:-1]:
+            total *= i
+        if method == "effective":
+            beta = (total - 1)/total
+    for i in range(n_cls):
+        samples_per_class = sums[i]
+        if method == "effective":
+            effective_num = 1 - np.power(beta, samples_per_class)
+            class_weight.append((1 - beta)/effective_num)
+        elif method == "binary":
+            class_weight.append(samples_per_class/(total - samples_per_class))
+        else:
+            class_weight.append(1/samples_per_class)
+    class_weight = np.array(class_weight)
+    if method == "log":
+        class_weight = np.log(total*class_weight)
+
+    if method != "binary":
+        class_weight = class_weight/np.sum(class_weight)*len(class_weight)
+
+    return class_weight
+
+
 def decode(*label_datas, class_num=1, threshold=0.5, version=1):
     """Decode the prediction (or label) grids of ONE image.
 

@@ -66,6 +66,9 @@ typedef struct yb_loss_params {
     float focal_gamma;               /* v4, v3 when use_focal */
     int32_t use_focal;               /* v3: use_focal_loss */
     int32_t use_scale;               /* v3: use_scale (v2: always 1) */
+    int32_t from_logits;             /* v3/v4 only: y_pred holds RAW head outputs; the kernel applies the
+                                        head transform of yolov4/models/__init__.py:42-60 (sigmoid xy/c/p,
+                                        anchor*exp wh) and returns dL/d(raw) */
     double inv_batch;                /* 1 / N of reduce_mean(axis=0); N = GLOBAL batch when sharded */
 } yb_loss_params;
 

@@ -243,3 +243,23 @@ def loss_and_grad(spec: GridLossSpec, y_true, y_pred, dtype=torch.float64, threa
     grad = yp.grad.detach().numpy()
     return (float(total.detach().reshape(-1)[0]), grad,
             {k: float(v.detach().reshape(-1)[0]) for k, v in terms.items()})
+
+
+def activate_head(raw, anchors, bbox_num, class_num):
+    """The v3/v4 head transform (yolov4/models/__init__.py:42-60, Anchor layer backbone.py:59-60):
+    sigmoid on xy / objectness / class scores, anchor * exp on wh; torch, differentiable."""
+    shp = raw.shape
+    z = raw.reshape(-1, bbox_num, 5 + class_num)
+    anc = torch.as_tensor(np.asarray(anchors, dtype=np.float64), dtype=raw.dtype).reshape(1, bbox_num, 2)
+    out = torch.cat([torch.sigmoid(z[..., 0:2]), torch.exp(z[..., 2:4]) * anc, torch.sigmoid(z[..., 4:])], dim=-1)
+    return out.reshape(shp)
+
+
+def loss_and_grad_from_logits(spec: GridLossSpec, y_true, raw, dtype=torch.float64):
+    """(loss, dL/d raw): the oracle loss composed with the head transform."""
+    yt = torch.as_tensor(np.asarray(y_true), dtype=dtype)
+    z = torch.as_tensor(np.asarray(raw), dtype=dtype).clone().requires_grad_(True)
+    act = activate_head(z, spec.anchors, spec.bbox_num, spec.class_num)
+    total = loss_terms(spec, yt, act)["total"]
+    total.reshape(-1)[0].backward()
+    return float(total.detach().reshape(-1)[0]), z.grad.detach().numpy()

@@ -205,3 +205,27 @@ def test_fused_loss_decode_equals_separate_calls():
         assert torch.equal(off0, off1)
         n = int(off0[-1])
         assert n > 0 and torch.equal(rows0[:n], rows1[:n])
+
+
+def test_from_logits_head_fusion():
+    """Raw head outputs in, d/d(raw) out: equals the oracle loss composed with sigmoid / anchor*exp."""
+    from tf2_yolo_b200.grid_loss import wrap_yolo_loss_from_logits
+    for ver, name in ((4, "v4-608"), (3, "v3-416")):
+        cfg = synth.make_config(name, batch=2, seed=71)
+        S, B, C = cfg["grids"][1], cfg["bbox_num"], cfg["class_num"]
+        anc = cfg["anchors"][B:2 * B]
+        act = cfg["y_preds"][1].astype(np.float64).reshape(-1, B, 5 + C)
+        raw = act.copy()                                   # invert the head transform of the synthetic outputs
+        raw[..., 0:2] = np.log(act[..., 0:2] / (1 - act[..., 0:2]))
+        raw[..., 4:] = np.log(act[..., 4:] / (1 - act[..., 4:]))
+        raw[..., 2:4] = np.log(act[..., 2:4] / anc[None])
+        raw = raw.reshape(cfg["y_preds"][1].shape).astype(np.float32)
+        kw = dict(anchors=anc, loss_weight=[1, 5, 1] if ver == 4 else [1, 1, 5, 1])
+        fn = wrap_yolo_loss_from_logits(ver, (S, S), B, C, **kw)
+        loss, grad = fn.value_and_grad(cfg["y_trues"][1], raw)
+        spec = ol.GridLossSpec(version=ver, grid_shape=(S, S), bbox_num=B, class_num=C, **kw)
+        l_ref, g_ref = ol.loss_and_grad_from_logits(spec, cfg["y_trues"][1], raw)
+        assert abs(float(loss) - l_ref) <= LOSS_RTOL * abs(l_ref), (ver, float(loss), l_ref)
+        check_grad(grad, g_ref, f"logits v{ver}")
+    with pytest.raises(ValueError):
+        wrap_yolo_loss_from_logits(2, (13, 13), 5, 20, anchors=synth.ANCHORS_V2)

@@ -37,6 +37,7 @@ class LossParams(C.Structure):
         ("focal_gamma", C.c_float),
         ("use_focal", C.c_int32),
         ("use_scale", C.c_int32),
+        ("from_logits", C.c_int32),
         ("inv_batch", C.c_double),
     ]
 

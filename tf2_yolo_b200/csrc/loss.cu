@@ -73,6 +73,7 @@ struct LossLaunch {
     float* loss_out;       // [n_scales]
     double* terms_out;     // [n_scales][YB_LOSS_TERMS] or null
     double* metrics_out;   // [n_scales][YB_LOSS_METRICS] or null
+    int from_logits;       // all scales: y_pred holds raw head outputs
     // fused decode counting (yb_loss_decode_fused): per-cell hit counts in decode OUTPUT order
     unsigned int* dec_counts;
     unsigned int* dec_n_hot;
@@ -197,12 +198,13 @@ __device__ __forceinline__ void focal_term(float e, float g, float& f, float& df
 // a handful of shuffles and the consumer warps never synchronise with each other - only with
 // the producer, through the full/done mbarriers of the stage.
 
-template <int V>
+template <int V, bool kLogits>
 __device__ __forceinline__ void class_row(float* q, const float* t, float m, int C, int lane, bool write,
                                           double lwc, double& part) {
     // cross-entropy over the C class scores of one responsible box (v2-v4) / object cell (v1)
     for (int k = lane; k < C; k += 32) {
-        const double p = (double)q[k], tk = (double)t[k];
+        const double p = kLogits ? 1.0 / (1.0 + exp(-(double)q[k])) : (double)q[k];
+        const double tk = (double)t[k];
         const double pc = fmin(fmax(p, kEps), 1.0 - kEps);
         const double band = (p >= kEps && p <= 1.0 - kEps) ? 1.0 : 0.0;
         double l, g;
@@ -214,7 +216,7 @@ __device__ __forceinline__ void class_row(float* q, const float* t, float m, int
             g = -(tk / pc - (1.0 - tk) / (1.0 - pc));
         }
         part -= (double)m * l;
-        if (write) q[k] = (float)(lwc * (double)m * g * band);
+        if (write) q[k] = (float)(lwc * (double)m * g * band * (kLogits ? p * (1.0 - p) : 1.0));
     }
 }
 
@@ -241,7 +243,9 @@ __device__ __forceinline__ int warp_argmax(const float* v, int C, int lane) {
     return arg;
 }
 
-template <int V, bool kMetrics, bool kDecode>
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+
+template <int V, bool kMetrics, bool kDecode, bool kLogits = false>
 __global__ void __launch_bounds__(kLossMaxThreads)
 loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
     constexpr int kAcc = kMetrics ? kTerms : kLossTerms;  // per-thread accumulators
@@ -384,6 +388,10 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                 if (valid) {
                     px = pc[0]; py = pc[1]; pw = pc[2]; ph = pc[3]; c = pc[4];
                     tx = tc[0]; ty = tc[1]; tw = tc[2]; th = tc[3]; obj = tc[4];
+                    if (kLogits) {  // head transform: sigmoid offsets / objectness, anchor * exp sizes
+                        px = sigmoidf_(px); py = sigmoidf_(py); c = sigmoidf_(c);
+                        pw = aw * expf(pw); ph = ah * expf(ph);
+                    }
                 }
                 const float iou = grid_iou_f32(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh);
                 // argmax over the boxes of the cell (first maximum, like tf.argmax)
@@ -561,6 +569,10 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                             }
                         }
                     }
+                    if (kLogits) {  // chain rule through the head transform
+                        g0 *= px * (1.f - px); g1 *= py * (1.f - py); g4 *= c * (1.f - c);
+                        g2 *= pw; g3 *= ph;
+                    }
                     if (write) {
                         pc[0] = g0; pc[1] = g1; pc[2] = g2; pc[3] = g3; pc[4] = g4;
                         // class scores of a non-responsible box get exactly zero gradient;
@@ -587,7 +599,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     float* q = (V == 1) ? sp + rc * S.pcf + 5 * B : sp + rc * S.pcf + rb * bstride + 5;
                     const float* t = st + rc * S.tcf + 5;
                     double part = 0.0;
-                    class_row<V>(q, t, m, C, lane, write, (double)S.lw[(V == 4) ? 2 : 3] * S.inv_n_d, part);
+                    class_row<V, kLogits>(q, t, m, C, lane, write, (double)S.lw[(V == 4) ? 2 : 3] * S.inv_n_d, part);
                     acc[(V == 4) ? 2 : 3] += part;
                 }
             }
@@ -746,9 +758,26 @@ static int launch_loss_variant(const LossLaunch& L, int grid, int threads, size_
     return (int)cudaGetLastError();
 }
 
+template <int V, bool kMetrics>
+static int launch_loss_logits(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
+    YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V, kMetrics, false, true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    loss_fwd_bwd_kernel<V, kMetrics, false, true><<<grid, threads, smem, stream>>>(L);
+    return (int)cudaGetLastError();
+}
+
 template <int V>
 static int launch_loss(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
     const bool m = L.metrics_out != nullptr, d = L.dec_counts != nullptr;
+    if (L.from_logits) {
+        if (V != 3 && V != 4) return YB_E_PARAM;  // v1/v2 heads end in a softmax
+        if (d) return YB_E_PARAM;                 // decode counting needs activated scores
+        if (V == 3 || V == 4) {
+            constexpr int W = (V == 3 || V == 4) ? V : 4;
+            return m ? launch_loss_logits<W, true>(L, grid, threads, smem, stream)
+                     : launch_loss_logits<W, false>(L, grid, threads, smem, stream);
+        }
+    }
     if (m && d) return launch_loss_variant<V, true, true>(L, grid, threads, smem, stream);
     if (m) return launch_loss_variant<V, true, false>(L, grid, threads, smem, stream);
     if (d) return launch_loss_variant<V, false, true>(L, grid, threads, smem, stream);
@@ -783,9 +812,11 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     memset(&L, 0, sizeof(L));
     L.n_scales = n_scales;
     const int version = scales[0].p.version;
+    L.from_logits = scales[0].p.from_logits ? 1 : 0;
     int cell_bytes_max = 0;
     for (int s = 0; s < n_scales; ++s) {
         if (scales[s].p.version != version) return YB_E_PARAM;
+        if ((scales[s].p.from_logits ? 1 : 0) != L.from_logits) return YB_E_PARAM;
         int rc = fill_scale(scales[s], L.sc[s]);
         if (rc != YB_OK) return rc;
         cell_bytes_max = max(cell_bytes_max, (L.sc[s].pcf + L.sc[s].tcf) * 4);

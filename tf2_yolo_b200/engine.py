@@ -64,7 +64,7 @@ workspaces = _WorkspacePool()
 def make_loss_params(version, grid_shape, bbox_num, class_num, anchors=None, binary_weight=1.0,
                      loss_weight=(1, 1, 1, 1), wh_reg_weight=0.01, ignore_thresh=0.6,
                      truth_thresh=1.0, label_smooth=0.0, focal_loss_gamma=2.0,
-                     use_focal_loss=False, use_scale=True):
+                     use_focal_loss=False, use_scale=True, from_logits=False):
     if version not in (1, 2, 3, 4):
         raise ValueError(f"Invalid version: {version}")
     if bbox_num > N.YB_MAX_BOXES:
@@ -93,6 +93,9 @@ def make_loss_params(version, grid_shape, bbox_num, class_num, anchors=None, bin
     p.focal_gamma = float(focal_loss_gamma)
     p.use_focal = int(bool(use_focal_loss))
     p.use_scale = int(bool(use_scale))
+    if from_logits and version not in (3, 4):
+        raise ValueError("from_logits is available for the v3/v4 heads (sigmoid scores); v1/v2 end in a softmax")
+    p.from_logits = int(bool(from_logits))
     p.inv_batch = 1.0
     return p
 

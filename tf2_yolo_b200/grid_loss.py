@@ -124,3 +124,18 @@ def cal_iou_grid(xywh_true, xywh_pred, grid_shape, return_ciou=False):
     bt = xywh_true.float().contiguous()
     bp = xywh_pred.float().contiguous()
     return engine.grid_iou(bt, bp, grid_shape, want_ciou=return_ciou)
+
+
+def wrap_yolo_loss_from_logits(version, grid_shape, bbox_num, class_num, **kwargs):
+    """Extension: the same loss with the head transform folded in.
+
+    ``yolo_loss(y_true, raw)`` takes the RAW outputs of the head's 1x1 convolutions
+    (yolov4/models/__init__.py:42-60 without the activations / Anchor layer / per-box Concatenate
+    re-ordering: layout [tx, ty, tw, th, tc, tp_0..tp_{C-1}] per box), applies sigmoid to
+    xy / objectness / class scores and ``anchor * exp`` to wh inside the kernel, and returns the
+    gradient with respect to the raw values - one read and one write of the head tensor instead
+    of the activation round trip.  v3 / v4 only; ``anchors`` are required; the anchors are the
+    constants the loss sees (not trainable through this entry point)."""
+    if kwargs.get("anchors") is None:
+        raise ValueError("from-logits needs the anchors of the scale")
+    return GridLoss(version, grid_shape, bbox_num, class_num, from_logits=True, **kwargs)

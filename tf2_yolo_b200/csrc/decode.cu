@@ -28,45 +28,6 @@ __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul
 template <>
 __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
 
-// count (and optionally emit) the hits of one cell; whole warp cooperates.
-template <typename T, bool kEmit>
-__device__ __forceinline__ int cell_hits(const T* __restrict__ cell, int B, int C, int version, T thr,
-                                         int lane, double* __restrict__ rows, long long row0,
-                                         long long cap, int xi, int yi, int gw, int gh) {
-    int n = 0;
-    const int bstride = (version == 1) ? 5 : 5 + C;
-    for (int b = 0; b < B; ++b) {
-        const T* box = cell + b * bstride;
-        const T c = box[4];
-        const T* prob = (version == 1) ? cell + 5 * B : box + 5;
-        for (int k0 = 0; k0 < C; k0 += 32) {
-            const int k = k0 + lane;
-            T p = 0;
-            bool hit = false;
-            if (k < C) {
-                p = prob[k];
-                hit = mul_rn<T>(c, p) >= thr;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (kEmit && hit) {
-                const long long r = row0 + n + __popc(m & ((1u << lane) - 1u));
-                if (r < cap) {
-                    double* o = rows + r * 7;
-                    o[0] = ((double)xi + (double)box[0]) / (double)gw;
-                    o[1] = ((double)yi + (double)box[1]) / (double)gh;
-                    o[2] = (double)box[2];
-                    o[3] = (double)box[3];
-                    o[4] = (double)c;
-                    o[5] = (double)k;
-                    o[6] = (double)p;
-                }
-            }
-            n += __popc(m);
-        }
-    }
-    return n;
-}
-
 // K1: persistent CTAs; a producer warp streams tiles of cells through a shared-memory
 // ring with 1-D bulk-async copies (TMA), consumer warps own whole cells (lane = cell*B + box),
 // each lane walks the C class scores of its box (lanes are an odd number of words apart ->
@@ -77,7 +38,7 @@ constexpr int kDecStages = 3;
 template <typename T>
 __global__ void __launch_bounds__((kDecMaxConsumerWarps + 1) * 32)
 decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __restrict__ counts,
-                    unsigned int* __restrict__ n_hot, long long* __restrict__ hot_cells) {
+                    unsigned int* __restrict__ n_hot, HotBox* __restrict__ hot_boxes) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[kDecStages], done[kDecStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -151,14 +112,18 @@ decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __rest
 #pragma unroll 4
                     for (int k = 0; k < C; ++k) n += (mul_rn<T>(c, prob[k]) >= thr) ? 1 : 0;
                 }
-                int tot = 0;
-                for (int q = 0; q < B; ++q) tot += __shfl_sync(0xffffffffu, n, lc * B + q);
-                if (valid && lb == 0) {
+                int tot = 0, before = 0;
+                for (int q = 0; q < B; ++q) {
+                    const int nq = __shfl_sync(0xffffffffu, n, lc * B + q);
+                    tot += nq;
+                    before += (q < lb) ? nq : 0;
+                }
+                if (valid) {
                     const long long g = cell0 + cell;
                     const long long img = g / L.cells[s];
                     const long long o = img * L.cell_base[L.n_scales] + L.cell_base[s] + (g - img * L.cells[s]);
-                    counts[o] = (unsigned)tot;
-                    if (tot > 0) hot_cells[atomicAdd(n_hot, 1u)] = o;
+                    if (lb == 0) counts[o] = (unsigned)tot;
+                    if (n > 0) hot_boxes[atomicAdd(n_hot, 1u)] = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
                 }
             }
             mbar_arrive(&done[stage]);
@@ -166,44 +131,76 @@ decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __rest
     }
 }
 
-// K2: one warp per cell that has hits (work list from K1): the cell is first copied to a
-// per-warp shared-memory buffer with independent coalesced loads (one DRAM round trip instead
-// of a dependent chain), then re-evaluated and its rows written in (box, class) order at the
-// scanned offset.
+// K2: eight lanes per box that has hits (work list from K1): the lanes take contiguous slices of
+// the box's C class scores (one coalesced read of the box, independent loads), count their hits,
+// prefix-sum across the group and write the rows, in class order, at
+// offsets[cell] + rows of the cell's earlier boxes.
+constexpr int kEmitGroup = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 decode_emit_kernel(const __grid_constant__ DecodeLaunch L, const unsigned int* __restrict__ n_hot,
-                   const long long* __restrict__ hot_cells, const long long* __restrict__ offsets,
-                   double* __restrict__ rows, long long cap, long long* __restrict__ row_offsets,
-                   int buf_elems) {
-    extern __shared__ __align__(16) unsigned char emit_smem[];
-    const int lane = threadIdx.x & 31;
-    T* buf = reinterpret_cast<T*>(emit_smem) + (size_t)(threadIdx.x >> 5) * buf_elems;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+                   const HotBox* __restrict__ hot_boxes, const long long* __restrict__ offsets,
+                   double* __restrict__ rows, long long cap, long long* __restrict__ row_offsets) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_threads = (long long)gridDim.x * blockDim.x;
     const long long per_img = L.cell_base[L.n_scales];
     const T thr = (T)L.thr;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i <= L.n_img;
-         i += (long long)gridDim.x * blockDim.x)
-        row_offsets[i] = offsets[i * per_img];
+    for (long long i = tid; i <= L.n_img; i += n_threads) row_offsets[i] = offsets[i * per_img];
     const long long n = *n_hot;
-    for (long long w = warp; w < n; w += n_warps) {
-        const long long o = hot_cells[w];  // output-order cell index
-        const long long img = o / per_img;
-        const long long rem = o - img * per_img;
-        int s = 0;
-        while (rem >= L.cell_base[s + 1]) ++s;
-        const long long cell = rem - L.cell_base[s];
-        const int yi = (int)(cell / L.gw[s]), xi = (int)(cell - (long long)yi * L.gw[s]);
-        const T* ptr = reinterpret_cast<const T*>(L.preds[s]) + (img * L.cells[s] + cell) * L.pcf[s];
-        const long long row0 = offsets[o];
-        if (L.pcf[s] <= buf_elems) {
-            __syncwarp();
-            for (int i = lane; i < L.pcf[s]; i += 32) buf[i] = ptr[i];
-            __syncwarp();
-            ptr = buf;
+    const int sub = threadIdx.x & (kEmitGroup - 1);
+    const long long n_groups = n_threads / kEmitGroup;
+    // whole warps iterate together (uniform trip count) so the group shuffles stay converged
+    const long long rounds = (n + n_groups - 1) / n_groups;
+    for (long long it = 0; it < rounds; ++it) {
+        const long long w = it * n_groups + tid / kEmitGroup;
+        const bool live = w < n;
+        HotBox hb = make_hot(0, 0, 0, 0, 0);
+        if (live) hb = hot_boxes[w];
+        const int s = (int)(hb.packed & 15u), b = (int)((hb.packed >> 4) & 63u);
+        const int C = L.C, B = L.B[s];
+        const T* cptr = reinterpret_cast<const T*>(L.preds[s]) + (size_t)hb.mem_idx * L.pcf[s];
+        const T* box = cptr + b * ((L.version == 1) ? 5 : 5 + C);
+        const T* prob = (L.version == 1) ? cptr + 5 * B : box + 5;
+        const int per = (C + kEmitGroup - 1) / kEmitGroup;
+        const int k0 = sub * per, k1 = min(C, k0 + per);
+        T c = 0;
+        long long r = 0;
+        if (live) {
+            c = box[4];
+            r = offsets[hb.out_idx] + (long long)(hb.packed >> 10);
         }
-        cell_hits<T, true>(ptr, L.B[s], L.C, L.version, thr, lane, rows, row0, cap, xi, yi, L.gw[s], L.gh[s]);
+        int cnt = 0;
+        if (live)
+            for (int k = k0; k < k1; ++k) cnt += (mul_rn<T>(c, prob[k]) >= thr) ? 1 : 0;
+        // exclusive prefix of cnt over the lanes of the group
+        int inc = cnt;
+#pragma unroll
+        for (int o = 1; o < kEmitGroup; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, o, kEmitGroup);
+            if (sub >= o) inc += v;
+        }
+        const int ex = inc - cnt;
+        if (live && cnt > 0) {
+            const unsigned cell = hb.mem_idx % (unsigned)L.cells[s];  // position inside the image
+            const int yi = (int)(cell / (unsigned)L.gw[s]), xi = (int)(cell - (unsigned)yi * (unsigned)L.gw[s]);
+            const double bx = ((double)xi + (double)box[0]) / (double)L.gw[s];
+            const double by = ((double)yi + (double)box[1]) / (double)L.gh[s];
+            const double bw = (double)box[2], bh = (double)box[3], bc = (double)c;
+            r += ex;
+            for (int k = k0; k < k1; ++k) {
+                const T p = prob[k];
+                if (mul_rn<T>(c, p) >= thr) {
+                    if (r < cap) {
+                        double* o = rows + r * 7;
+                        o[0] = bx; o[1] = by; o[2] = bw; o[3] = bh; o[4] = bc;
+                        o[5] = (double)k;
+                        o[6] = (double)p;
+                    }
+                    ++r;
+                }
+            }
+        }
     }
 }
 
@@ -246,17 +243,19 @@ static size_t decode_counts_bytes(long long total_cells) {
 static size_t decode_offsets_bytes(long long total_cells) {
     return align_up((size_t)(total_cells + 2) * sizeof(long long), 256);
 }
-static size_t decode_hot_bytes(long long total_cells) {
-    return align_up((size_t)(total_cells + 1) * sizeof(long long), 256);
+static size_t decode_hot_bytes(long long total_boxes) {
+    return align_up((size_t)(total_boxes + 1) * sizeof(HotBox), 256);
 }
 
 extern "C" size_t yb_decode_workspace_bytes(const yb_decode_params* p, int64_t n_img) {
     if (p == nullptr || n_img < 0) return 0;
-    long long per_img = 0;
-    for (int s = 0; s < p->n_scales && s < YB_MAX_SCALES; ++s)
+    long long per_img = 0, boxes_per_img = 0;
+    for (int s = 0; s < p->n_scales && s < YB_MAX_SCALES; ++s) {
         per_img += (long long)p->grid_h[s] * p->grid_w[s];
+        boxes_per_img += (long long)p->grid_h[s] * p->grid_w[s] * (p->bbox_num[s] > 0 ? p->bbox_num[s] : 1);
+    }
     const long long total = per_img * n_img;
-    return 256 + decode_counts_bytes(total) + decode_offsets_bytes(total) + decode_hot_bytes(total) +
+    return 256 + decode_counts_bytes(total) + decode_offsets_bytes(total) + decode_hot_bytes(boxes_per_img * n_img) +
            scan_workspace_bytes(total > 0 ? total : 1);
 }
 
@@ -270,12 +269,17 @@ int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params
     if (workspace_bytes < yb_decode_workspace_bytes(p, n_img) || ((uintptr_t)workspace & 255))
         return YB_E_WORKSPACE;
     const long long total = L.n_img * L.cell_base[L.n_scales];
+    for (int s = 0; s < L.n_scales; ++s)
+        if (L.n_img * L.cells[s] > 0xffffffffll || L.B[s] > 32 || (long long)L.B[s] * L.C >= (1 << 22))
+            return YB_E_SHAPE;  // HotBox packs the cell index in 32 bits, box in 6, row offset in 22
     ws.total_cells = total;
     ws.n_hot = reinterpret_cast<unsigned int*>(workspace);
     ws.counts = reinterpret_cast<unsigned int*>((char*)workspace + 256);
     ws.offsets = reinterpret_cast<long long*>((char*)ws.counts + decode_counts_bytes(total));
-    ws.hot = reinterpret_cast<long long*>((char*)ws.offsets + decode_offsets_bytes(total));
-    ws.scan_ws = (char*)ws.hot + decode_hot_bytes(total);
+    long long total_boxes = 0;
+    for (int s = 0; s < L.n_scales; ++s) total_boxes += L.n_img * L.cells[s] * L.B[s];
+    ws.hot = reinterpret_cast<HotBox*>((char*)ws.offsets + decode_offsets_bytes(total));
+    ws.scan_ws = (char*)ws.hot + decode_hot_bytes(total_boxes);
     return YB_OK;
 }
 
@@ -283,20 +287,14 @@ int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double
                   long long* row_offsets, cudaStream_t stream) {
     int rc = exclusive_scan_u32(ws.counts, ws.total_cells, ws.offsets, ws.scan_ws, stream);
     if (rc != 0) return rc;
-    const size_t esz = is_f64 ? 8 : 4;
     const int threads = 256;
-    const int blocks2 = kNumSMs * 32;  // ~one hot cell per warp; idle warps exit at once
-    int max_pcf = 0;
-    for (int s = 0; s < L.n_scales; ++s) max_pcf = max(max_pcf, L.pcf[s]);
-    int buf_elems = (max_pcf + 3) / 4 * 4;
-    if ((size_t)buf_elems * esz * (threads / 32) > 24 * 1024) buf_elems = 0;  // fat cells: read in place
-    const size_t smem2 = (size_t)buf_elems * esz * (threads / 32);
+    const int blocks2 = kNumSMs * 8;
     if (is_f64)
-        decode_emit_kernel<double><<<blocks2, threads, smem2, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
-                                                                        row_offsets, buf_elems);
+        decode_emit_kernel<double><<<blocks2, threads, 0, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
+                                                                    row_offsets);
     else
-        decode_emit_kernel<float><<<blocks2, threads, smem2, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
-                                                                       row_offsets, buf_elems);
+        decode_emit_kernel<float><<<blocks2, threads, 0, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
+                                                                   row_offsets);
     return (int)cudaGetLastError();
 }
 

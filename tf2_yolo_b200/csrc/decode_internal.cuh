@@ -22,11 +22,25 @@ struct DecodeLaunch {
     int stage_bytes;
 };
 
+// Work-list entry for a BOX with hits: everything the emit pass needs, no 64-bit divisions.
+struct __align__(16) HotBox {
+    long long out_idx;     // the cell's position in OUTPUT order (image, scale, y, x): index into offsets
+    unsigned int mem_idx;  // the cell's position inside its scale tensor: img * cells + cell
+    unsigned int packed;   // bits 0..3 scale, 4..9 box, 10..31 rows of the cell's earlier boxes
+};
+__host__ __device__ inline HotBox make_hot(long long o, unsigned mem_idx, int scale, int box, unsigned rows_before) {
+    HotBox h;
+    h.out_idx = o;
+    h.mem_idx = mem_idx;
+    h.packed = (unsigned)scale | ((unsigned)box << 4) | (rows_before << 10);
+    return h;
+}
+
 struct DecodeWs {          // carved out of the caller's decode workspace
-    unsigned int* n_hot;   // number of cells with hits
+    unsigned int* n_hot;   // number of boxes with hits
     unsigned int* counts;  // hits per cell, OUTPUT order (image, scale, y, x)
     long long* offsets;    // exclusive scan of counts (+ total)
-    long long* hot;        // work list of cells with hits
+    HotBox* hot;           // work list of boxes with hits
     void* scan_ws;
     long long total_cells;
 };

@@ -77,7 +77,7 @@ struct LossLaunch {
     // fused decode counting (yb_loss_decode_fused): per-cell hit counts in decode OUTPUT order
     unsigned int* dec_counts;
     unsigned int* dec_n_hot;
-    long long* dec_hot;
+    HotBox* dec_hot;
     long long dec_per_img;                   // cells per image over all scales
     long long dec_cell_base[YB_MAX_SCALES];  // first cell of a scale inside an image
     long long dec_cells[YB_MAX_SCALES];      // grid_h * grid_w
@@ -415,14 +415,18 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
 #pragma unroll 4
                         for (int k = 0; k < C; ++k) n += (__fmul_rn(c, prob[k]) >= L.dec_thr) ? 1 : 0;
                     }
-                    int tot = 0;
-                    for (int q = 0; q < B; ++q) tot += __shfl_sync(0xffffffffu, n, lc * B + q);
-                    if (valid && lb == 0) {
+                    int tot = 0, before = 0;
+                    for (int q = 0; q < B; ++q) {
+                        const int nq = __shfl_sync(0xffffffffu, n, lc * B + q);
+                        tot += nq;
+                        before += (q < lb) ? nq : 0;
+                    }
+                    if (valid) {
                         const long long g = cell0 + cell;
                         const long long img = g / L.dec_cells[s];
                         const long long o = img * L.dec_per_img + L.dec_cell_base[s] + (g - img * L.dec_cells[s]);
-                        L.dec_counts[o] = (unsigned)tot;
-                        if (tot > 0) L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = o;
+                        if (lb == 0) L.dec_counts[o] = (unsigned)tot;
+                        if (n > 0) L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
                     }
                 }
                 if (kMetrics) {

@@ -170,11 +170,11 @@ __global__ void __launch_bounds__(256)
 nms_small_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W,
                  unsigned char* __restrict__ keep) {
     const int lane = threadIdx.x & 31;
-    for (;;) {
-        unsigned w = 0;
-        if (lane == 0) w = atomicAdd(&W.ctrl[2], 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= W.ctrl[0]) break;
+    // static round-robin over the work list (segments are at most 32 boxes: balanced enough, and a
+    // work-stealing atomic per segment costs more than the segment)
+    const unsigned n_work = W.ctrl[0];
+    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work; w += n_warps) {
         const int seg = W.small_list[w];
         const int n = (int)W.seg_count[seg];
         const long long start = W.seg_start[seg];
@@ -284,16 +284,12 @@ nms_big_kernel(const double* __restrict__ rows, double thr, double conf_thr, dou
     __shared__ unsigned long long s_mask[kSweep];
     __shared__ int s_kept[kSweep];
     __shared__ int s_nkept;
-    __shared__ unsigned s_work;
     __shared__ long long s_scan[32];
     const int tid = threadIdx.x;
 
-    for (;;) {
+    const unsigned n_work = W.ctrl[1];
+    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
         __syncthreads();
-        if (tid == 0) s_work = atomicAdd(&W.ctrl[3], 1u);
-        __syncthreads();
-        const unsigned wi = s_work;
-        if (wi >= W.ctrl[1]) break;
         const int seg = W.big_list[wi];
         const int n = (int)W.seg_count[seg];
         const long long start = W.seg_start[seg];

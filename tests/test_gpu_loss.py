@@ -229,3 +229,43 @@ def test_from_logits_head_fusion():
         check_grad(grad, g_ref, f"logits v{ver}")
     with pytest.raises(ValueError):
         wrap_yolo_loss_from_logits(2, (13, 13), 5, 20, anchors=synth.ANCHORS_V2)
+
+
+def test_loss_bits_do_not_depend_on_the_schedule():
+    """Tiles are handed out dynamically, so which CTA sums which cells changes from launch to
+    launch; the binned (exact) accumulation must still give identical bits every time, for the
+    loss, every term and the in-training metric sums."""
+    cfg = synth.make_config("v4-608", batch=16, seed=11)
+    B, C = cfg["bbox_num"], cfg["class_num"]
+    fns = [wrap(4)((S, S), B, C, anchors=cfg["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1])
+           for si, S in enumerate(cfg["grids"])]
+    yts = [torch.from_numpy(a).cuda() for a in cfg["y_trues"]]
+    yps = [torch.from_numpy(a).cuda() for a in cfg["y_preds"]]
+    ref = None
+    for _ in range(6):
+        loss, dpreds, terms, metrics = fused_losses(fns, yts, yps, want_terms=True, want_metrics=True)
+        cur = (loss.clone(), terms.clone(), metrics.clone(), [d.clone() for d in dpreds])
+        if ref is None:
+            ref = cur
+            continue
+        assert torch.equal(cur[0], ref[0]) and torch.equal(cur[1], ref[1]) and torch.equal(cur[2], ref[2])
+        assert all(torch.equal(a, b) for a, b in zip(cur[3], ref[3]))
+    # the terms agree with an fp64 sum of the same addends far below the loss tolerance
+    spec = ol.GridLossSpec(version=4, grid_shape=(cfg["grids"][2],) * 2, bbox_num=B, class_num=C,
+                           anchors=cfg["anchors"][2 * B:3 * B], loss_weight=[1, 5, 1])
+    l_ref, _, _ = ol.loss_and_grad(spec, cfg["y_trues"][2], cfg["y_preds"][2])
+    assert abs(ref[1][2, 0].item() - l_ref) <= LOSS_RTOL * abs(l_ref)
+
+
+def test_nonfinite_inputs_propagate():
+    """An Inf / NaN head output must poison the loss like it does in the reference (sums of
+    non-finite addends), not vanish in the binned accumulation."""
+    cfg = synth.make_config("v3-416", batch=2, seed=12)
+    B, C = cfg["bbox_num"], cfg["class_num"]
+    S = cfg["grids"][0]
+    fn = wrap(3)((S, S), B, C, anchors=cfg["anchors"][:B])
+    yt = torch.from_numpy(cfg["y_trues"][0]).cuda()
+    yp = torch.from_numpy(cfg["y_preds"][0]).cuda().clone()
+    yp[0, 0, 0, 2] = float("nan")     # width of box 0 in cell (0, 0)
+    loss, _ = fn.value_and_grad(yt, yp)
+    assert not np.isfinite(float(loss.reshape(-1)[0]))

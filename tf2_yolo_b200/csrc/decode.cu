@@ -109,7 +109,7 @@ decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __rest
                     const T* box = sp + (size_t)cell * pcf + lb * ((L.version == 1) ? 5 : 5 + C);
                     const T* prob = (L.version == 1) ? sp + (size_t)cell * pcf + 5 * B : box + 5;
                     const T c = box[4];
-#pragma unroll 4
+#pragma unroll 16
                     for (int k = 0; k < C; ++k) n += (mul_rn<T>(c, prob[k]) >= thr) ? 1 : 0;
                 }
                 int tot = 0, before = 0;

@@ -15,9 +15,14 @@
 //                   written in place, zero-fill of the box's class-score gradients;
 //                   the rare responsible boxes then get their class cross-entropy and
 //                   gradient from the whole warp (fp64).  No CTA-wide barrier.
-//   reduction     : fp64 partial sums per thread -> warp -> CTA -> global partials,
-//                   last CTA sums them in a fixed order (deterministic) and emits
-//                   the fp32 loss of every scale.
+//   scheduling    : tiles are handed out by a global ticket counter (the first tile of a
+//                   CTA is its block index), so SMs that stream faster take more tiles
+//                   and every CTA finishes within one tile of the others.
+//   reduction     : every addend is split onto two fixed binary grids (2^-12 and 2^-42)
+//                   before it is accumulated, so all additions are exact and the sums do
+//                   not depend on which CTA took which tile: thread -> warp -> CTA ->
+//                   fp64 atomics in global memory stay bit-reproducible; the last CTA
+//                   combines the two grids and emits the fp32 loss of every scale.
 //
 // The loss is cell-local; the only coupling is the argmax over the boxes of one
 // cell and the final sum, so HBM traffic is exactly: read y_pred, read y_true,
@@ -37,6 +42,22 @@ constexpr int kTerms = 10;     // 5 loss terms + 5 in-training metric sums
 constexpr int kLossTerms = 5;
 constexpr float kEpsF = 1e-07f;
 constexpr double kEps = 1e-07;
+constexpr int kCtrlWords = 4;  // [0] finished CTAs, [1] tile tickets
+
+// Order-independent accumulation.  x is rounded onto the grid 2^-12 (adding 1.5*2^40 makes the
+// ulp of the sum 2^-12), the exact remainder onto 2^-42; what is left (< 2^-43 per addend) is
+// dropped.  Sums of grid points are exact while |sum| < 2^41 resp. 2^11 (more than 16 M addends
+// per term), so they are associative: any schedule gives the same bits.  Beyond those bounds the
+// additions round like ordinary fp64 sums.  NaN / Inf propagate.
+constexpr double kBinHi = 1649267441664.0;  // 1.5 * 2^40
+constexpr double kBinLo = 1536.0;           // 1.5 * 2^10
+__device__ __forceinline__ void bin_add(double& hi, double& lo, double x) {
+    const double h = __dsub_rn(__dadd_rn(x, kBinHi), kBinHi);
+    const double r = (h == x) ? 0.0 : __dsub_rn(x, h);
+    const double l = __dsub_rn(__dadd_rn(r, kBinLo), kBinLo);
+    hi = __dadd_rn(hi, h);
+    lo = __dadd_rn(lo, l);
+}
 
 struct LossScaleDev {
     const float* y_true;
@@ -68,8 +89,8 @@ struct LossLaunch {
     int total_tiles;
     int stage_bytes;       // bytes of one ring stage
     int n_stages;
-    double* partials;      // [gridDim][n_scales][kTerms]
-    unsigned int* counter;
+    double* gacc;          // [n_scales][kAcc][2] order-independent sums (zero on entry, re-zeroed on exit)
+    unsigned int* ctrl;    // [kCtrlWords]
     float* loss_out;       // [n_scales]
     double* terms_out;     // [n_scales][YB_LOSS_TERMS] or null
     double* metrics_out;   // [n_scales][YB_LOSS_METRICS] or null
@@ -245,6 +266,18 @@ __device__ __forceinline__ int warp_argmax(const float* v, int C, int lane) {
 
 __device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
 
+#ifdef YB_LOSS_PROFILE
+__device__ unsigned long long yb_loss_prof[1024 * 6];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define YB_PROF(slot) do { yb_loss_prof[blockIdx.x * 6 + (slot)] = gtimer(); } while (0)
+#else
+#define YB_PROF(slot) do { } while (0)
+#endif
+
 template <int V, bool kMetrics, bool kDecode, bool kLogits = false>
 __global__ void __launch_bounds__(kLossMaxThreads)
 loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
@@ -257,11 +290,12 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
 
     unsigned char* ring = smem;
     double* s_acc = reinterpret_cast<double*>(smem + (size_t)n_stages * L.stage_bytes);
-    // s_acc: [ncw][n_scales][kTerms]
+    // s_acc: [ncw][n_scales][kTerms][2]
     const int n_sc = L.n_scales;
-    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + ncw * n_sc * kTerms);
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_acc + ncw * n_sc * kTerms * 2);
     uint64_t* done = full + kMaxStages;
     __shared__ int s_is_last;
+    __shared__ int s_tile[kMaxStages];  // tile held by each ring stage, -1 = no more work
 
     if (tid == 0) {
         for (int i = 0; i < kMaxStages; ++i) {
@@ -270,24 +304,30 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
         }
         mbar_fence_init();
     }
-    for (int i = tid; i < ncw * n_sc * kTerms; i += blockDim.x) s_acc[i] = 0.0;
+    for (int i = tid; i < ncw * n_sc * kTerms * 2; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
+    if (tid == 0) YB_PROF(0);
 
-    const int n_my = (L.total_tiles > (int)blockIdx.x)
-                         ? (L.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x
-                         : 0;
+    const int total_tiles = L.total_tiles;
 
     if (warp == ncw) {
         // ===================== producer warp =====================
+        // Iteration t fills ring stage t % n_stages with the next tile (or posts the end marker)
+        // and then retires tile t-(n_stages-1): waits for the consumers, stores the stage (now
+        // holding dL/dy_pred) back, and waits until the store has read shared memory, which
+        // frees that stage for iteration t+1.
         int s_ld = 0, s_st = 0;
-        for (int t = 0; t < n_my + n_stages - 1; ++t) {
-            if (t < n_my) {
-                const int tile = blockIdx.x + t * gridDim.x;
+        int next = ((int)blockIdx.x < total_tiles) ? (int)blockIdx.x : -1;  // lane 0's view
+        int n_loaded = 0;
+        bool end_posted = false;
+        for (int t = 0;; ++t) {
+            const int stage = t % n_stages;
+            const int tile = __shfl_sync(0xffffffffu, next, 0);
+            if (tile >= 0) {
                 while (tile >= L.sc[s_ld].tile_base + L.sc[s_ld].n_tiles) ++s_ld;
                 const LossScaleDev& S = L.sc[s_ld];
                 const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
                 const int nc = (int)min((long long)S.tile_cells, S.n_cells - cell0);
-                const int stage = t % n_stages;
                 float* sp = reinterpret_cast<float*>(ring + (size_t)stage * L.stage_bytes);
                 float* st = sp + S.tile_cells * S.pcf;
                 const float* gp = S.y_pred + cell0 * S.pcf;
@@ -295,6 +335,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                 if (S.bulk_ok && (nc & 3) == 0) {
                     if (lane == 0) {
                         const uint32_t bp = (uint32_t)nc * S.pcf * 4u, bt = (uint32_t)nc * S.tcf * 4u;
+                        s_tile[stage] = tile;
                         mbar_arrive_expect_tx(&full[stage], bp + bt);
                         bulk_g2s(sp, gp, bp, &full[stage]);
                         bulk_g2s(st, gt, bt, &full[stage]);
@@ -303,20 +344,35 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     for (int i = lane; i < nc * S.pcf; i += 32) sp[i] = __ldg(gp + i);
                     for (int i = lane; i < nc * S.tcf; i += 32) st[i] = __ldg(gt + i);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&full[stage]);
+                    if (lane == 0) {
+                        s_tile[stage] = tile;
+                        mbar_arrive(&full[stage]);
+                    }
                 }
+                ++n_loaded;
+                // ticket for the next tile; the atomic's latency overlaps the retire step below
+                if (lane == 0) {
+                    const unsigned tk = atomicAdd(&L.ctrl[1], 1u) + gridDim.x;
+                    next = (tk < (unsigned)total_tiles) ? (int)tk : -1;
+                }
+            } else if (!end_posted) {
+                if (lane == 0) {
+                    s_tile[stage] = -1;
+                    mbar_arrive(&full[stage]);
+                }
+                end_posted = true;
             }
             const int j = t - (n_stages - 1);
-            if (j >= 0) {
-                const int tile = blockIdx.x + j * gridDim.x;
-                while (tile >= L.sc[s_st].tile_base + L.sc[s_st].n_tiles) ++s_st;
+            if (j >= 0 && j < n_loaded) {
+                const int jstage = j % n_stages;
+                mbar_wait(&done[jstage], (j / n_stages) & 1);
+                const int jt = s_tile[jstage];
+                while (jt >= L.sc[s_st].tile_base + L.sc[s_st].n_tiles) ++s_st;
                 const LossScaleDev& S = L.sc[s_st];
-                const int stage = j % n_stages;
-                mbar_wait(&done[stage], (j / n_stages) & 1);
                 if (S.dpred != nullptr) {
-                    const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
+                    const long long cell0 = (long long)(jt - S.tile_base) * S.tile_cells;
                     const int nc = (int)min((long long)S.tile_cells, S.n_cells - cell0);
-                    float* sp = reinterpret_cast<float*>(ring + (size_t)stage * L.stage_bytes);
+                    float* sp = reinterpret_cast<float*>(ring + (size_t)jstage * L.stage_bytes);
                     float* gd = S.dpred + cell0 * S.pcf;
                     if (S.bulk_ok && (nc & 3) == 0) {
                         if (lane == 0) {
@@ -330,13 +386,17 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     __syncwarp();
                 }
             }
+            if (end_posted && j >= n_loaded - 1) break;
         }
+        if (lane == 0) YB_PROF(2);
         if (lane == 0) bulk_wait_all<0>();
+        if (lane == 0) YB_PROF(3);
     } else {
         // ===================== consumer warps =====================
-        double acc[kAcc];
+        double hi[kAcc], lo[kAcc];
 #pragma unroll
-        for (int k = 0; k < kAcc; ++k) acc[k] = 0.0;
+        for (int k = 0; k < kAcc; ++k) hi[k] = lo[k] = 0.0;
+        auto add = [&](int k, double v) { bin_add(hi[k], lo[k], v); };
         int cur = -1;
         int cpw = 0, lc = 0, lb = 0;  // cells per warp, this lane's local cell / box
         bool lane_on = false;
@@ -344,14 +404,21 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
         auto flush = [&](int s) {
 #pragma unroll
             for (int k = 0; k < kAcc; ++k) {
-                const double v = warp_sum(acc[k]);
-                if (lane == 0) s_acc[(warp * n_sc + s) * kTerms + k] += v;
-                acc[k] = 0.0;
+                const double vh = warp_sum(hi[k]), vl = warp_sum(lo[k]);   // exact: grid points
+                if (lane == 0) {
+                    double* a = s_acc + ((warp * n_sc + s) * kTerms + k) * 2;
+                    a[0] += vh;
+                    a[1] += vl;
+                }
+                hi[k] = lo[k] = 0.0;
             }
         };
 
-        for (int it = 0; it < n_my; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
+        for (int it = 0;; ++it) {
+            const int stage = it % n_stages;
+            mbar_wait(&full[stage], (it / n_stages) & 1);
+            const int tile = s_tile[stage];
+            if (tile < 0) break;
             int s = (cur < 0) ? 0 : cur;
             while (tile >= L.sc[s].tile_base + L.sc[s].n_tiles) ++s;
             if (s != cur) {
@@ -368,15 +435,12 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
             const LossScaleDev& S = L.sc[s];
             const long long cell0 = (long long)(tile - S.tile_base) * S.tile_cells;
             const int nc = (int)min((long long)S.tile_cells, S.n_cells - cell0);
-            const int stage = it % n_stages;
             float* sp = reinterpret_cast<float*>(ring + (size_t)stage * L.stage_bytes);
             const float* st = sp + S.tile_cells * S.pcf;
             const int B = S.B, C = S.C;
             const int bstride = (V == 1) ? 5 : (5 + C);
             const bool write = S.dpred != nullptr;
             const float inv_n = S.inv_n;
-
-            mbar_wait(&full[stage], (it / n_stages) & 1);
 
             for (int c0 = warp * cpw; c0 < nc; c0 += ncw * cpw) {
                 const int cell = c0 + lc;
@@ -412,7 +476,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     int n = 0;
                     if (valid) {
                         const float* prob = (V == 1) ? sp + cell * S.pcf + 5 * B : pc + 5;
-#pragma unroll 4
+#pragma unroll 16
                         for (int k = 0; k < C; ++k) n += (__fmul_rn(c, prob[k]) >= L.dec_thr) ? 1 : 0;
                     }
                     int tot = 0, before = 0;
@@ -435,9 +499,9 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     float cmax = __shfl_sync(0xffffffffu, c, lc * B);
                     for (int q = 1; q < B; ++q) cmax = fmaxf(cmax, __shfl_sync(0xffffffffu, c, lc * B + q));
                     if (valid && lb == 0) {
-                        acc[kAcc - 5] += (obj == ((cmax > 0.5f) ? 1.f : 0.f)) ? 1.0 : 0.0;
-                        acc[kAcc - 4] += (double)(best * obj);
-                        acc[kAcc - 3] += (double)obj;
+                        add(kAcc - 5, (obj == ((cmax > 0.5f) ? 1.f : 0.f)) ? 1.0 : 0.0);
+                        add(kAcc - 4, (double)(best * obj));
+                        add(kAcc - 3, (double)obj);
                     }
                     float eq = 0.f;  // argmax(class scores) agrees with the label's class
                     unsigned om = __ballot_sync(0xffffffffu, valid && obj != 0.f && (V != 1 || lb == 0));
@@ -452,11 +516,11 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         if (lane == src) eq = (ap == at) ? 1.f : 0.f;
                     }
                     if (V == 1) eq = __shfl_sync(0xffffffffu, eq, lc * B);  // per-cell class scores
-                    if (valid && (V != 1 || lb == 0)) acc[kAcc - 2] += (double)(eq * obj);
+                    if (valid && (V != 1 || lb == 0)) add(kAcc - 2, (double)(eq * obj));
                     float hit = iou * (eq * obj);
                     float hmax = __shfl_sync(0xffffffffu, hit, lc * B);
                     for (int q = 1; q < B; ++q) hmax = fmaxf(hmax, __shfl_sync(0xffffffffu, hit, lc * B + q));
-                    if (valid && lb == 0) acc[kAcc - 1] += (hmax >= S.recall_thr) ? 1.0 : 0.0;
+                    if (valid && lb == 0) add(kAcc - 1, (hmax >= S.recall_thr) ? 1.0 : 0.0);
                 }
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f;
                 float pos = 0.f;
@@ -465,19 +529,19 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         pos = obj * resp;
                         const float neg = 1.f - pos;
                         const float dx = tx - px, dy = ty - py;
-                        acc[0] += (double)(pos * (dx * dx + dy * dy));
+                        add(0, (double)(pos * (dx * dx + dy * dy)));
                         g0 = -2.f * S.lw[0] * pos * dx * inv_n;
                         g1 = -2.f * S.lw[0] * pos * dy * inv_n;
                         const float sw = sqrtf(fmaxf(pw, kEpsF)), sh = sqrtf(fmaxf(ph, kEpsF));
                         const float dw = sqrtf(fmaxf(tw, kEpsF)) - sw, dh = sqrtf(fmaxf(th, kEpsF)) - sh;
-                        acc[1] += (double)(pos * (dw * dw + dh * dh));
+                        add(1, (double)(pos * (dw * dw + dh * dh)));
                         g2 = (pw >= kEpsF) ? -S.lw[1] * pos * dw / sw * inv_n : 0.f;
                         g3 = (ph >= kEpsF) ? -S.lw[1] * pos * dh / sh * inv_n : 0.f;
                         if (pos != 0.f) {  // objectness regresses to the IoU, which carries gradient
                             BoxGrad bg;
                             box_fwd_bwd<false>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
                             const double d = bg.iou - (double)c;
-                            acc[2] += (double)pos * d * d + (double)(S.bw * neg * c * c);
+                            add(2, (double)pos * d * d + (double)(S.bw * neg * c * c));
                             const double gi = 2.0 * S.lw[2] * pos * d * S.inv_n_d;
                             g0 += (float)(gi * bg.diou[0]);
                             g1 += (float)(gi * bg.diou[1]);
@@ -485,7 +549,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                             g3 += (float)(gi * bg.diou[3]);
                             g4 = (float)(-gi) + 2.f * S.lw[2] * S.bw * neg * c * inv_n;
                         } else {
-                            acc[2] += (double)(S.bw * neg * c * c);
+                            add(2, (double)(S.bw * neg * c * c));
                             g4 = 2.f * S.lw[2] * S.bw * neg * c * inv_n;
                         }
                     } else {
@@ -496,7 +560,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         const float lpw = logf(pw / aw), lph = logf(ph / ah);
                         if (V == 4) {
                             // wh regulariser, every box (loss.py:156-160)
-                            acc[3] += (double)(lpw * lpw + lph * lph);
+                            add(3, (double)(lpw * lpw + lph * lph));
                             g2 = 2.f * S.whw * lpw / pw * inv_n;
                             g3 = 2.f * S.whw * lph / ph * inv_n;
                             // focal objectness with label smoothing (loss.py:119-143)
@@ -527,28 +591,28 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                                 // CIoU box term (loss.py:113-117)
                                 BoxGrad bg;
                                 box_fwd_bwd<true>(px, py, pw, ph, tx, ty, tw, th, S.gw, S.gh, bg);
-                                acc[0] += (double)pos * (1.0 - bg.ciou);
+                                add(0, (double)pos * (1.0 - bg.ciou));
                                 const double gb = -(double)S.lw[0] * pos * S.inv_n_d;
                                 g0 += (float)(gb * bg.dciou[0]);
                                 g1 += (float)(gb * bg.dciou[1]);
                                 g2 += (float)(gb * bg.dciou[2]);
                                 g3 += (float)(gb * bg.dciou[3]);
                             }
-                            acc[1] += (double)lcf;
+                            add(1, (double)lcf);
                             g4 = S.lw[1] * gc * band * inv_n;
                         } else {  // V == 2 or 3
-                            acc[4] += (double)(lpw * lpw + lph * lph);
+                            add(4, (double)(lpw * lpw + lph * lph));
                             g2 = 2.f * S.whw * lpw / pw * inv_n;
                             g3 = 2.f * S.whw * lph / ph * inv_n;
                             if (pos != 0.f) {
                                 const float sc = S.use_scale ? (2.f - tw * th) : 1.f;
                                 const float dx = tx - px, dy = ty - py;
-                                acc[0] += (double)(pos * sc * (dx * dx + dy * dy));
+                                add(0, (double)(pos * sc * (dx * dx + dy * dy)));
                                 g0 = -2.f * S.lw[0] * pos * sc * dx * inv_n;
                                 g1 = -2.f * S.lw[0] * pos * sc * dy * inv_n;
                                 const float dlw = logf(fmaxf(tw / aw, kEpsF)) - lpw;
                                 const float dlh = logf(fmaxf(th / ah, kEpsF)) - lph;
-                                acc[1] += (double)(pos * sc * (dlw * dlw + dlh * dlh));
+                                add(1, (double)(pos * sc * (dlw * dlw + dlh * dlh)));
                                 g2 += -2.f * S.lw[1] * pos * sc * dlw / pw * inv_n;
                                 g3 += -2.f * S.lw[1] * pos * sc * dlh / ph * inv_n;
                             }
@@ -564,11 +628,11 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                                     lcf += pos * fp;
                                     gc -= pos * dfp;
                                 }
-                                acc[2] += (double)lcf;
+                                add(2, (double)lcf);
                                 g4 = S.lw[2] * gc * band * inv_n;
                             } else {
                                 const float om = 1.f - c;
-                                acc[2] += (double)(pos * om * om + S.bw * neg * c * c);
+                                add(2, (double)(pos * om * om + S.bw * neg * c * c));
                                 g4 = S.lw[2] * (-2.f * pos * om + 2.f * S.bw * neg * c) * inv_n;
                             }
                         }
@@ -604,49 +668,39 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     const float* t = st + rc * S.tcf + 5;
                     double part = 0.0;
                     class_row<V, kLogits>(q, t, m, C, lane, write, (double)S.lw[(V == 4) ? 2 : 3] * S.inv_n_d, part);
-                    acc[(V == 4) ? 2 : 3] += part;
+                    add((V == 4) ? 2 : 3, part);
                 }
             }
             fence_proxy_async();
             mbar_arrive(&done[stage]);
         }
         if (cur >= 0) flush(cur);
+        if (tid == 0) YB_PROF(1);
     }
 
-    // ---- CTA partials -> global, last CTA reduces in a fixed order ------------
+    // ---- CTA sums -> global (exact, order-independent adds), last CTA finishes -------
     __syncthreads();
-    const int n_vals = L.n_scales * kAcc;
-    if (tid < n_vals) {
-        const int s = tid / kAcc, k = tid - s * kAcc;
+    const int n_vals = L.n_scales * kAcc * 2;
+    for (int i = tid; i < n_vals; i += (int)blockDim.x) {
+        const int s = i / (kAcc * 2), r = i - s * (kAcc * 2);
         double v = 0.0;
-        for (int w = 0; w < ncw; ++w) v += s_acc[(w * n_sc + s) * kTerms + k];
-        L.partials[(size_t)blockIdx.x * n_vals + tid] = v;
+        for (int w = 0; w < ncw; ++w) v += s_acc[(w * n_sc + s) * kTerms * 2 + r];
+        if (v != 0.0) atomicAdd(&L.gacc[i], v);
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_is_last = (atomicAdd(L.counter, 1u) == gridDim.x - 1);
+    if (tid == 0) s_is_last = (atomicAdd(&L.ctrl[0], 1u) == gridDim.x - 1);
     __syncthreads();
+    if (tid == 0) YB_PROF(4);
     if (!s_is_last) return;
     __threadfence();
     double* s_fin = s_acc;  // reuse: [n_scales][kTerms]
-    __syncthreads();
-    for (int i = warp; i < n_vals; i += (int)(blockDim.x >> 5)) {
-        // each lane owns blocks lane, lane+32, ...: independent loads first (latency overlapped),
-        // then a fixed-order sum -> deterministic
-        double v = 0.0;
-        for (int b0 = lane; b0 < (int)gridDim.x; b0 += 32 * 8) {
-            double t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int b = b0 + 32 * u;
-                t[u] = (b < (int)gridDim.x) ? __ldcg(&L.partials[(size_t)b * n_vals + i]) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) v += t[u];
-        }
-        v = warp_sum(v);
+    for (int i = tid; i < L.n_scales * kAcc; i += (int)blockDim.x) {
         const int s = i / kAcc, k = i - s * kAcc;
-        if (lane == 0) s_fin[s * kTerms + k] = v;
+        const double vh = __ldcg(&L.gacc[2 * i]), vl = __ldcg(&L.gacc[2 * i + 1]);
+        L.gacc[2 * i] = 0.0;      // leave the workspace reusable
+        L.gacc[2 * i + 1] = 0.0;
+        s_fin[s * kTerms + k] = vh + vl;
     }
     __syncthreads();
     if (tid < L.n_scales) {
@@ -675,7 +729,11 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
             o[9] = cells;
         }
     }
-    if (tid == 0) *L.counter = 0u;  // leave the workspace reusable
+    if (tid == 0) {
+        L.ctrl[0] = 0u;
+        L.ctrl[1] = 0u;
+    }
+    if (tid == 0) YB_PROF(5);
 }
 
 // ---- grid IoU (public cal_iou of the loss modules) ----------------------------
@@ -703,8 +761,8 @@ static int env_int(const char* name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
-static size_t loss_partials_bytes(int n_scales) {
-    return align_up((size_t)kNumSMs * 8 * n_scales * kTerms * sizeof(double), 256);
+static size_t loss_gacc_bytes(int n_scales) {
+    return align_up((size_t)n_scales * kTerms * 2 * sizeof(double), 256);
 }
 
 static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
@@ -792,10 +850,16 @@ static int launch_loss(const LossLaunch& L, int grid, int threads, size_t smem, 
 
 using namespace yb;
 
+#ifdef YB_LOSS_PROFILE
+extern "C" int yb_debug_loss_profile(unsigned long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, yb::yb_loss_prof, sizeof(unsigned long long) * 1024 * 6);
+}
+#endif
+
 extern "C" size_t yb_loss_workspace_bytes(int n_scales) {
     if (n_scales < 1) n_scales = 1;
     if (n_scales > YB_MAX_SCALES) n_scales = YB_MAX_SCALES;
-    return loss_partials_bytes(n_scales) + 256;
+    return loss_gacc_bytes(n_scales) + 256;
 }
 
 struct FusedDecode {   // optional: count decode hits inside the loss pass
@@ -834,7 +898,7 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     int ctas_per_sm = max(1, min(8, env_int("YB_LOSS_CTAS_PER_SM", 4)));
     const int tile_env = env_int("YB_LOSS_TILE_CELLS", 0);
     const size_t sm_smem = 228 * 1024, static_smem = 192;
-    auto acc_bytes = [&](int warps) { return sizeof(double) * warps * n_scales * kTerms; };
+    auto acc_bytes = [&](int warps) { return sizeof(double) * warps * n_scales * kTerms * 2; };
     const size_t bar_bytes = 2 * kMaxStages * sizeof(uint64_t);
     int total_tiles = 0, stage_bytes = 0, ncw = kLossMaxConsumerWarps;
     for (int pass = 0; pass < 2; ++pass) {  // pass 0 assumes the maximum warp count, pass 1 the real one
@@ -874,8 +938,8 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     L.total_tiles = total_tiles;
     L.stage_bytes = stage_bytes;
     L.n_stages = n_stages;
-    L.partials = reinterpret_cast<double*>(workspace);
-    L.counter = reinterpret_cast<unsigned int*>((char*)workspace + loss_partials_bytes(n_scales));
+    L.gacc = reinterpret_cast<double*>(workspace);
+    L.ctrl = reinterpret_cast<unsigned int*>((char*)workspace + loss_gacc_bytes(n_scales));
     L.loss_out = loss_out;
     L.terms_out = terms_out;
     L.metrics_out = metrics_out;
@@ -895,7 +959,8 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     const size_t smem = (size_t)n_stages * stage_bytes + acc_bytes(ncw) + bar_bytes;
     const int threads = (ncw + 1) * 32;
     int grid = min(max(total_tiles, 1), kNumSMs * ctas_per_sm);
-    YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
+    // sums + control words start at zero (the kernel also leaves them zeroed)
+    YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, loss_gacc_bytes(n_scales) + kCtrlWords * sizeof(unsigned int), stream));
     switch (version) {
         case 1: return launch_loss<1>(L, grid, threads, smem, stream);
         case 2: return launch_loss<2>(L, grid, threads, smem, stream);

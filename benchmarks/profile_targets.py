@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Short driver for ncu captures of the non-loss kernels (k-means assignment, dense-scene NMS,
+PR matching):  python benchmarks/profile_targets.py [kmeans] [nms] [map]
+Each target runs warm-ups and a few launches; use with `ncu -k regex:<kernel> -s <skip> -c <n>`."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tf2_yolo_b200 import engine, synth  # noqa: E402
+from tf2_yolo_b200._native import YB_DIST_IOU  # noqa: E402
+
+what = sys.argv[1:] or ["kmeans", "nms"]
+if "kmeans" in what:
+    rng = np.random.default_rng(4)
+    n = int(os.environ.get("YB_PROF_KM_N", 50_000_000))
+    data = torch.from_numpy(synth.make_kmeans_boxes(rng, n, 9)).cuda()
+    centers = torch.from_numpy(np.sort(rng.uniform(0.02, 0.8, (9, 2)), axis=0)).cuda()
+    for _ in range(4):
+        engine.kmeans_assign(data, centers, YB_DIST_IOU)
+    torch.cuda.synchronize()
+    del data
+if "nms" in what:
+    rng = np.random.default_rng(4)
+    n_img, per_img, C = int(os.environ.get("YB_PROF_NMS_IMG", 8)), 100_000, 80
+    rows = np.concatenate([synth.make_dense_candidates(rng, per_img, C) for _ in range(n_img)])
+    offs = torch.arange(0, (n_img + 1) * per_img, per_img, dtype=torch.int64, device="cuda")
+    dev = torch.from_numpy(rows).cuda()
+    for mode in (1, 2):
+        for _ in range(2):
+            engine.nms_batch(dev, offs, C, 0.45, mode)
+    torch.cuda.synchronize()
+print("ok")

@@ -9,6 +9,7 @@
 // bulk-async copies (TMA); every thread keeps k*(d+1) accumulators in registers
 // (compile-time k bound, predicated adds - no atomics in the hot loop), reduced
 // warp -> CTA -> global partials -> last CTA in a fixed order (deterministic).
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -16,7 +17,8 @@
 namespace yb {
 
 constexpr int kKmThreads = 256;
-constexpr int kKmMaxStages = 3;
+constexpr int kKmWarps = kKmThreads / 32;
+constexpr int kKmMaxStages = 4;
 
 struct KmLaunch {
     const double* data;
@@ -24,7 +26,7 @@ struct KmLaunch {
     const double* centers;
     int k, d, kind;
     int bulk_ok;
-    int tile_pts, n_stages;
+    int tile_pts, n_stages;   // per-WARP tile (points) and ring depth
     int* assign;
     double* sums;       // [k][d]
     long long* counts;  // [k]
@@ -32,38 +34,51 @@ struct KmLaunch {
     unsigned int* counter;
 };
 
-// Per-bracket table entry: box area a with j centroid areas <= a lies in [lo, hi).
-struct __align__(16) KmBracket {
-    double lo, hi;     // sorted neighbours (0 below the smallest, 1e300 above the largest)
-    double gm2;        // lo * hi: a*a < gm2  <=>  lo is the closer centroid
-    int idx_lo, idx_hi;  // original cluster indices of lo / hi
-};
+// NumPy's argmin over the rounded iou_dist values (kmeans.py:12-22,32,80), first minimum wins;
+// returns the SORTED slot of the winner.  Cold path (near ties, degenerate centroids, NaN).
+__device__ __noinline__ int km_exact_slot(double a, int k, const double* carea, const int* rank) {
+    double bd = 0.0;
+    int best = 0;
+    for (int c = 0; c < k; ++c) {
+        const double ca = carea[c];
+        const double dist = 1.0 - fmin(ca, a) / fmax(ca, a);
+        if (c == 0 || dist < bd) {
+            bd = dist;
+            best = c;
+        }
+    }
+    return rank[best];
+}
 
-// Shared memory: [ring: n_stages x tile_pts x D doubles][acc: K x 256 x D doubles][cnt: K x 256 ints]
-// Every thread owns one column of the accumulator planes, so the per-box update is a plain
-// load / add / store at a dynamic cluster index (no atomics, no k-way predicated adds).
+// Shared memory: [ring: 8 warps x n_stages x tile_pts x D doubles][acc: K x 256 x D doubles][cnt: K x 256 ints]
+// Every WARP streams its own tiles through its own ring (lane 0 issues the bulk copies, the warp
+// waits on its own mbarriers): no block-wide barrier anywhere in the streaming loop.  Every thread
+// owns one column of the accumulator planes, so the per-box update is a plain load / add / store
+// at a dynamic slot index (no atomics, no k-way predicated adds).
 template <int K, int D, bool kIou, bool kAssign>
 __global__ void __launch_bounds__(kKmThreads, 2)
 kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* ring = reinterpret_cast<double*>(smem);
-    double* s_acc = ring + (size_t)L.n_stages * L.tile_pts * D;               // [K][256][D]
+    double* s_acc = ring + (size_t)kKmWarps * L.n_stages * L.tile_pts * D;    // [K][256][D]
     int* s_cnt = reinterpret_cast<int*>(s_acc + (size_t)K * D * kKmThreads);  // [K][256]
-    __shared__ uint64_t full[kKmMaxStages];
+    __shared__ uint64_t full[kKmWarps][kKmMaxStages];
     __shared__ double s_center[K * D];
     __shared__ double s_carea[K];
-    __shared__ double s_sarea[K + 1];      // centroid areas, ascending
-    __shared__ int s_sidx[K + 1];          // original index of the j-th smallest area
-    __shared__ KmBracket s_br[K + 1];
-    __shared__ int s_exact_all;            // 1: degenerate centroid set -> every box takes the exact loop
-    __shared__ double s_red[(kKmThreads / 32) * K * (D + 1)];
+    __shared__ double s_sarea[K];          // centroid areas, ascending
+    __shared__ int s_sidx[K];              // original index of the s-th smallest area
+    __shared__ int s_rank[K];              // sorted slot of original index c
+    __shared__ int s_thr_hi[K];            // high words of the k-1 decision thresholds (INT_MAX beyond)
+    __shared__ double2 s_edge[K];          // slot s is certain for lo < area < hi
+    __shared__ double s_red[kKmWarps * K * (D + 1)];
     __shared__ int s_is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = L.k;  // <= K
     const int n_stages = L.n_stages, tile_pts = L.tile_pts;
 
     if (tid == 0) {
-        for (int i = 0; i < kKmMaxStages; ++i) mbar_init(&full[i], 1);
+        for (int w = 0; w < kKmWarps; ++w)
+            for (int i = 0; i < kKmMaxStages; ++i) mbar_init(&full[w][i], 1);
         mbar_fence_init();
     }
     if (tid < K * D) s_center[tid] = (tid < k * D) ? L.centers[tid] : 0.0;
@@ -72,119 +87,149 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     __syncthreads();
     if (tid < K) s_carea[tid] = (tid < k && D >= 2) ? __dmul_rn(s_center[tid * D], s_center[tid * D + 1]) : 0.0;
     __syncthreads();
-    // iou_dist is a function of the AREA only and monotone in it on either side of the box's
-    // area a, so the nearest centroid is one of the two sorted areas lo <= a < hi bracketing
-    // the box, and lo/a > a/hi  <=>  lo*hi > a*a: sort the k areas once, bracket the box,
-    // compare a*a with the precomputed lo*hi - no division at all.  The shortcut is taken only
-    // when it provably agrees with NumPy's first-minimum argmin over the ROUNDED distances
-    // fl(1 - fl(min/max)):
-    //   * |lo*hi - a*a| > 1e-15 * a*hi  => the two ratios differ by > 7e-16, more than the
-    //     rounding of the ratios and of 1 - r can hide, so the rounded distances are ordered
-    //     like the exact ones;
-    //   * neighbouring areas differ by > 1e-6 relative and the winning ratio is >= 2^-20, so
-    //     every farther centroid's rounded distance is strictly larger (no tie to break).
-    // Anything else (duplicate / non-finite centroids, near ties, boxes 2^20 times smaller or
-    // larger than every centroid) takes the exact k-way loop with IEEE divisions.
+    // iou_dist is a function of the AREA only and monotone in it on either side of the box's area
+    // a, so the nearest centroid is one of the two sorted areas lo <= a < hi bracketing the box, and
+    // lo/a > a/hi  <=>  a < sqrt(lo*hi).  The assignment is therefore a step function of a with
+    // k-1 thresholds g_j = sqrt(A_j * A_j+1) over the sorted areas A: the slot is a count of
+    // thresholds below a.  The count is taken on the HIGH WORDS of the doubles (integer compares);
+    // it can be off by one only when a is within 2^-20 of a threshold.  The shortcut is accepted
+    // only when it provably agrees with NumPy's first-minimum argmin over the ROUNDED distances
+    // fl(1 - fl(min/max)):  slot s is certain for  g_{s-1}(1+d) < a < g_s(1-d)  with
+    // d = 2e-15 + 1e-15 sqrt(A_j+1 / A_j): there the two candidate ratios differ by > 2e-15, more
+    // than the roundings of the ratios and of 1 - r can hide (4.4e-16), so the rounded distances
+    // are ordered like the exact ones, strictly; the edges are also clamped so that the winning
+    // ratio is >= 2^-20, and neighbouring areas must differ by > 1e-6 relative, so every farther
+    // centroid's rounded distance is strictly larger still (no tie to break).  A miscounted slot
+    // always lands outside its own edges.  Anything else (duplicate / non-finite / extreme
+    // centroids, near ties, far-away boxes, NaN) takes the exact k-way loop with IEEE divisions.
     if (tid == 0) {
-        int bad = 0;
+        int bad = (D < 2) ? 1 : 0;
         for (int c = 0; c < k; ++c) {
             const double a = s_carea[c];
-            if (!(a > 0.0) || !(a < 1e100)) bad = 1;
+            if (!(a > 1e-100) || !(a < 1e100)) bad = 1;
             int r = 0;
             for (int q = 0; q < k; ++q) r += (s_carea[q] < a || (s_carea[q] == a && q < c)) ? 1 : 0;
             s_sarea[r] = a;
             s_sidx[r] = c;
-        }
-        for (int j = k; j <= K; ++j) {
-            s_sarea[j] = INFINITY;
-            s_sidx[j] = 0;
-        }
-        for (int j = 0; j <= K; ++j) {
-            KmBracket b;
-            b.lo = (j > 0 && j <= k) ? s_sarea[j - 1] : 0.0;
-            b.hi = (j < k) ? s_sarea[j] : 1e300;
-            b.gm2 = __dmul_rn(b.lo, b.hi);
-            b.idx_lo = (j > 0 && j <= k) ? s_sidx[j - 1] : 0;
-            b.idx_hi = (j < k) ? s_sidx[j] : 0;
-            s_br[j] = b;
+            s_rank[c] = r;
         }
         for (int j = 0; j + 1 < k && !bad; ++j)
             if (!(s_sarea[j + 1] - s_sarea[j] > 1e-6 * s_sarea[j + 1])) bad = 1;
-        s_exact_all = bad;
+        const double tiny = 9.5367431640625e-07, huge = 1048576.0;  // 2^-20, 2^20
+        for (int sl = 0; sl < K; ++sl) {
+            double lo = INFINITY, hi = -INFINITY;   // never certain
+            int th = INT_MAX;
+            if (!bad && sl < k) {
+                lo = s_sarea[sl] * tiny * (1.0 + 1e-12);
+                hi = s_sarea[sl] * huge * (1.0 - 1e-12);
+                if (sl > 0) {
+                    const double A0 = s_sarea[sl - 1], A1 = s_sarea[sl];
+                    const double g = sqrt(A0 * A1), dl = 2e-15 + 1e-15 * sqrt(A1 / A0);
+                    lo = fmax(lo, g * (1.0 + dl));
+                }
+                if (sl + 1 < k) {
+                    const double A0 = s_sarea[sl], A1 = s_sarea[sl + 1];
+                    const double g = sqrt(A0 * A1), dl = 2e-15 + 1e-15 * sqrt(A1 / A0);
+                    hi = fmin(hi, g * (1.0 - dl));
+                    th = __double2hiint(g);
+                }
+            }
+            s_edge[sl] = make_double2(lo, hi);
+            s_thr_hi[sl] = th;
+        }
     }
     __syncthreads();
-    const bool exact_all = (s_exact_all != 0) || D < 2;
-    double sarea[K];  // sorted areas in registers: the bracket index is a count of K compares
+    int thr_hi[K > 1 ? K - 1 : 1];   // threshold high words in registers
 #pragma unroll
-    for (int c = 0; c < K; ++c) sarea[c] = s_sarea[c];
+    for (int c = 0; c + 1 < K; ++c) thr_hi[c] = s_thr_hi[c];
 
     const long long n_tiles = (L.n + tile_pts - 1) / tile_pts;
-    const long long n_my = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    auto issue = [&](long long t) {
-        const long long tile = blockIdx.x + t * gridDim.x;
-        const long long p0 = tile * tile_pts;
+    const long long wg = (long long)blockIdx.x * kKmWarps + warp, n_wg = (long long)gridDim.x * kKmWarps;
+    const long long n_my = (n_tiles > wg) ? (n_tiles - wg + n_wg - 1) / n_wg : 0;
+    double* my_ring = ring + (size_t)warp * n_stages * tile_pts * D;
+    uint64_t* my_full = full[warp];
+    auto issue = [&](long long t, int stage) {   // lane 0 only
+        const long long p0 = (wg + t * n_wg) * tile_pts;
         const int np = (int)min((long long)tile_pts, L.n - p0);
-        const int stage = (int)(t % n_stages);
-        double* dst = ring + (size_t)stage * tile_pts * D;
         const uint32_t bytes = (uint32_t)np * D * 8u;
         if (L.bulk_ok && (bytes & 15u) == 0u) {
-            mbar_arrive_expect_tx(&full[stage], bytes);
-            bulk_g2s(dst, L.data + p0 * D, bytes, &full[stage]);
+            mbar_arrive_expect_tx(&my_full[stage], bytes);
+            bulk_g2s(my_ring + (size_t)stage * tile_pts * D, L.data + p0 * D, bytes, &my_full[stage]);
         } else {
-            mbar_arrive(&full[stage]);  // consumers read global memory directly for this tile
+            mbar_arrive(&my_full[stage]);  // the warp reads global memory directly for this tile
         }
     };
-    if (tid == 0)
-        for (long long t = 0; t < min((long long)(n_stages - 1), n_my); ++t) issue(t);
+    if (lane == 0)
+        for (int t = 0; t < n_stages - 1 && t < n_my; ++t) issue(t, t);
 
     double* my_acc = s_acc + tid * D;
     int* my_cnt = s_cnt + tid;
+    int stage = 0, issue_stage = n_stages - 1;
+    uint32_t parity = 0;
     for (long long it = 0; it < n_my; ++it) {
-        if (tid == 0 && it + n_stages - 1 < n_my) issue(it + n_stages - 1);
-        const long long tile = blockIdx.x + it * gridDim.x;
-        const long long p0 = tile * tile_pts;
+        // the stage refilled here held tile it-1: every lane left it before the __syncwarp below
+        if (lane == 0 && it + n_stages - 1 < n_my) issue(it + n_stages - 1, issue_stage);
+        issue_stage = (issue_stage + 1 == n_stages) ? 0 : issue_stage + 1;
+        const long long p0 = (wg + it * n_wg) * tile_pts;
         const int np = (int)min((long long)tile_pts, L.n - p0);
-        const int stage = (int)(it % n_stages);
         const bool staged = L.bulk_ok && ((((uint32_t)np * D * 8u) & 15u) == 0u);
-        const double* src = staged ? ring + (size_t)stage * tile_pts * D : L.data + p0 * D;
-        mbar_wait(&full[stage], (uint32_t)((it / n_stages) & 1));
-#pragma unroll 2
-        for (int i = tid; i < np; i += kKmThreads) {
-            double v[D];
-            if (D == 2) {
-                const double2 t2 = *reinterpret_cast<const double2*>(src + (size_t)i * 2);
-                v[0] = t2.x;
-                v[D - 1] = t2.y;
-            } else {
+        const double* src = staged ? my_ring + (size_t)stage * tile_pts * D : L.data + p0 * D;
+        mbar_wait(&my_full[stage], parity);
+        if (kIou && D == 2) {
+            // batches of kU boxes per lane: loads, areas, slots and certainty tests of the whole
+            // batch are independent chains; only the accumulator updates are ordered
+            constexpr int kU = 4;
+            for (int base = 0; base < np; base += 32 * kU) {
+                double2 bx[kU];
+                int slot[kU];
+                bool have[kU], sure[kU];
+                double area[kU];
 #pragma unroll
-                for (int j = 0; j < D; ++j) v[j] = src[(size_t)i * D + j];
-            }
-            int best = 0;
-            if (kIou) {
-                const double a = __dmul_rn(v[0], v[D > 1 ? 1 : 0]);
-                int j = 0;  // number of centroid areas <= a
+                for (int u = 0; u < kU; ++u) {
+                    const int i = base + u * 32 + lane;
+                    have[u] = i < np;
+                    bx[u] = have[u] ? *reinterpret_cast<const double2*>(src + (size_t)i * 2) : make_double2(0.0, 0.0);
+                }
 #pragma unroll
-                for (int c = 0; c < K; ++c) j += (sarea[c] <= a) ? 1 : 0;
-                const KmBracket b = s_br[j];
-                const double tiny = 9.5367431640625e-07;  // 2^-20
-                const double q = __dmul_rn(a, a);
-                const double band = __dmul_rn(1e-15, __dmul_rn(a, b.hi));
-                const bool take_lo = b.gm2 > q;  // lo/a > a/hi: the smaller centroid is closer
-                best = take_lo ? b.idx_lo : b.idx_hi;
-                const bool far_enough = take_lo ? (b.lo >= tiny * a) : (a >= tiny * b.hi);
-                const bool sure = (fabs(b.gm2 - q) > band) && far_enough && !exact_all;
-                if (!sure) {
-                    double bd = 0.0;
-                    best = 0;
-                    for (int c = 0; c < k; ++c) {
-                        const double ca = s_carea[c];
-                        const double dist = 1.0 - fmin(ca, a) / fmax(ca, a);
-                        if (c == 0 || dist < bd) {
-                            bd = dist;
-                            best = c;
-                        }
+                for (int u = 0; u < kU; ++u) {
+                    area[u] = __dmul_rn(bx[u].x, bx[u].y);
+                    const int ah = __double2hiint(area[u]);
+                    int sl = 0;
+#pragma unroll
+                    for (int c = 0; c + 1 < K; ++c) sl += (ah > thr_hi[c]) ? 1 : 0;
+                    slot[u] = sl;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const double2 e = s_edge[slot[u]];
+                    sure[u] = area[u] > e.x && area[u] < e.y;
+                }
+#pragma unroll
+                for (int u = 0; u < kU; ++u)
+                    if (have[u] && !sure[u]) slot[u] = km_exact_slot(area[u], k, s_carea, s_rank);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    if (have[u]) {
+                        if (kAssign) L.assign[p0 + base + u * 32 + lane] = s_sidx[slot[u]];
+                        double2* acc = reinterpret_cast<double2*>(my_acc + slot[u] * (2 * kKmThreads));
+                        double2 t2 = *acc;
+                        t2.x += bx[u].x;
+                        t2.y += bx[u].y;
+                        *acc = t2;
+                        my_cnt[slot[u] * kKmThreads] += 1;
                     }
                 }
+            }
+        } else {
+        for (int i = lane; i < np; i += 32) {
+            double v[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) v[j] = src[(size_t)i * D + j];
+            int slot = 0;   // accumulator slot: SORTED position for iou_dist, cluster index otherwise
+            if (kIou) {
+                const double a = __dmul_rn(v[0], v[D > 1 ? 1 : 0]);
+                slot = km_exact_slot(a, k, s_carea, s_rank);
+                if (kAssign) L.assign[p0 + i] = s_sidx[slot];
             } else {
                 double bd = 0.0;
                 for (int c = 0; c < k; ++c) {
@@ -197,41 +242,40 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
                     const double dist = sqrt(sq);
                     if (c == 0 || dist < bd) {
                         bd = dist;
-                        best = c;
+                        slot = c;
                     }
                 }
+                if (kAssign) L.assign[p0 + i] = slot;
             }
-            if (kAssign) L.assign[p0 + i] = best;
-            double* slot = my_acc + best * (D * kKmThreads);
-            if (D == 2) {
-                double2 t2 = *reinterpret_cast<double2*>(slot);
-                t2.x += v[0];
-                t2.y += v[D - 1];
-                *reinterpret_cast<double2*>(slot) = t2;
-            } else {
+            double* acc = my_acc + slot * (D * kKmThreads);
 #pragma unroll
-                for (int j = 0; j < D; ++j) slot[j] += v[j];
-            }
-            my_cnt[best * kKmThreads] += 1;
+            for (int j = 0; j < D; ++j) acc[j] += v[j];
+            my_cnt[slot * kKmThreads] += 1;
         }
-        __syncthreads();  // stage free for the next bulk load
+        }
+        __syncwarp();  // stage free for the next bulk load
+        if (++stage == n_stages) {
+            stage = 0;
+            parity ^= 1u;
+        }
     }
 
     // ---- reduction: thread columns -> warp -> CTA -> global partials -> last CTA ----
     constexpr int NV = K * (D + 1);
-    for (int c = 0; c < K; ++c) {
+    for (int c = 0; c < K; ++c) {   // c = cluster index; its accumulator slot is its sorted rank (iou_dist)
+        const int sl = (kIou && c < k) ? s_rank[c] : c;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            const double sres = warp_sum(my_acc[c * (D * kKmThreads) + j]);
+            const double sres = warp_sum(my_acc[sl * (D * kKmThreads) + j]);
             if (lane == 0) s_red[warp * NV + c * (D + 1) + j] = sres;
         }
-        const int cs = warp_sum(my_cnt[c * kKmThreads]);
+        const int cs = warp_sum(my_cnt[sl * kKmThreads]);
         if (lane == 0) s_red[warp * NV + c * (D + 1) + D] = (double)cs;  // exact below 2^53
     }
     __syncthreads();
     if (tid < NV) {
         double sres = 0.0;
-        for (int w = 0; w < kKmThreads / 32; ++w) sres += s_red[w * NV + tid];
+        for (int w = 0; w < kKmWarps; ++w) sres += s_red[w * NV + tid];
         L.partials[(size_t)blockIdx.x * NV + tid] = sres;
     }
     __threadfence();
@@ -240,7 +284,7 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
-    for (int i = warp; i < NV; i += kKmThreads / 32) {
+    for (int i = warp; i < NV; i += kKmWarps) {
         double sres = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) sres += __ldcg(&L.partials[(size_t)b * NV + i]);
         sres = warp_sum(sres);
@@ -297,23 +341,25 @@ constexpr int kKmGrid = kNumSMs * 4;  // upper bound of the launch grid (partial
 
 template <int K, int D>
 static int launch_km(KmLaunch L, cudaStream_t stream) {
-    // accumulator planes + ring must fit: prefer 2 stages of 2048 boxes and 2 CTAs per SM (measured best:
-    // the per-tile barrier cost is amortised over 8 boxes per thread, see benchmarks/km_sweep.sh)
+    // accumulator planes + 8 per-warp rings must fit: prefer 2 stages of 256-point tiles per warp and
+    // 2 CTAs per SM (benchmarks/km_sweep.sh)
     const size_t acc = (size_t)K * kKmThreads * (D * sizeof(double) + sizeof(int));
-    const size_t budget2 = (227 * 1024) / 2 - 5 * 1024;   // per CTA with 2 CTAs/SM (static smem + reservation)
+    const size_t budget2 = (227 * 1024) / 2 - 4 * 1024;   // per CTA with 2 CTAs/SM (static smem + reservation)
     const size_t budget1 = 227 * 1024 - 8 * 1024;
-    int tile = 2048, stages = 2;
-    auto need = [&](int t, int st) { return acc + (size_t)st * t * D * sizeof(double); };
-    while (need(tile, stages) > budget2 && tile > 512) tile >>= 1;
+    int tile = 256, stages = 2;
+    auto need = [&](int t, int st) { return acc + (size_t)kKmWarps * st * t * D * sizeof(double); };
+    while (need(tile, stages) > budget2 && stages > 2) --stages;
+    while (need(tile, stages) > budget2 && tile > 32) tile >>= 1;
     if (need(tile, stages) > budget2) {   // fat k*d: one CTA per SM
-        tile = 1024;
-        while (need(tile, stages) > budget1 && tile > 128) tile >>= 1;
+        tile = 128;
+        stages = 3;
+        while (need(tile, stages) > budget1 && tile > 32) tile >>= 1;
         if (need(tile, stages) > budget1) return YB_E_SHAPE;
     }
     int ctas = (need(tile, stages) <= budget2) ? 2 : 1;
     {   // tuning hooks (debug): YB_KM_TILE / YB_KM_STAGES / YB_KM_CTAS
         const char* e;
-        if ((e = getenv("YB_KM_TILE")) && atoi(e) >= 128) tile = atoi(e) / 128 * 128;
+        if ((e = getenv("YB_KM_TILE")) && atoi(e) >= 32) tile = atoi(e) / 32 * 32;
         if ((e = getenv("YB_KM_STAGES")) && atoi(e) >= 2 && atoi(e) <= kKmMaxStages) stages = atoi(e);
         if ((e = getenv("YB_KM_CTAS")) && atoi(e) >= 1 && atoi(e) <= 4) ctas = atoi(e);
         if (need(tile, stages) > budget1) return YB_E_SHAPE;
@@ -322,7 +368,7 @@ static int launch_km(KmLaunch L, cudaStream_t stream) {
     L.n_stages = stages;
     const size_t smem = need(tile, stages);
     const long long n_tiles = (L.n + tile - 1) / tile;
-    const int grid = (int)max(1LL, min((long long)kNumSMs * ctas, n_tiles));
+    const int grid = (int)max(1LL, min((long long)kNumSMs * ctas, (n_tiles + kKmWarps - 1) / kKmWarps));
 #define YB_KM_LAUNCH(IOU, ASSIGN)                                                                          \
     do {                                                                                                   \
         YB_CUDA_TRY(cudaFuncSetAttribute(kmeans_assign_kernel<K, D, IOU, ASSIGN>,                          \

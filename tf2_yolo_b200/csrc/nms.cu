@@ -26,69 +26,136 @@ namespace yb {
 
 constexpr double kIouEps = 1e-07;  // utils/tools.py:26
 constexpr int kBigThreads = 256;
-constexpr int kBigCap = 2048;      // boxes per segment held in shared memory
+constexpr int kBigCap = 1536;      // boxes per segment held in shared memory
+constexpr int kBigP = 2048;        // power-of-two padding of the index arrays of such a segment
 constexpr int kSweep = 64;         // sweep block (one 64-bit mask word per box)
 
+// np.maximum / np.minimum: NaN propagates (fmax/fmin would drop it)
+__device__ __forceinline__ double np_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+__device__ __forceinline__ double np_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+// the same for operands known not to be NaN: one compare + select
+__device__ __forceinline__ double sel_max(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double sel_min(double a, double b) { return a < b ? a : b; }
+
 // IoU (MODE 1) or DIoU (MODE 2) of "true" box t against "pred" box p, the
-// reference's operation order (tools.py:649-682).
+// reference's operation order (tools.py:649-682), NaN/Inf behaving as in NumPy.
 template <int MODE>
 __device__ __forceinline__ double pair_iou(double tx, double ty, double tw, double th, double px,
                                            double py, double pw, double ph) {
     const double thw = tw / 2.0, thh = th / 2.0, phw = pw / 2.0, phh = ph / 2.0;
     const double t0x = tx - thw, t0y = ty - thh, t1x = tx + thw, t1y = ty + thh;
     const double p0x = px - phw, p0y = py - phh, p1x = px + phw, p1y = py + phh;
-    const double iw = fmax(fmin(p1x, t1x) - fmax(p0x, t0x), 0.0);
-    const double ih = fmax(fmin(p1y, t1y) - fmax(p0y, t0y), 0.0);
+    const double iw = np_max(np_min(p1x, t1x) - np_max(p0x, t0x), 0.0);
+    const double ih = np_max(np_min(p1y, t1y) - np_max(p0y, t0y), 0.0);
     const double inter = iw * ih;
     const double uni = pw * ph + tw * th - inter;
     const double iou = inter / (uni + kIouEps);
     if (MODE == 1) return iou;
-    const double ew = fmax(p1x, t1x) - fmin(p0x, t0x), eh = fmax(p1y, t1y) - fmin(p0y, t0y);
+    const double ew = np_max(p1x, t1x) - np_min(p0x, t0x), eh = np_max(p1y, t1y) - np_min(p0y, t0y);
     const double c2 = ew * ew + eh * eh;
     const double dx = tx - px, dy = ty - py;
     const double rho2 = dx * dx + dy * dy;
     return iou - rho2 / c2;
 }
 
-// Does box t suppress box p, i.e. is fl(IoU) (MODE 1) / fl(fl(IoU) - fl(rho2/c2)) (MODE 2) >= thr ?
-// Same truth value as comparing pair_iou<MODE>() with thr, but decided WITHOUT a division
-// whenever the cross-multiplied inequality holds with a margin wider than every rounding
-// error involved; only pairs inside that margin (and non-finite cases) evaluate the exact
-// expression.  fp64 division is the latency of this kernel, the margin test is ~10 multiplies.
+// A box as the sweeps use it: corners and area computed ONCE per box with the reference's
+// operations (x -+ w/2, y -+ h/2, w*h: tools.py:649-653,660), so every pair starts from the same
+// bits the broadcast expression produces.  A box with a NaN among these values can neither
+// suppress nor be suppressed (NumPy propagates the NaN into the IoU, which compares False): it is
+// staged as an inverted box at infinity, whose overlap with anything is negative.
+struct BoxC {
+    double x0, x1, y0, y1, area, cx, cy;
+};
+
+__device__ __forceinline__ BoxC make_box(double x, double y, double w, double h) {
+    BoxC b;
+    const double hw = w / 2.0, hh = h / 2.0;
+    b.x0 = x - hw; b.x1 = x + hw; b.y0 = y - hh; b.y1 = y + hh;
+    b.area = w * h;
+    b.cx = x; b.cy = y;
+    const double probe = ((b.x0 + b.x1) + (b.y0 + b.y1)) + b.area;   // NaN iff any of them is (or inf - inf)
+    if (probe != probe && (b.x0 != b.x0 || b.x1 != b.x1 || b.y0 != b.y0 || b.y1 != b.y1 || b.area != b.area)) {
+        b.x0 = INFINITY; b.x1 = -INFINITY; b.y0 = INFINITY; b.y1 = -INFINITY;
+    }
+    return b;
+}
+
+// fp64 division the compiler may not move: the sweeps reach the exact expression for a vanishing
+// fraction of the pairs, but a plain `/` lets the compiler hoist the division (and its slow path
+// for a zero numerator) in front of the margin tests of EVERY pair.
+__device__ __forceinline__ double div_pinned(double a, double b) {
+    double q;
+    asm volatile("div.rn.f64 %0, %1, %2;" : "=d"(q) : "d"(a), "d"(b));
+    return q;
+}
+
+// Exact decision from the original rows: the reference's expression with IEEE divisions.
 template <int MODE>
-__device__ __forceinline__ bool suppresses(double tx, double ty, double tw, double th, double px,
-                                           double py, double pw, double ph, double thr) {
+__device__ __forceinline__ bool suppresses_exact(const double* __restrict__ rows, long long ra, long long rb,
+                                                 double thr) {
+    const double* a = rows + ra * 7;
+    const double* b = rows + rb * 7;
+    const double tx = a[0], ty = a[1], tw = a[2], th = a[3], px = b[0], py = b[1], pw = b[2], ph = b[3];
     const double thw = tw / 2.0, thh = th / 2.0, phw = pw / 2.0, phh = ph / 2.0;
     const double t0x = tx - thw, t0y = ty - thh, t1x = tx + thw, t1y = ty + thh;
     const double p0x = px - phw, p0y = py - phh, p1x = px + phw, p1y = py + phh;
-    const double iw = fmax(fmin(p1x, t1x) - fmax(p0x, t0x), 0.0);
-    const double ih = fmax(fmin(p1y, t1y) - fmax(p0y, t0y), 0.0);
+    const double iw = np_max(np_min(p1x, t1x) - np_max(p0x, t0x), 0.0);
+    const double ih = np_max(np_min(p1y, t1y) - np_max(p0y, t0y), 0.0);
     const double inter = iw * ih;
-    const double den = (pw * ph + tw * th - inter) + kIouEps;
-    if (MODE == 1) {
-        if (thr > 0.0) {
-            // x = inter/den (real).  x >= thr => fl(x) >= thr;  x < thr(1-2^-51) => fl(x) < thr.
-            const double P = thr * den;
-            if (inter >= P * (1.0 + 4.5e-16)) return true;
-            if (inter <= P * (1.0 - 9.0e-16)) return false;
-        }
-        return inter / den >= thr;
-    }
-    const double ew = fmax(p1x, t1x) - fmin(p0x, t0x), eh = fmax(p1y, t1y) - fmin(p0y, t0y);
+    const double uni = pw * ph + tw * th - inter;
+    const double iou = div_pinned(inter, uni + kIouEps);
+    if (MODE == 1) return iou >= thr;
+    const double ew = np_max(p1x, t1x) - np_min(p0x, t0x), eh = np_max(p1y, t1y) - np_min(p0y, t0y);
     const double c2 = ew * ew + eh * eh;
     const double dx = tx - px, dy = ty - py;
     const double rho2 = dx * dx + dy * dy;
-    {
-        // y = inter/den - rho2/c2 (real); the computed value differs from y by < 4e-16 for
-        // |terms| <= 1, so |y - thr| > 1e-15 decides.  y - thr = (A - B - thr*S) / S with
-        // A = inter*c2, B = rho2*den, S = den*c2 > 0; every product carries 2^-53 relative error.
-        const double A = inter * c2, B = rho2 * den, S = den * c2;
-        const double lhs = A - B, rhs = thr * S;
-        const double slack = 4.5e-16 * (A + B + fabs(rhs)) + 2.0e-15 * S;
-        if (lhs - rhs > slack && inter <= den && rho2 <= c2) return true;
-        if (rhs - lhs > slack && inter <= den && rho2 <= c2) return false;
+    return (iou - div_pinned(rho2, c2)) >= thr;
+}
+
+// Does box a suppress box b, i.e. is fl(IoU) (MODE 1) / fl(fl(IoU) - fl(rho2/c2)) (MODE 2) >= thr ?
+// Returns 1 / 0 when the answer is certain WITHOUT a division, -1 when the exact expression must be
+// evaluated:
+//   * thr > 0 and the boxes do not overlap: inter = 0, so IoU = 0 (or NaN) and DIoU <= 0 (or NaN):
+//     never >= thr.  This also covers NaN boxes (staged with negative overlap).
+//   * otherwise the cross-multiplied inequality is tested with a margin wider than every rounding
+//     error involved (x = inter/den real: x >= thr => fl(x) >= thr; x < thr(1-2^-51) => fl(x) < thr).
+template <int MODE>
+__device__ __forceinline__ int suppresses_fast(const BoxC& a, const BoxC& b, double thr, bool pos_thr) {
+    const double iw = sel_min(a.x1, b.x1) - sel_max(a.x0, b.x0);
+    const double ih = sel_min(a.y1, b.y1) - sel_max(a.y0, b.y0);
+    if (!pos_thr) return -1;
+    if (!(iw > 0.0 && ih > 0.0)) return 0;
+    const double inter = iw * ih;
+    const double den = ((b.area + a.area) - inter) + kIouEps;
+    if (!(den > 0.0)) return -1;
+    if (MODE == 1) {
+        const double P = thr * den;
+        if (inter >= P * (1.0 + 4.5e-16)) return 1;
+        if (inter <= P * (1.0 - 9.0e-16)) return 0;
+        return -1;
     }
-    return (inter / den - rho2 / c2) >= thr;
+    const double ew = sel_max(a.x1, b.x1) - sel_min(a.x0, b.x0), eh = sel_max(a.y1, b.y1) - sel_min(a.y0, b.y0);
+    const double c2 = ew * ew + eh * eh;
+    const double dx = a.cx - b.cx, dy = a.cy - b.cy;
+    const double rho2 = dx * dx + dy * dy;
+    // y = inter/den - rho2/c2 (real); the computed value differs from y by < 4e-16 for
+    // |terms| <= 1, so |y - thr| > 1e-15 decides.  y - thr = (A - B - thr*S) / S with
+    // A = inter*c2, B = rho2*den, S = den*c2 > 0; every product carries 2^-53 relative error.
+    const double A = inter * c2, B = rho2 * den, S = den * c2;
+    const double lhs = A - B, rhs = thr * S;
+    const double slack = 4.5e-16 * (A + B + fabs(rhs)) + 2.0e-15 * S;
+    const bool sane = inter <= den && rho2 <= c2;
+    if (lhs - rhs > slack && sane) return 1;
+    if (rhs - lhs > slack && sane) return 0;
+    return -1;
+}
+
+template <int MODE>
+__device__ __forceinline__ bool suppresses(const BoxC& a, const BoxC& b, double thr, bool pos_thr,
+                                           const double* __restrict__ rows, long long ra, long long rb) {
+    const int r = suppresses_fast<MODE>(a, b, thr, pos_thr);
+    if (r >= 0) return r != 0;
+    return suppresses_exact<MODE>(rows, ra, rb, thr);
 }
 
 struct NmsWs {
@@ -103,7 +170,7 @@ struct NmsWs {
     int* local_rank;         // [R]
     int* small_list;         // [n_seg]
     int* big_list;           // [n_seg]
-    double* gbox;            // [5][R]: x, y, w, h, conf  (segments > kBigCap)
+    double* gbox;            // [7][R]: planes X(2) Y(2) C(2) A(1) of segments > kBigCap
     int* gmem_pad;           // [2R] padded handle array
     int* gord_pad;           // [2R]
     unsigned char* gremoved; // [R]
@@ -165,11 +232,22 @@ __global__ void nms_scatter_kernel(const long long* __restrict__ row_offsets, lo
 }
 
 // ---- small segments: one warp each ---------------------------------------------
+__device__ __forceinline__ BoxC shfl_box(const BoxC& b, int src, bool with_centre) {
+    BoxC r;
+    r.x0 = __shfl_sync(0xffffffffu, b.x0, src); r.x1 = __shfl_sync(0xffffffffu, b.x1, src);
+    r.y0 = __shfl_sync(0xffffffffu, b.y0, src); r.y1 = __shfl_sync(0xffffffffu, b.y1, src);
+    r.area = __shfl_sync(0xffffffffu, b.area, src);
+    r.cx = with_centre ? __shfl_sync(0xffffffffu, b.cx, src) : 0.0;
+    r.cy = with_centre ? __shfl_sync(0xffffffffu, b.cy, src) : 0.0;
+    return r;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
 nms_small_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W,
                  unsigned char* __restrict__ keep) {
     const int lane = threadIdx.x & 31;
+    const bool pos_thr = thr > 0.0;
     // static round-robin over the work list (segments are at most 32 boxes: balanced enough, and a
     // work-stealing atomic per segment costs more than the segment)
     const unsigned n_work = W.ctrl[0];
@@ -198,16 +276,18 @@ nms_small_kernel(const double* __restrict__ rows, double thr, double conf_thr, d
             x = r[0]; y = r[1]; bw = r[2]; bh = r[3];
             conf = __dmul_rn(r[4], r[6]);
         }
+        const BoxC mine = make_box(x, y, bw, bh);
         // visit rank: descending confidence, ties -> higher original index first
         int vis = 0;
         unsigned sup = 0;
-#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const double cj = __shfl_sync(0xffffffffu, conf, j);
             vis += (cj > conf || (cj == conf && j > lane)) ? 1 : 0;
-            const double xj = __shfl_sync(0xffffffffu, x, j), yj = __shfl_sync(0xffffffffu, y, j);
-            const double wj = __shfl_sync(0xffffffffu, bw, j), hj = __shfl_sync(0xffffffffu, bh, j);
-            if (MODE != 3 && suppresses<(MODE == 3 ? 1 : MODE)>(x, y, bw, bh, xj, yj, wj, hj, thr)) sup |= 1u << j;
+            if (MODE != 3) {
+                const BoxC other = shfl_box(mine, j, MODE == 2);
+                const int mj = __shfl_sync(0xffffffffu, m, j);
+                if (lane < n && suppresses<(MODE == 3 ? 1 : MODE)>(mine, other, thr, pos_thr, rows, m, mj)) sup |= 1u << j;
+            }
         }
         unsigned dead = 0, seen = 0;
         if (MODE == 3) {
@@ -272,20 +352,216 @@ __device__ __forceinline__ void block_bitonic(int* h, int P, Less less) {
     }
 }
 
+// Scratch shared by all segments of a CTA (static shared memory).
+struct BigShared {
+    unsigned long long mask[kSweep];
+    double2 kX[kSweep], kY[kSweep], kC[kSweep];  // kept boxes of the current sweep block, compact
+    double kA[kSweep];
+    int kept[kSweep];
+    int krow[kSweep];
+    int nkept;
+    long long scan[32];
+};
+
+// One segment.  The planes hold the boxes in VISIT order: X = (x0, x1), Y = (y0, y1), C = (x, y)
+// (DIoU only), A = area; soft-NMS (MODE 3) keeps X = (x, y), Y = (w, h) instead.  cf (confidences,
+// later the keep flags) aliases A.  SMEM only tells the compiler which address space the plane
+// pointers live in (the function is inlined once per space).
+template <int MODE, bool SMEM>
+__device__ __forceinline__ void nms_segment(const double* __restrict__ rows, double thr, double conf_thr, double sigma,
+                                            const NmsWs& W, int seg, int n, long long start, int P, int* mem, int* ord,
+                                            double2* X, double2* Y, double2* C, double* A, unsigned char* rem,
+                                            BigShared& S, unsigned char* __restrict__ keep) {
+    constexpr int M = (MODE == 3) ? 1 : MODE;
+    constexpr int kJpt = (M == 2) ? 2 : 3;   // boxes a thread carries at once through the kept list
+    const int tid = threadIdx.x;
+    const bool pos_thr = thr > 0.0;
+    double* cf = A;
+
+    // 1. original order: sort row ids ascending
+    for (int i = tid; i < P; i += kBigThreads) mem[i] = (i < n) ? W.members[start + i] : INT_MAX;
+    __syncthreads();
+    block_bitonic(mem, P, [](int a, int b) { return a < b; });
+    for (int i = tid; i < n; i += kBigThreads) {
+        const int m = mem[i];
+        W.members[start + i] = m;
+        const double* r = rows + (long long)m * 7;
+        cf[i] = __dmul_rn(r[4], r[6]);
+        ord[i] = i;
+    }
+    for (int i = n + tid; i < P; i += kBigThreads) ord[i] = INT_MAX;
+    __syncthreads();
+    // 2. visit order: confidence descending, ties -> higher original index first
+    block_bitonic(ord, P, [cf, n](int a, int b) {
+        if (a >= n || b >= n) return a < b;
+        const double ca = cf[a], cb = cf[b];
+        return ca > cb || (ca == cb && a > b);
+    });
+    if (MODE == 3) {
+        // soft-NMS: every box multiplies its confidence by exp(-IoU^2/sigma) for each earlier-visited
+        // box it overlaps (in visit order); deleted <=> it was decayed below conf_thr.
+        for (int v = tid; v < n; v += kBigThreads) {
+            const double* r = rows + (long long)mem[ord[v]] * 7;
+            X[v] = make_double2(r[0], r[1]);
+            Y[v] = make_double2(r[2], r[3]);
+        }
+        __syncthreads();
+        for (int v = tid; v < n; v += kBigThreads) {
+            double c = cf[ord[v]];
+            const double2 xy = X[v], wh = Y[v];
+            bool decayed = false;
+            for (int i = 0; i < v; ++i) {
+                const double2 pxy = X[i], pwh = Y[i];
+                const double iou = pair_iou<1>(pxy.x, pxy.y, pwh.x, pwh.y, xy.x, xy.y, wh.x, wh.y);
+                if (iou >= thr) {
+                    c = c * exp(-1.0 * (iou * iou) / sigma);
+                    decayed = true;
+                }
+            }
+            rem[v] = (decayed && c < conf_thr) ? 1 : 0;
+        }
+        __syncthreads();
+    } else {
+        // boxes in visit order (the confidence plane is dead from here on)
+        __syncthreads();
+        for (int v = tid; v < n; v += kBigThreads) {
+            const double* r = rows + (long long)mem[ord[v]] * 7;
+            const BoxC b = make_box(r[0], r[1], r[2], r[3]);
+            X[v] = make_double2(b.x0, b.x1);
+            Y[v] = make_double2(b.y0, b.y1);
+            if (M == 2) C[v] = make_double2(b.cx, b.cy);
+            A[v] = b.area;
+            rem[v] = 0;
+        }
+        __syncthreads();
+    }
+    auto load_box = [&](int v) {
+        BoxC b;
+        const double2 x = X[v], y = Y[v];
+        b.x0 = x.x; b.x1 = x.y; b.y0 = y.x; b.y1 = y.y;
+        b.area = A[v];
+        if (M == 2) { const double2 c = C[v]; b.cx = c.x; b.cy = c.y; } else { b.cx = 0.0; b.cy = 0.0; }
+        return b;
+    };
+    // 3. blocked greedy sweep
+    for (int blk = 0; MODE != 3 && blk < n; blk += kSweep) {
+        const int m = min(kSweep, n - blk);
+        if (tid < kSweep) S.mask[tid] = 0ull;
+        __syncthreads();
+        {   // 64x64 upper-triangular mask, 4 threads per row (16 columns each)
+            const int i = tid >> 2, part = tid & 3;
+            if (i < m && !rem[blk + i]) {
+                const BoxC bi = load_box(blk + i);
+                unsigned long long bits = 0ull;
+                const int j0 = max(part * 16, i + 1), j1 = min(part * 16 + 16, m);
+                for (int j = j0; j < j1; ++j) {
+                    const BoxC bj = load_box(blk + j);
+                    int r = suppresses_fast<M>(bi, bj, thr, pos_thr);
+                    if (r < 0) r = suppresses_exact<M>(rows, mem[ord[blk + i]], mem[ord[blk + j]], thr) ? 1 : 0;
+                    if (r) bits |= 1ull << j;
+                }
+                if (bits) atomicOr(&S.mask[i], bits);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long dead = 0ull;
+            for (int i = 0; i < m; ++i) if (rem[blk + i]) dead |= 1ull << i;
+            int nk = 0;
+            for (int i = 0; i < m; ++i) {
+                if (!((dead >> i) & 1ull)) {
+                    dead |= S.mask[i];
+                    S.kept[nk++] = blk + i;
+                }
+            }
+            for (int i = 0; i < m; ++i) rem[blk + i] = (unsigned char)((dead >> i) & 1ull);
+            S.nkept = nk;
+        }
+        __syncthreads();
+        const int nk = S.nkept;
+        if (blk + m >= n) continue;   // last block: nothing left to suppress (uniform)
+        if (tid < nk) {               // kept boxes of this block, compact
+            const int v = S.kept[tid];
+            S.kX[tid] = X[v];
+            S.kY[tid] = Y[v];
+            if (M == 2) S.kC[tid] = C[v];
+            S.kA[tid] = A[v];
+            S.krow[tid] = mem[ord[v]];
+        }
+        __syncthreads();
+        // every surviving box behind the block against the block's kept boxes, kJpt boxes per
+        // thread in flight (independent fp64 chains; the kept box is one broadcast load for all)
+        for (int base = blk + m; base < n; base += kBigThreads * kJpt) {
+            BoxC bj[kJpt];
+            int jj[kJpt];
+            bool alive[kJpt];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < kJpt; ++u) {
+                jj[u] = base + u * kBigThreads + tid;
+                alive[u] = jj[u] < n && !rem[jj[u]];
+                if (alive[u]) bj[u] = load_box(jj[u]);
+                any |= alive[u];
+            }
+            if (!any) continue;
+            for (int q = 0; q < nk; ++q) {
+                BoxC bi;
+                {
+                    const double2 x = S.kX[q], y = S.kY[q];
+                    bi.x0 = x.x; bi.x1 = x.y; bi.y0 = y.x; bi.y1 = y.y;
+                    bi.area = S.kA[q];
+                    if (M == 2) { const double2 c = S.kC[q]; bi.cx = c.x; bi.cy = c.y; } else { bi.cx = 0.0; bi.cy = 0.0; }
+                }
+                any = false;
+#pragma unroll
+                for (int u = 0; u < kJpt; ++u) {
+                    if (alive[u]) {
+                        int r = suppresses_fast<M>(bi, bj[u], thr, pos_thr);
+                        if (r < 0) r = suppresses_exact<M>(rows, S.krow[q], mem[ord[jj[u]]], thr) ? 1 : 0;
+                        if (r) {
+                            alive[u] = false;
+                            rem[jj[u]] = 1;
+                        }
+                    }
+                    any |= alive[u];
+                }
+                if (!any) break;
+            }
+        }
+        __syncthreads();
+    }
+    // 4. survivors back in original order: keep flag per original position goes into
+    //    the (now dead) confidence plane, then a block scan gives each survivor its rank
+    for (int v = tid; v < n; v += kBigThreads) cf[ord[v]] = rem[v] ? 0.0 : 1.0;
+    __syncthreads();
+    long long carry = 0;
+    for (int base = 0; base < n; base += kBigThreads) {
+        const int i = base + tid;
+        const int kf = (i < n && cf[i] != 0.0) ? 1 : 0;
+        long long total;
+        const long long ex = block_exclusive_scan((long long)kf, S.scan, total);
+        if (i < n) {
+            W.local_rank[start + i] = kf ? (int)(carry + ex) : -1;
+            keep[mem[i]] = (unsigned char)kf;
+        }
+        carry += total;
+    }
+    if (tid == 0) W.seg_kept[seg] = (unsigned)carry;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(kBigThreads)
+__global__ void __launch_bounds__(kBigThreads, 2)
 nms_big_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W, long long R,
                unsigned char* __restrict__ keep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* s_box = reinterpret_cast<double*>(smem_raw);                 // [5][kBigCap]
-    int* s_mem = reinterpret_cast<int*>(s_box + 5 * kBigCap);            // [kBigCap]
-    int* s_ord = s_mem + kBigCap;                                        // [kBigCap]
-    unsigned char* s_rem = reinterpret_cast<unsigned char*>(s_ord + kBigCap);  // [kBigCap]
-    __shared__ unsigned long long s_mask[kSweep];
-    __shared__ int s_kept[kSweep];
-    __shared__ int s_nkept;
-    __shared__ long long s_scan[32];
-    const int tid = threadIdx.x;
+    double2* s_X = reinterpret_cast<double2*>(smem_raw);                  // [kBigCap] each
+    double2* s_Y = s_X + kBigCap;
+    double2* s_C = s_Y + kBigCap;
+    double* s_A = reinterpret_cast<double*>(s_C + kBigCap);
+    int* s_mem = reinterpret_cast<int*>(s_A + kBigCap);                   // [kBigP]
+    int* s_ord = s_mem + kBigP;                                           // [kBigP]
+    unsigned char* s_rem = reinterpret_cast<unsigned char*>(s_ord + kBigP);  // [kBigCap]
+    __shared__ BigShared S;
 
     const unsigned n_work = W.ctrl[1];
     for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
@@ -295,122 +571,17 @@ nms_big_kernel(const double* __restrict__ rows, double thr, double conf_thr, dou
         const long long start = W.seg_start[seg];
         int P = 1;
         while (P < n) P <<= 1;
-        const bool in_smem = n <= kBigCap;
-        int* mem = in_smem ? s_mem : W.gmem_pad + 2 * start;
-        int* ord = in_smem ? s_ord : W.gord_pad + 2 * start;
-        double* bx = in_smem ? s_box : W.gbox + start;
-        const long long bs = in_smem ? kBigCap : R;  // stride between the 5 planes
-        double* by = bx + bs; double* bwd = bx + 2 * bs; double* bht = bx + 3 * bs; double* cf = bx + 4 * bs;
-        unsigned char* rem = in_smem ? s_rem : W.gremoved + start;
-
-        // 1. original order: sort row ids ascending
-        for (int i = tid; i < P; i += kBigThreads) mem[i] = (i < n) ? W.members[start + i] : INT_MAX;
-        __syncthreads();
-        block_bitonic(mem, P, [](int a, int b) { return a < b; });
-        for (int i = tid; i < n; i += kBigThreads) {
-            const int m = mem[i];
-            W.members[start + i] = m;
-            const double* r = rows + (long long)m * 7;
-            cf[i] = __dmul_rn(r[4], r[6]);
-            ord[i] = i;
+        if (n <= kBigCap) {
+            nms_segment<MODE, true>(rows, thr, conf_thr, sigma, W, seg, n, start, P, s_mem, s_ord, s_X, s_Y, s_C, s_A,
+                                    s_rem, S, keep);
+        } else {   // planes in the global scratch: [X 2R | Y 2R | C 2R | A R] doubles
+            double2* gX = reinterpret_cast<double2*>(W.gbox) + start;
+            double2* gY = reinterpret_cast<double2*>(W.gbox + 2 * R) + start;
+            double2* gC = reinterpret_cast<double2*>(W.gbox + 4 * R) + start;
+            double* gA = W.gbox + 6 * R + start;
+            nms_segment<MODE, false>(rows, thr, conf_thr, sigma, W, seg, n, start, P, W.gmem_pad + 2 * start,
+                                     W.gord_pad + 2 * start, gX, gY, gC, gA, W.gremoved + start, S, keep);
         }
-        for (int i = n + tid; i < P; i += kBigThreads) ord[i] = INT_MAX;
-        __syncthreads();
-        // 2. visit order: confidence descending, ties -> higher original index first
-        block_bitonic(ord, P, [cf, n](int a, int b) {
-            if (a >= n || b >= n) return a < b;
-            const double ca = cf[a], cb = cf[b];
-            return ca > cb || (ca == cb && a > b);
-        });
-        // boxes in visit order (conf plane is dead from here on)
-        for (int v = tid; v < n; v += kBigThreads) {
-            const double* r = rows + (long long)mem[ord[v]] * 7;
-            bx[v] = r[0]; by[v] = r[1]; bwd[v] = r[2]; bht[v] = r[3];
-            rem[v] = 0;
-        }
-        __syncthreads();
-        if (MODE == 3) {
-            // soft-NMS: every box multiplies its confidence by exp(-IoU^2/sigma) for each earlier-visited
-            // box it overlaps (in visit order); deleted <=> it was decayed below conf_thr.
-            for (int v = tid; v < n; v += kBigThreads) {
-                double c = cf[ord[v]];
-                const double x = bx[v], y = by[v], w = bwd[v], h = bht[v];
-                bool decayed = false;
-                for (int i = 0; i < v; ++i) {
-                    const double iou = pair_iou<1>(bx[i], by[i], bwd[i], bht[i], x, y, w, h);
-                    if (iou >= thr) {
-                        c = c * exp(-1.0 * (iou * iou) / sigma);
-                        decayed = true;
-                    }
-                }
-                rem[v] = (decayed && c < conf_thr) ? 1 : 0;
-            }
-            __syncthreads();
-        }
-        // 3. blocked greedy sweep
-        for (int blk = 0; MODE != 3 && blk < n; blk += kSweep) {
-            const int m = min(kSweep, n - blk);
-            if (tid < kSweep) s_mask[tid] = 0ull;
-            __syncthreads();
-            {   // 64x64 upper-triangular mask, 4 threads per row (16 columns each)
-                const int i = tid >> 2, part = tid & 3;
-                if (i < m && !rem[blk + i]) {
-                    const double x = bx[blk + i], y = by[blk + i], w = bwd[blk + i], h = bht[blk + i];
-                    unsigned long long bits = 0ull;
-                    const int j0 = max(part * 16, i + 1), j1 = min(part * 16 + 16, m);
-#pragma unroll 4
-                    for (int j = j0; j < j1; ++j)
-                        if (suppresses<(MODE == 3 ? 1 : MODE)>(x, y, w, h, bx[blk + j], by[blk + j], bwd[blk + j], bht[blk + j], thr))
-                            bits |= 1ull << j;
-                    if (bits) atomicOr(&s_mask[i], bits);
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned long long dead = 0ull;
-                for (int i = 0; i < m; ++i) if (rem[blk + i]) dead |= 1ull << i;
-                int nk = 0;
-                for (int i = 0; i < m; ++i) {
-                    if (!((dead >> i) & 1ull)) {
-                        dead |= s_mask[i];
-                        s_kept[nk++] = blk + i;
-                    }
-                }
-                for (int i = 0; i < m; ++i) rem[blk + i] = (unsigned char)((dead >> i) & 1ull);
-                s_nkept = nk;
-            }
-            __syncthreads();
-            const int nk = s_nkept;
-            for (int j = blk + m + tid; j < n; j += kBigThreads) {
-                if (rem[j]) continue;
-                const double x = bx[j], y = by[j], w = bwd[j], h = bht[j];
-                for (int q = 0; q < nk; ++q) {
-                    const int i = s_kept[q];
-                    if (suppresses<(MODE == 3 ? 1 : MODE)>(bx[i], by[i], bwd[i], bht[i], x, y, w, h, thr)) {
-                        rem[j] = 1;
-                        break;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        // 4. survivors back in original order: keep flag per original position goes into
-        //    the (now dead) confidence plane, then a block scan gives each survivor its rank
-        for (int v = tid; v < n; v += kBigThreads) cf[ord[v]] = rem[v] ? 0.0 : 1.0;
-        __syncthreads();
-        long long carry = 0;
-        for (int base = 0; base < n; base += kBigThreads) {
-            const int i = base + tid;
-            const int kf = (i < n && cf[i] != 0.0) ? 1 : 0;
-            long long total;
-            const long long ex = block_exclusive_scan((long long)kf, s_scan, total);
-            if (i < n) {
-                W.local_rank[start + i] = kf ? (int)(carry + ex) : -1;
-                keep[mem[i]] = (unsigned char)kf;
-            }
-            carry += total;
-        }
-        if (tid == 0) W.seg_kept[seg] = (unsigned)carry;
     }
 }
 
@@ -491,7 +662,7 @@ static size_t nms_layout(long long R, long long n_seg, NmsWs* W, char* base) {
     YB_CARVE(local_rank, int, R)
     YB_CARVE(small_list, int, n_seg)
     YB_CARVE(big_list, int, n_seg)
-    YB_CARVE(gbox, double, 5 * R)
+    YB_CARVE(gbox, double, 7 * R)
     YB_CARVE(gmem_pad, int, 2 * R)
     YB_CARVE(gord_pad, int, 2 * R)
     YB_CARVE(gremoved, unsigned char, R)
@@ -550,7 +721,7 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
     YB_CUDA_TRY(cudaGetLastError());
 
     const int small_blocks = (int)min((long long)kNumSMs * 4, (n_seg * 32 + threads - 1) / threads);
-    const size_t big_smem = sizeof(double) * 5 * kBigCap + sizeof(int) * 2 * kBigCap + kBigCap;
+    const size_t big_smem = sizeof(double) * 7 * kBigCap + sizeof(int) * 2 * kBigP + kBigCap;
     const int big_blocks = (int)min((long long)kNumSMs * 2, n_seg);
 #define YB_NMS_LAUNCH(M)                                                                                       \
     do {                                                                                                       \

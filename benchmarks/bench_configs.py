@@ -27,7 +27,10 @@ if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 
 
-def timed(fn, warm=3, reps=10, flush=None):
+def timed(fn, warm=3, reps=10, flush=None, burst=1):
+    """Median / min CUDA-event time of one call.  burst > 1 queues that many calls between the two
+    events (inputs larger than L2 only), so the host's launch latency is hidden behind the GPU work
+    as it is in a real loop; burst == 1 with a flush buffer is for working sets that fit L2."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -37,10 +40,11 @@ def timed(fn, warm=3, reps=10, flush=None):
             flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fn()
+        for _ in range(burst):
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        ts.append(e0.elapsed_time(e1) / burst)
     return float(np.median(ts)), float(np.min(ts))
 
 
@@ -67,8 +71,9 @@ def grid_config(name, version, out):
     small = loss_bytes < 126e6
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
     rows = torch.empty((4096 * batch, 7), dtype=torch.float64, device="cuda")
-    t_loss, t_loss_min = timed(lambda: fused_losses(fns, yt, yp, dpreds=dp), flush=flush)
-    t_dec, _ = timed(lambda: engine.decode_batch(yp, C, 0.5, version, rows=rows), flush=flush)
+    burst = 1 if small else 8
+    t_loss, t_loss_min = timed(lambda: fused_losses(fns, yt, yp, dpreds=dp), flush=flush, burst=burst)
+    t_dec, _ = timed(lambda: engine.decode_batch(yp, C, 0.5, version, rows=rows), flush=flush, burst=burst)
     _, offs = engine.decode_batch(yp, C, 0.5, version, rows=rows)
     t_nms, _ = timed(lambda: engine.nms_batch(rows, offs, C, 0.45, 2 if version == 4 else 1))
     out[name] = {
@@ -77,7 +82,7 @@ def grid_config(name, version, out):
         "decode_ms": t_dec, "decode_GBps": dec_bytes / t_dec / 1e6, "decode_frac": dec_bytes / t_dec / 1e6 / PEAK,
         "nms_ms": t_nms, "rows_per_image": int(offs[-1]) / batch,
         "images_per_s_loss_decode_nms": batch / ((t_loss + t_dec + t_nms) * 1e-3),
-        "l2": "flushed between iterations (working set < L2)" if small else "inputs larger than L2",
+        "l2": "flushed between iterations (working set < L2), one call per timing" if small else "inputs larger than L2, 8 calls queued per timing",
     }
     print(name, json.dumps(out[name]))
 
@@ -102,8 +107,8 @@ def kmeans_bench(out, n=50_000_000, k=9):
     rng = np.random.default_rng(4)
     data = torch.from_numpy(synth.make_kmeans_boxes(rng, n, k)).cuda()
     centers = torch.from_numpy(np.sort(rng.uniform(0.02, 0.8, (k, 2)), axis=0)).cuda()
-    t, tmin = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU))
-    t2, _ = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU, want_assign=True))
+    t, tmin = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU), burst=8)
+    t2, _ = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU, want_assign=True), burst=8)
     out["kmeans_50M"] = {"boxes": n, "k": k, "ms_per_iteration": t, "GBps": 16 * n / t / 1e6,
                          "frac_of_measured_hbm": 16 * n / t / 1e6 / PEAK, "ms_with_assignments": t2}
     print("kmeans_50M", json.dumps(out["kmeans_50M"]))

@@ -50,6 +50,11 @@ __device__ __noinline__ int km_exact_slot(double a, int k, const double* carea, 
     return rank[best];
 }
 
+constexpr int kLutShift = 13;                 // high word >> 13: sign, exponent, 7 mantissa bits
+constexpr int kLutCells = 2048;               // 16 octaves x 128 cells: areas in [2^-15, 2)
+constexpr int kLutBase = (1023 - 15) << 7;    // cell index of 2^-15
+constexpr int kCntBits = 7;                   // packed per-lane counters: 9 slots x 7 bits
+
 // Shared memory: [ring: 8 warps x n_stages x tile_pts x D doubles][acc: K x 256 x D doubles][cnt: K x 256 ints]
 // Every WARP streams its own tiles through its own ring (lane 0 issues the bulk copies, the warp
 // waits on its own mbarriers): no block-wide barrier anywhere in the streaming loop.  Every thread
@@ -62,6 +67,8 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     double* ring = reinterpret_cast<double*>(smem);
     double* s_acc = ring + (size_t)kKmWarps * L.n_stages * L.tile_pts * D;    // [K][256][D]
     int* s_cnt = reinterpret_cast<int*>(s_acc + (size_t)K * D * kKmThreads);  // [K][256]
+    double* s_red = ring;                  // [8][K*(D+1)], after the streaming loop (ring is dead)
+    constexpr bool kBoxes = kIou && D == 2;   // the anchor case: (w,h) boxes, iou_dist
     __shared__ uint64_t full[kKmWarps][kKmMaxStages];
     __shared__ double s_center[K * D];
     __shared__ double s_carea[K];
@@ -69,8 +76,8 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     __shared__ int s_sidx[K];              // original index of the s-th smallest area
     __shared__ int s_rank[K];              // sorted slot of original index c
     __shared__ int s_thr_hi[K];            // high words of the k-1 decision thresholds (INT_MAX beyond)
-    __shared__ double2 s_edge[K];          // slot s is certain for lo < area < hi
-    __shared__ double s_red[kKmWarps * K * (D + 1)];
+    __shared__ int2 s_win[K];              // slot s is certain for win.x < hiword(area) < win.y
+    __shared__ unsigned char s_lut[kBoxes ? kLutCells : 16];  // cell of hiword(area) -> certain slot | 0xFF
     __shared__ int s_is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = L.k;  // <= K
@@ -90,18 +97,20 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     // iou_dist is a function of the AREA only and monotone in it on either side of the box's area
     // a, so the nearest centroid is one of the two sorted areas lo <= a < hi bracketing the box, and
     // lo/a > a/hi  <=>  a < sqrt(lo*hi).  The assignment is therefore a step function of a with
-    // k-1 thresholds g_j = sqrt(A_j * A_j+1) over the sorted areas A: the slot is a count of
-    // thresholds below a.  The count is taken on the HIGH WORDS of the doubles (integer compares);
-    // it can be off by one only when a is within 2^-20 of a threshold.  The shortcut is accepted
-    // only when it provably agrees with NumPy's first-minimum argmin over the ROUNDED distances
+    // k-1 thresholds g_j = sqrt(A_j * A_j+1) over the sorted areas A.  The shortcut is accepted only
+    // where it provably agrees with NumPy's first-minimum argmin over the ROUNDED distances
     // fl(1 - fl(min/max)):  slot s is certain for  g_{s-1}(1+d) < a < g_s(1-d)  with
     // d = 2e-15 + 1e-15 sqrt(A_j+1 / A_j): there the two candidate ratios differ by > 2e-15, more
     // than the roundings of the ratios and of 1 - r can hide (4.4e-16), so the rounded distances
-    // are ordered like the exact ones, strictly; the edges are also clamped so that the winning
+    // are ordered like the exact ones, strictly; the window is also clamped so that the winning
     // ratio is >= 2^-20, and neighbouring areas must differ by > 1e-6 relative, so every farther
-    // centroid's rounded distance is strictly larger still (no tie to break).  A miscounted slot
-    // always lands outside its own edges.  Anything else (duplicate / non-finite / extreme
-    // centroids, near ties, far-away boxes, NaN) takes the exact k-way loop with IEEE divisions.
+    // centroid's rounded distance is strictly larger still (no tie to break).
+    // Everything is decided on the HIGH WORD of the area (positive doubles order like their bit
+    // patterns): a table over cells of 2^-7 relative width maps a cell that lies entirely inside
+    // one slot's certainty window to that slot (one byte load per box); a cell that touches a
+    // threshold counts the thresholds below the high word and tests the slot's window; what is
+    // still uncertain (near ties, duplicate / non-finite / extreme centroids, far-away boxes, NaN)
+    // takes the exact k-way loop with IEEE divisions.
     if (tid == 0) {
         int bad = (D < 2) ? 1 : 0;
         for (int c = 0; c < k; ++c) {
@@ -134,7 +143,8 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
                     th = __double2hiint(g);
                 }
             }
-            s_edge[sl] = make_double2(lo, hi);
+            // hiword(a) > hiword(lo) => a > lo;  hiword(a) < hiword(hi) => a < hi
+            s_win[sl] = (lo < hi) ? make_int2(__double2hiint(lo), __double2hiint(hi)) : make_int2(INT_MAX, INT_MIN);
             s_thr_hi[sl] = th;
         }
     }
@@ -142,14 +152,120 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     int thr_hi[K > 1 ? K - 1 : 1];   // threshold high words in registers
 #pragma unroll
     for (int c = 0; c + 1 < K; ++c) thr_hi[c] = s_thr_hi[c];
+    auto count_slot = [&](int ah) {
+        int sl = 0;
+#pragma unroll
+        for (int c = 0; c + 1 < K; ++c) sl += (ah > thr_hi[c]) ? 1 : 0;
+        return sl;
+    };
+    if (kBoxes) {
+        for (int cell = tid; cell < kLutCells; cell += kKmThreads) {
+            const int lo_h = (kLutBase + cell) << kLutShift, hi_h = lo_h + ((1 << kLutShift) - 1);
+            const int s1 = count_slot(lo_h), s2 = count_slot(hi_h);
+            const int2 w = s_win[s1];
+            s_lut[cell] = (s1 == s2 && lo_h > w.x && hi_h < w.y) ? (unsigned char)s1 : (unsigned char)0xFF;
+        }
+        __syncthreads();
+    }
 
     const long long n_tiles = (L.n + tile_pts - 1) / tile_pts;
     const long long wg = (long long)blockIdx.x * kKmWarps + warp, n_wg = (long long)gridDim.x * kKmWarps;
     const long long n_my = (n_tiles > wg) ? (n_tiles - wg + n_wg - 1) / n_wg : 0;
+    double* my_acc = s_acc + tid * D;
+    int* my_cnt = s_cnt + tid;
+
+    // per-lane box counters: 7-bit fields of one 64-bit register (K <= 9), flushed to the shared
+    // counter plane before a field can overflow; larger K counts in shared memory directly
+    constexpr bool kPacked = kBoxes && K * kCntBits <= 64;
+    unsigned long long cnt_pack = 0ull;
+    int cnt_pending = 0;
+    auto flush_counts = [&]() {
+#pragma unroll
+        for (int c = 0; c < K; ++c) my_cnt[c * kKmThreads] += (int)((cnt_pack >> (kCntBits * c)) & ((1u << kCntBits) - 1u));
+        cnt_pack = 0ull;
+        cnt_pending = 0;
+    };
+
+    // one batch of kU boxes of a lane: loads, areas and slots of the whole batch are independent
+    // chains; only the accumulator updates are ordered
+    constexpr int kU = 4;
+    auto process_boxes = [&](const double2 (&bx)[kU], const bool (&have)[kU], long long first) {
+        int slot[kU];
+        double area[kU];
+        bool all_sure = true;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            area[u] = __dmul_rn(bx[u].x, bx[u].y);
+            const unsigned cell = (unsigned)((__double2hiint(area[u]) >> kLutShift) - kLutBase);
+            slot[u] = (cell < (unsigned)kLutCells) ? (int)s_lut[cell] : 0xFF;
+            all_sure = all_sure && (slot[u] != 0xFF || !have[u]);
+        }
+        if (!all_sure) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                if (have[u] && slot[u] == 0xFF) {
+                    const int ah = __double2hiint(area[u]);
+                    const int sl = count_slot(ah);
+                    const int2 w = s_win[sl];
+                    slot[u] = (ah > w.x && ah < w.y) ? sl : km_exact_slot(area[u], k, s_carea, s_rank);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            if (have[u]) {
+                if (kAssign) L.assign[first + u * 32] = s_sidx[slot[u]];
+                double2* acc = reinterpret_cast<double2*>(my_acc + slot[u] * (2 * kKmThreads));
+                double2 t2 = *acc;
+                t2.x += bx[u].x;
+                t2.y += bx[u].y;
+                *acc = t2;
+                if (kPacked) cnt_pack += 1ull << (kCntBits * slot[u]);
+                else my_cnt[slot[u] * kKmThreads] += 1;
+            }
+        }
+        if (kPacked) {
+            cnt_pending += kU;
+            if (cnt_pending > (1 << kCntBits) - 1 - kU) flush_counts();
+        }
+    };
+    // generic point (any D, euclidean or iou_dist): exact k-way loop
+    auto process_point = [&](const double* src, int i, long long p0) {
+        double v[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = src[(size_t)i * D + j];
+        int slot = 0;   // accumulator slot: SORTED position for iou_dist, cluster index otherwise
+        if (kIou) {
+            const double a = __dmul_rn(v[0], v[D > 1 ? 1 : 0]);
+            slot = km_exact_slot(a, k, s_carea, s_rank);
+            if (kAssign) L.assign[p0 + i] = s_sidx[slot];
+        } else {
+            double bd = 0.0;
+            for (int c = 0; c < k; ++c) {
+                double sq = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const double df = s_center[c * D + j] - v[j];
+                    sq = __dadd_rn(sq, __dmul_rn(df, df));
+                }
+                const double dist = sqrt(sq);
+                if (c == 0 || dist < bd) {
+                    bd = dist;
+                    slot = c;
+                }
+            }
+            if (kAssign) L.assign[p0 + i] = slot;
+        }
+        double* acc = my_acc + slot * (D * kKmThreads);
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc[j] += v[j];
+        my_cnt[slot * kKmThreads] += 1;
+    };
+
     double* my_ring = ring + (size_t)warp * n_stages * tile_pts * D;
     uint64_t* my_full = full[warp];
-    auto issue = [&](long long t, int stage) {   // lane 0 only
-        const long long p0 = (wg + t * n_wg) * tile_pts;
+    const long long tile_step = n_wg * tile_pts;
+    auto issue = [&](long long p0, int stage) {   // lane 0 only
         const int np = (int)min((long long)tile_pts, L.n - p0);
         const uint32_t bytes = (uint32_t)np * D * 8u;
         if (L.bulk_ok && (bytes & 15u) == 0u) {
@@ -159,99 +275,48 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
             mbar_arrive(&my_full[stage]);  // the warp reads global memory directly for this tile
         }
     };
+    long long p_issue = wg * tile_pts;   // first point of the next tile to issue
     if (lane == 0)
-        for (int t = 0; t < n_stages - 1 && t < n_my; ++t) issue(t, t);
-
-    double* my_acc = s_acc + tid * D;
-    int* my_cnt = s_cnt + tid;
+        for (int t = 0; t < n_stages - 1 && t < n_my; ++t, p_issue += tile_step) issue(p_issue, t);
     int stage = 0, issue_stage = n_stages - 1;
     uint32_t parity = 0;
-    for (long long it = 0; it < n_my; ++it) {
+    long long p0 = wg * tile_pts;
+    for (long long it = 0; it < n_my; ++it, p0 += tile_step) {
         // the stage refilled here held tile it-1: every lane left it before the __syncwarp below
-        if (lane == 0 && it + n_stages - 1 < n_my) issue(it + n_stages - 1, issue_stage);
+        if (lane == 0 && it + n_stages - 1 < n_my) {
+            issue(p_issue, issue_stage);
+            p_issue += tile_step;
+        }
         issue_stage = (issue_stage + 1 == n_stages) ? 0 : issue_stage + 1;
-        const long long p0 = (wg + it * n_wg) * tile_pts;
         const int np = (int)min((long long)tile_pts, L.n - p0);
         const bool staged = L.bulk_ok && ((((uint32_t)np * D * 8u) & 15u) == 0u);
         const double* src = staged ? my_ring + (size_t)stage * tile_pts * D : L.data + p0 * D;
         mbar_wait(&my_full[stage], parity);
-        if (kIou && D == 2) {
-            // batches of kU boxes per lane: loads, areas, slots and certainty tests of the whole
-            // batch are independent chains; only the accumulator updates are ordered
-            constexpr int kU = 4;
-            for (int base = 0; base < np; base += 32 * kU) {
-                double2 bx[kU];
-                int slot[kU];
-                bool have[kU], sure[kU];
-                double area[kU];
+        if (kBoxes) {
+            if (np == tile_pts) {   // full tile: no bounds tests
+                const bool have[kU] = {true, true, true, true};
+                for (int base = 0; base < tile_pts; base += 32 * kU) {
+                    double2 bx[kU];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const int i = base + u * 32 + lane;
-                    have[u] = i < np;
-                    bx[u] = have[u] ? *reinterpret_cast<const double2*>(src + (size_t)i * 2) : make_double2(0.0, 0.0);
+                    for (int u = 0; u < kU; ++u)
+                        bx[u] = *reinterpret_cast<const double2*>(src + (size_t)(base + u * 32 + lane) * 2);
+                    process_boxes(bx, have, p0 + base + lane);
                 }
+            } else {
+                for (int base = 0; base < np; base += 32 * kU) {
+                    double2 bx[kU];
+                    bool have[kU];
 #pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    area[u] = __dmul_rn(bx[u].x, bx[u].y);
-                    const int ah = __double2hiint(area[u]);
-                    int sl = 0;
-#pragma unroll
-                    for (int c = 0; c + 1 < K; ++c) sl += (ah > thr_hi[c]) ? 1 : 0;
-                    slot[u] = sl;
-                }
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    const double2 e = s_edge[slot[u]];
-                    sure[u] = area[u] > e.x && area[u] < e.y;
-                }
-#pragma unroll
-                for (int u = 0; u < kU; ++u)
-                    if (have[u] && !sure[u]) slot[u] = km_exact_slot(area[u], k, s_carea, s_rank);
-#pragma unroll
-                for (int u = 0; u < kU; ++u) {
-                    if (have[u]) {
-                        if (kAssign) L.assign[p0 + base + u * 32 + lane] = s_sidx[slot[u]];
-                        double2* acc = reinterpret_cast<double2*>(my_acc + slot[u] * (2 * kKmThreads));
-                        double2 t2 = *acc;
-                        t2.x += bx[u].x;
-                        t2.y += bx[u].y;
-                        *acc = t2;
-                        my_cnt[slot[u] * kKmThreads] += 1;
+                    for (int u = 0; u < kU; ++u) {
+                        const int i = base + u * 32 + lane;
+                        have[u] = i < np;
+                        bx[u] = have[u] ? *reinterpret_cast<const double2*>(src + (size_t)i * 2) : make_double2(0.0, 0.0);
                     }
+                    process_boxes(bx, have, p0 + base + lane);
                 }
             }
         } else {
-        for (int i = lane; i < np; i += 32) {
-            double v[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) v[j] = src[(size_t)i * D + j];
-            int slot = 0;   // accumulator slot: SORTED position for iou_dist, cluster index otherwise
-            if (kIou) {
-                const double a = __dmul_rn(v[0], v[D > 1 ? 1 : 0]);
-                slot = km_exact_slot(a, k, s_carea, s_rank);
-                if (kAssign) L.assign[p0 + i] = s_sidx[slot];
-            } else {
-                double bd = 0.0;
-                for (int c = 0; c < k; ++c) {
-                    double sq = 0.0;
-#pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        const double df = s_center[c * D + j] - v[j];
-                        sq = __dadd_rn(sq, __dmul_rn(df, df));
-                    }
-                    const double dist = sqrt(sq);
-                    if (c == 0 || dist < bd) {
-                        bd = dist;
-                        slot = c;
-                    }
-                }
-                if (kAssign) L.assign[p0 + i] = slot;
-            }
-            double* acc = my_acc + slot * (D * kKmThreads);
-#pragma unroll
-            for (int j = 0; j < D; ++j) acc[j] += v[j];
-            my_cnt[slot * kKmThreads] += 1;
-        }
+            for (int i = lane; i < np; i += 32) process_point(src, i, p0);
         }
         __syncwarp();  // stage free for the next bulk load
         if (++stage == n_stages) {
@@ -259,11 +324,13 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
             parity ^= 1u;
         }
     }
+    if (kPacked) flush_counts();
+    __syncthreads();   // every warp has left its ring: s_red may reuse it
 
     // ---- reduction: thread columns -> warp -> CTA -> global partials -> last CTA ----
     constexpr int NV = K * (D + 1);
-    for (int c = 0; c < K; ++c) {   // c = cluster index; its accumulator slot is its sorted rank (iou_dist)
-        const int sl = (kIou && c < k) ? s_rank[c] : c;
+    for (int c = 0; c < K; ++c) {   // c = cluster index; its accumulator slot is its sorted rank (boxes)
+        const int sl = (kBoxes && c < k) ? s_rank[c] : c;
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             const double sres = warp_sum(my_acc[sl * (D * kKmThreads) + j]);

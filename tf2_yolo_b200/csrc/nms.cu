@@ -29,6 +29,7 @@ constexpr int kBigThreads = 256;
 constexpr int kBigCap = 1536;      // boxes per segment held in shared memory
 constexpr int kBigP = 2048;        // power-of-two padding of the index arrays of such a segment
 constexpr int kSweep = 64;         // sweep block (one 64-bit mask word per box)
+constexpr int kTiny = 8;           // segments up to this size share a warp (one 8-lane group each)
 
 // np.maximum / np.minimum: NaN propagates (fmax/fmin would drop it)
 __device__ __forceinline__ double np_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
@@ -163,12 +164,12 @@ struct NmsWs {
     unsigned int* seg_count; // [n_seg + 1]
     unsigned int* seg_fill;  // [n_seg]
     unsigned int* seg_kept;  // [n_seg + 1]
-    unsigned int* ctrl;      // [8]: small_n, big_n, small_cursor, big_cursor
+    unsigned int* ctrl;      // [8]: n_small (9..32 boxes), n_big, n_tiny (<= 8 boxes)
     long long* seg_start;    // [n_seg + 2]
     long long* out_start;    // [n_seg + 2]
     int* members;            // [R]
     int* local_rank;         // [R]
-    int* small_list;         // [n_seg]
+    int* small_list;         // [n_seg]: tiny segments from the front, one-warp segments from the back
     int* big_list;           // [n_seg]
     double* gbox;            // [7][R]: planes X(2) Y(2) C(2) A(1) of segments > kBigCap
     int* gmem_pad;           // [2R] padded handle array
@@ -223,8 +224,10 @@ __global__ void nms_scatter_kernel(const long long* __restrict__ row_offsets, lo
         const unsigned c = W.seg_count[s];
         if (c == 0u) {
             W.seg_kept[s] = 0u;
-        } else if (c <= 32u) {
-            W.small_list[atomicAdd(&W.ctrl[0], 1u)] = (int)s;
+        } else if (c <= (unsigned)kTiny) {   // tiny segments fill the list from the front ...
+            W.small_list[atomicAdd(&W.ctrl[2], 1u)] = (int)s;
+        } else if (c <= 32u) {               // ... one-warp segments from the back
+            W.small_list[n_seg - 1 - (long long)atomicAdd(&W.ctrl[0], 1u)] = (int)s;
         } else {
             W.big_list[atomicAdd(&W.ctrl[1], 1u)] = (int)s;
         }
@@ -232,103 +235,136 @@ __global__ void nms_scatter_kernel(const long long* __restrict__ row_offsets, lo
 }
 
 // ---- small segments: one warp each ---------------------------------------------
+template <int GW>
 __device__ __forceinline__ BoxC shfl_box(const BoxC& b, int src, bool with_centre) {
     BoxC r;
-    r.x0 = __shfl_sync(0xffffffffu, b.x0, src); r.x1 = __shfl_sync(0xffffffffu, b.x1, src);
-    r.y0 = __shfl_sync(0xffffffffu, b.y0, src); r.y1 = __shfl_sync(0xffffffffu, b.y1, src);
-    r.area = __shfl_sync(0xffffffffu, b.area, src);
-    r.cx = with_centre ? __shfl_sync(0xffffffffu, b.cx, src) : 0.0;
-    r.cy = with_centre ? __shfl_sync(0xffffffffu, b.cy, src) : 0.0;
+    r.x0 = __shfl_sync(0xffffffffu, b.x0, src, GW); r.x1 = __shfl_sync(0xffffffffu, b.x1, src, GW);
+    r.y0 = __shfl_sync(0xffffffffu, b.y0, src, GW); r.y1 = __shfl_sync(0xffffffffu, b.y1, src, GW);
+    r.area = __shfl_sync(0xffffffffu, b.area, src, GW);
+    r.cx = with_centre ? __shfl_sync(0xffffffffu, b.cx, src, GW) : 0.0;
+    r.cy = with_centre ? __shfl_sync(0xffffffffu, b.cy, src, GW) : 0.0;
     return r;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(256)
-nms_small_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W,
-                 unsigned char* __restrict__ keep) {
+// One segment per GROUP of GW lanes (GW = 32: one per warp; GW = 8: four tiny segments share a
+// warp).  seg < 0 = idle group.  Every lane of the warp runs every shuffle (loops go to the
+// largest segment of the warp), so the full-mask shuffles stay converged.
+template <int MODE, int GW>
+__device__ __forceinline__ void nms_group_segment(const double* __restrict__ rows, double thr, double conf_thr,
+                                                  double sigma, const NmsWs& W, int seg, bool pos_thr,
+                                                  unsigned char* __restrict__ keep) {
+    constexpr unsigned GM = (GW == 32) ? 0xffffffffu : ((1u << GW) - 1u);
     const int lane = threadIdx.x & 31;
-    const bool pos_thr = thr > 0.0;
-    // static round-robin over the work list (segments are at most 32 boxes: balanced enough, and a
-    // work-stealing atomic per segment costs more than the segment)
-    const unsigned n_work = W.ctrl[0];
-    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work; w += n_warps) {
-        const int seg = W.small_list[w];
-        const int n = (int)W.seg_count[seg];
-        const long long start = W.seg_start[seg];
-        const unsigned valid = (n == 32) ? 0xffffffffu : ((1u << n) - 1u);
+    const int gl = lane & (GW - 1);        // lane inside the group
+    const int gshift = lane & ~(GW - 1);   // first lane of the group
+    const int n = (seg >= 0) ? (int)W.seg_count[seg] : 0;
+    const long long start = (seg >= 0) ? W.seg_start[seg] : 0;
+    int nmax = n;
+    if (GW < 32) {
+#pragma unroll
+        for (int o = GW; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    }
+    const unsigned valid = (n >= 32) ? 0xffffffffu : ((1u << n) - 1u);
 
-        // restore original order: rank the (atomically scattered) row ids, permute by shuffle
-        int m = (lane < n) ? W.members[start + lane] : INT_MAX;
-        {
-            int rk = 0;
-            for (int j = 0; j < n; ++j) rk += (__shfl_sync(0xffffffffu, m, j) < m) ? 1 : 0;
-            int src = lane;
-            for (int j = 0; j < n; ++j)
-                if (__shfl_sync(0xffffffffu, rk, j) == lane) src = j;
-            m = __shfl_sync(0xffffffffu, m, src);
-            if (lane < n) W.members[start + lane] = m;
+    // restore original order: rank the (atomically scattered) row ids, permute by shuffle
+    int m = (gl < n) ? W.members[start + gl] : INT_MAX;
+    {
+        int rk = 0;
+        for (int j = 0; j < nmax; ++j) {
+            const int mj = __shfl_sync(0xffffffffu, m, j, GW);   // every lane shuffles, whatever its n
+            rk += (j < n && mj < m) ? 1 : 0;
         }
+        int src = gl;
+        for (int j = 0; j < nmax; ++j) {
+            const int rj = __shfl_sync(0xffffffffu, rk, j, GW);
+            if (rj == gl && j < n) src = j;
+        }
+        m = __shfl_sync(0xffffffffu, m, src, GW);
+        if (gl < n) W.members[start + gl] = m;
+    }
 
-        double x = 0, y = 0, bw = 0, bh = 0, conf = 0;
-        if (lane < n) {
-            const double* r = rows + (long long)m * 7;
-            x = r[0]; y = r[1]; bw = r[2]; bh = r[3];
-            conf = __dmul_rn(r[4], r[6]);
+    double x = 0, y = 0, bw = 0, bh = 0, conf = 0;
+    if (gl < n) {
+        const double* r = rows + (long long)m * 7;
+        x = r[0]; y = r[1]; bw = r[2]; bh = r[3];
+        conf = __dmul_rn(r[4], r[6]);
+    }
+    const BoxC mine = make_box(x, y, bw, bh);
+    // visit rank: descending confidence, ties -> higher original index first
+    int vis = 0;
+    unsigned sup = 0;
+    for (int j = 0; j < nmax; ++j) {
+        const double cj = __shfl_sync(0xffffffffu, conf, j, GW);
+        vis += (j < n && (cj > conf || (cj == conf && j > gl))) ? 1 : 0;
+        if (MODE != 3) {
+            const BoxC other = shfl_box<GW>(mine, j, MODE == 2);
+            const int mj = __shfl_sync(0xffffffffu, m, j, GW);
+            if (gl < n && j < n && suppresses<(MODE == 3 ? 1 : MODE)>(mine, other, thr, pos_thr, rows, m, mj))
+                sup |= 1u << j;
         }
-        const BoxC mine = make_box(x, y, bw, bh);
-        // visit rank: descending confidence, ties -> higher original index first
-        int vis = 0;
-        unsigned sup = 0;
-        for (int j = 0; j < n; ++j) {
-            const double cj = __shfl_sync(0xffffffffu, conf, j);
-            vis += (cj > conf || (cj == conf && j > lane)) ? 1 : 0;
-            if (MODE != 3) {
-                const BoxC other = shfl_box(mine, j, MODE == 2);
-                const int mj = __shfl_sync(0xffffffffu, m, j);
-                if (lane < n && suppresses<(MODE == 3 ? 1 : MODE)>(mine, other, thr, pos_thr, rows, m, mj)) sup |= 1u << j;
-            }
-        }
-        unsigned dead = 0, seen = 0;
-        if (MODE == 3) {
-            // soft-NMS (utils/tools.py:736-786): the visit order is fixed up front and deleted boxes keep
-            // decaying others, so box j's final confidence is its own product over the boxes visited
-            // before it, taken in visit order - independent of every other box.
-            bool decayed = false;
-            for (int v = 0; v < n; ++v) {
-                const unsigned who = __ballot_sync(0xffffffffu, lane < n && vis == v);
-                if (who == 0u) continue;
-                const int src = __ffs(who) - 1;
-                const double xs = __shfl_sync(0xffffffffu, x, src), ys = __shfl_sync(0xffffffffu, y, src);
-                const double ws = __shfl_sync(0xffffffffu, bw, src), hs = __shfl_sync(0xffffffffu, bh, src);
-                if (lane < n && vis > v) {
-                    const double iou = pair_iou<1>(xs, ys, ws, hs, x, y, bw, bh);
-                    if (iou >= thr) {
-                        conf = conf * exp(-1.0 * (iou * iou) / sigma);
-                        decayed = true;
-                    }
+    }
+    unsigned dead = 0, seen = 0;
+    if (MODE == 3) {
+        // soft-NMS (utils/tools.py:736-786): the visit order is fixed up front and deleted boxes keep
+        // decaying others, so box j's final confidence is its own product over the boxes visited
+        // before it, taken in visit order - independent of every other box.
+        bool decayed = false;
+        for (int v = 0; v < nmax; ++v) {
+            const unsigned who = (__ballot_sync(0xffffffffu, gl < n && vis == v) >> gshift) & GM;
+            const int src = who ? (__ffs(who) - 1) : 0;
+            const double xs = __shfl_sync(0xffffffffu, x, src, GW), ys = __shfl_sync(0xffffffffu, y, src, GW);
+            const double ws = __shfl_sync(0xffffffffu, bw, src, GW), hs = __shfl_sync(0xffffffffu, bh, src, GW);
+            if (who != 0u && gl < n && vis > v) {
+                const double iou = pair_iou<1>(xs, ys, ws, hs, x, y, bw, bh);
+                if (iou >= thr) {
+                    conf = conf * exp(-1.0 * (iou * iou) / sigma);
+                    decayed = true;
                 }
             }
-            dead = __ballot_sync(0xffffffffu, lane < n && decayed && conf < conf_thr);
-        } else {
-            // greedy sweep, state replicated in every lane
-            for (int v = 0; v < n; ++v) {
-                const unsigned who = __ballot_sync(0xffffffffu, lane < n && vis == v);
-                if (who == 0u) continue;  // only with NaN confidences
-                const int src = __ffs(who) - 1;
-                const unsigned s = __shfl_sync(0xffffffffu, sup, src);
+        }
+        dead = (__ballot_sync(0xffffffffu, gl < n && decayed && conf < conf_thr) >> gshift) & GM;
+    } else {
+        // greedy sweep, state replicated in every lane of the group
+        for (int v = 0; v < nmax; ++v) {
+            const unsigned who = (__ballot_sync(0xffffffffu, gl < n && vis == v) >> gshift) & GM;
+            const int src = who ? (__ffs(who) - 1) : 0;
+            const unsigned sv = __shfl_sync(0xffffffffu, sup, src, GW);
+            if (who != 0u) {   // who == 0 only with NaN confidences
                 seen |= 1u << src;
-                if (!((dead >> src) & 1u)) dead |= s & ~seen & valid;
+                if (!((dead >> src) & 1u)) dead |= sv & ~seen & valid;
             }
         }
-        const unsigned alive = valid & ~dead;
-        if (lane < n) {
-            const bool k = (alive >> lane) & 1u;
-            keep[m] = k ? 1 : 0;
-            W.local_rank[start + lane] = k ? __popc(alive & ((1u << lane) - 1u)) : -1;
-        }
-        if (lane == 0) W.seg_kept[seg] = (unsigned)__popc(alive);
     }
+    const unsigned alive = valid & ~dead;
+    if (gl < n) {
+        const bool kf = (alive >> gl) & 1u;
+        keep[m] = kf ? 1 : 0;
+        W.local_rank[start + gl] = kf ? __popc(alive & ((1u << gl) - 1u)) : -1;
+    }
+    if (gl == 0 && seg >= 0) W.seg_kept[seg] = (unsigned)__popc(alive);
+}
+
+// Work of one CTA on the warp-sized lists: tiny segments four to a warp, then 9..32-box segments
+// one per warp; static round-robin over `n_workers` CTAs (a work-stealing atomic per segment
+// costs more than the segment).
+template <int MODE>
+__device__ __forceinline__ void nms_small_work(const double* __restrict__ rows, double thr, double conf_thr, double sigma,
+                                               const NmsWs& W, long long n_seg, unsigned worker, unsigned n_workers,
+                                               unsigned char* __restrict__ keep) {
+    const int lane = threadIdx.x & 31;
+    const bool pos_thr = thr > 0.0;
+    const unsigned wpb = blockDim.x >> 5;
+    const unsigned warp_id = worker * wpb + (threadIdx.x >> 5), n_warps = n_workers * wpb;
+    constexpr int kPerWarp = 32 / kTiny;
+    const unsigned n_tiny = W.ctrl[2];
+    for (unsigned w = warp_id; w * kPerWarp < n_tiny; w += n_warps) {
+        const unsigned e = w * kPerWarp + (lane / kTiny);
+        const int seg = (e < n_tiny) ? W.small_list[e] : -1;
+        nms_group_segment<MODE, kTiny>(rows, thr, conf_thr, sigma, W, seg, pos_thr, keep);
+    }
+    const unsigned n_small = W.ctrl[0];
+    for (unsigned w = warp_id; w < n_small; w += n_warps)
+        nms_group_segment<MODE, 32>(rows, thr, conf_thr, sigma, W, W.small_list[n_seg - 1 - (long long)w], pos_thr, keep);
 }
 
 // ---- big segments: one CTA each ---------------------------------------------------
@@ -549,10 +585,12 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
     if (tid == 0) W.seg_kept[seg] = (unsigned)carry;
 }
 
+// All suppression work of one yb_nms call in ONE launch: the first CTAs take the big segments
+// (longest jobs first, one CTA each), every other CTA works through the warp-sized lists.
 template <int MODE>
 __global__ void __launch_bounds__(kBigThreads, 2)
-nms_big_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W, long long R,
-               unsigned char* __restrict__ keep) {
+nms_sweep_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W, long long R,
+                 long long n_seg, unsigned big_blocks, unsigned char* __restrict__ keep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* s_X = reinterpret_cast<double2*>(smem_raw);                  // [kBigCap] each
     double2* s_Y = s_X + kBigCap;
@@ -563,8 +601,13 @@ nms_big_kernel(const double* __restrict__ rows, double thr, double conf_thr, dou
     unsigned char* s_rem = reinterpret_cast<unsigned char*>(s_ord + kBigP);  // [kBigCap]
     __shared__ BigShared S;
 
-    const unsigned n_work = W.ctrl[1];
-    for (unsigned wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    const unsigned n_big = W.ctrl[1];
+    const unsigned big_used = min(n_big, big_blocks);   // CTAs that have a big segment to start with
+    if (blockIdx.x >= big_used) {
+        nms_small_work<MODE>(rows, thr, conf_thr, sigma, W, n_seg, blockIdx.x - big_used, gridDim.x - big_used, keep);
+        return;
+    }
+    for (unsigned wi = blockIdx.x; wi < n_big; wi += big_used) {
         __syncthreads();
         const int seg = W.big_list[wi];
         const int n = (int)W.seg_count[seg];
@@ -720,16 +763,17 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
     nms_scatter_kernel<<<sc_blocks, threads, 0, stream>>>(row_offsets, n_img, n_rows, n_seg, W);
     YB_CUDA_TRY(cudaGetLastError());
 
-    const int small_blocks = (int)min((long long)kNumSMs * 4, (n_seg * 32 + threads - 1) / threads);
+    // one launch: up to 2 CTAs/SM worth of big-segment CTAs first, then the warp-list workers
     const size_t big_smem = sizeof(double) * 7 * kBigCap + sizeof(int) * 2 * kBigP + kBigCap;
-    const int big_blocks = (int)min((long long)kNumSMs * 2, n_seg);
+    const unsigned big_blocks = (unsigned)min((long long)kNumSMs * 2, n_seg);
+    const long long warp_jobs = (min((long long)n_rows, n_seg) + 7) / 8;   // <= one job per 8 segments... per warp
+    const unsigned small_blocks = (unsigned)max(1LL, min((long long)kNumSMs * 4, (warp_jobs + 7) / 8));
 #define YB_NMS_LAUNCH(M)                                                                                       \
     do {                                                                                                       \
-        nms_small_kernel<M><<<small_blocks, threads, 0, stream>>>(rows, nms_threshold, conf_thr, sigma, W, keep); \
-        YB_CUDA_TRY(cudaFuncSetAttribute(nms_big_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+        YB_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                          (int)big_smem));                                                      \
-        nms_big_kernel<M><<<big_blocks, kBigThreads, big_smem, stream>>>(rows, nms_threshold, conf_thr, sigma, W, \
-                                                                        n_rows, keep);                         \
+        nms_sweep_kernel<M><<<big_blocks + small_blocks, kBigThreads, big_smem, stream>>>(                     \
+            rows, nms_threshold, conf_thr, sigma, W, n_rows, n_seg, big_blocks, keep);                         \
     } while (0)
     if (iou_mode == 1) YB_NMS_LAUNCH(1);
     else if (iou_mode == 2) YB_NMS_LAUNCH(2);

@@ -80,7 +80,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -88,33 +88,44 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def wait_first_sample(self, keep_busy, timeout=5.0):
+        """Run `keep_busy()` (untimed work) until nvidia-smi has delivered its first line."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            keep_busy()
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples that arrived inside [t_begin, t_end] (host clock), i.e. under load."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], None, set()
+        sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [ln for t, ln in self.lines if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end)]
+        if not lines:   # region shorter than one sampling period: the nearest sample
+            lines = [ln for _, ln in self.lines[-1:]]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1]))
                 smax = float(f[2])
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": float(np.median(power)) if power else None}
 
 
 # ---------------------------------------------------------------------------
@@ -268,16 +279,21 @@ def run_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        # untimed local work (no collective) until nvidia-smi delivers its first line
+        clocks.wait_first_sample(lambda: (fused_losses(fns, dev_t, dev_p, global_batch=global_batch, dpreds=dpreds),
+                                          torch.cuda.synchronize()))
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         out = step(dev_t, dev_p, record=True)
     ev1.record()
     barrier()
+    t_end = time.perf_counter()
     ms = ev0.elapsed_time(ev1) / args.steps
     loss_ms = float(np.mean([a.elapsed_time(b) for a, b in loss_ev]))
-    clock_info = clocks.stop() if rank == 0 else None
+    clock_info = clocks.stop(t_begin, t_end) if rank == 0 else None   # samples inside the timed region
     loss_vals = out[0].cpu().numpy().tolist()
 
     # ---- end to end through the host-buffer API -----------------------------------
@@ -362,8 +378,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -25,7 +25,8 @@
 namespace yb {
 
 constexpr double kIouEps = 1e-07;  // utils/tools.py:26
-constexpr int kBigThreads = 256;
+constexpr int kBigThreads = 512;   // 2 CTAs/SM: 32 warps hide the fp64 latency of the sweeps
+constexpr int kMaskParts = kBigThreads / 64;   // threads per row of the 64x64 block mask
 constexpr int kBigCap = 1536;      // boxes per segment held in shared memory
 constexpr int kBigP = 2048;        // power-of-two padding of the index arrays of such a segment
 constexpr int kSweep = 64;         // sweep block (one 64-bit mask word per box)
@@ -409,7 +410,7 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
                                             double2* X, double2* Y, double2* C, double* A, unsigned char* rem,
                                             BigShared& S, unsigned char* __restrict__ keep) {
     constexpr int M = (MODE == 3) ? 1 : MODE;
-    constexpr int kJpt = (M == 2) ? 2 : 3;   // boxes a thread carries at once through the kept list
+    constexpr int kJpt = (M == 2) ? 1 : 2;   // boxes a thread carries at once through the kept list
     const int tid = threadIdx.x;
     const bool pos_thr = thr > 0.0;
     double* cf = A;
@@ -484,12 +485,13 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
         const int m = min(kSweep, n - blk);
         if (tid < kSweep) S.mask[tid] = 0ull;
         __syncthreads();
-        {   // 64x64 upper-triangular mask, 4 threads per row (16 columns each)
-            const int i = tid >> 2, part = tid & 3;
+        {   // 64x64 upper-triangular mask, kMaskParts threads per row
+            constexpr int kCols = 64 / kMaskParts;
+            const int i = tid / kMaskParts, part = tid % kMaskParts;
             if (i < m && !rem[blk + i]) {
                 const BoxC bi = load_box(blk + i);
                 unsigned long long bits = 0ull;
-                const int j0 = max(part * 16, i + 1), j1 = min(part * 16 + 16, m);
+                const int j0 = max(part * kCols, i + 1), j1 = min(part * kCols + kCols, m);
                 for (int j = j0; j < j1; ++j) {
                     const BoxC bj = load_box(blk + j);
                     int r = suppresses_fast<M>(bi, bj, thr, pos_thr);

@@ -190,7 +190,7 @@ def run_reference(args):
     value = per_step * args.steps / dt
     sample = (f"{per_step} images/step of the v4-608 workload, oracle port of the reference path "
               f"(torch-CPU fp32 loss fwd+bwd on {cores} threads; NumPy decode + DIoU-NMS); TensorFlow not installable")
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -370,12 +370,38 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+class _StdoutGuard:
+    """Keep fd 1 clean for the ONE JSON line: native libraries (NCCL prints its version banner on
+    stdout) write to stderr while the benchmark runs; emit() writes the line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
+GUARD = None
+
+
+def emit(line):
+    if GUARD is not None:
+        GUARD.emit(line)
+    else:
+        print(line)
+
+
 def main():
+    global GUARD
+    GUARD = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -37,8 +37,8 @@ CONFIG_NAME = "v4-608"
 CONF_THR, NMS_THR, NMS_MODE = 0.5, 0.45, 2
 ROW_CAPACITY_PER_IMG = 4096
 # my kernels per step: fused loss + decode count 1 | decode: look-back scan, emit | nms: classify,
-# segment scan, scatter, sweep, survivor scan, emit   (--unfused: one more, the separate decode count)
-LAUNCHES_PER_STEP = 1 + 2 + 6
+# scatter, sweep, emit   (--unfused: one more, the separate decode count)
+LAUNCHES_PER_STEP = 1 + 2 + 4
 
 
 def loss_algorithmic_bytes(cfg, batch):

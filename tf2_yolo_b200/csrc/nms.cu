@@ -5,8 +5,8 @@
 // Pipeline (all on the caller's stream, no host round trip; the true row count is
 // read on the device from row_offsets[n_img]):
 //   classify  : row -> segment (image, class); per-segment counts (atomics)
-//   scan      : segment start offsets
-//   scatter   : row ids grouped by segment; segments binned into work lists
+//   scatter   : per image: scan of its C segment counts (start offsets), row ids grouped by
+//               segment, segments binned into work lists
 //   small     : segments of <= 32 boxes, one WARP each: rank by confidence with
 //               shuffles, 32-bit suppression masks from warp-broadcast boxes,
 //               mask sweep in registers
@@ -14,7 +14,8 @@
 //               boxes staged in shared memory in visit order, blocked greedy sweep
 //               (64x64 IoU bitmask per block, serial resolve of the block, kept
 //               boxes of the block suppress the rest of the segment in parallel)
-//   scan+emit : survivors written in the reference's order (class-major, original
+//   emit      : per image: prefix of the survivor counts of earlier images + scan of its own C
+//               segments, survivors written in the reference's order (class-major, original
 //               order inside a class)
 #include <climits>
 #include <cstring>
@@ -165,18 +166,18 @@ struct NmsWs {
     unsigned int* seg_count; // [n_seg + 1]
     unsigned int* seg_fill;  // [n_seg]
     unsigned int* seg_kept;  // [n_seg + 1]
+    unsigned int* img_kept;  // [n_img + 1] survivors per image (atomics from the sweeps)
     unsigned int* ctrl;      // [8]: n_small (9..32 boxes), n_big, n_tiny (<= 8 boxes)
     long long* seg_start;    // [n_seg + 2]
     long long* out_start;    // [n_seg + 2]
     int* members;            // [R]
-    int* local_rank;         // [R]
+    int* local_rank;         // [R] by ROW id: rank among its segment's survivors, -1 = removed
     int* small_list;         // [n_seg]: tiny segments from the front, one-warp segments from the back
     int* big_list;           // [n_seg]
     double* gbox;            // [7][R]: planes X(2) Y(2) C(2) A(1) of segments > kBigCap
     int* gmem_pad;           // [2R] padded handle array
     int* gord_pad;           // [2R]
     unsigned char* gremoved; // [R]
-    void* scan_ws;
 };
 
 __device__ __forceinline__ long long device_row_count(const long long* row_offsets, long long n_img,
@@ -209,28 +210,46 @@ __global__ void nms_classify_kernel(const double* __restrict__ rows, const long 
     }
 }
 
-__global__ void nms_scatter_kernel(const long long* __restrict__ row_offsets, long long n_img, long long cap,
-                                   long long n_seg, NmsWs W) {
+// grid (n_img, Y): every CTA of image i scans the image's C segment counts (start offsets are
+// row_offsets[i] + exclusive scan: no device-wide scan, rows of an image stay inside its row range),
+// then scatters its share of the image's rows; the y == 0 CTA also bins the segments.
+__global__ void __launch_bounds__(256)
+nms_scatter_kernel(const long long* __restrict__ row_offsets, long long n_img, long long cap, int C, NmsWs W) {
+    __shared__ long long s_warp[32];
     const long long n = device_row_count(row_offsets, n_img, cap);
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nth = (long long)gridDim.x * blockDim.x;
-    for (long long i = tid; i < n; i += nth) {
-        const int seg = W.row_seg[i];
+    const long long img = blockIdx.x;
+    const long long r0 = min(row_offsets[img], n), r1 = min(row_offsets[img + 1], n);
+    const long long seg0 = img * C;
+    const int tid = threadIdx.x;
+    long long carry = 0;
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + tid;
+        const unsigned cnt = (c < C) ? W.seg_count[seg0 + c] : 0u;
+        long long total;
+        const long long ex = block_exclusive_scan((long long)cnt, s_warp, total);
+        if (c < C) {
+            W.seg_start[seg0 + c] = r0 + carry + ex;   // same value from every CTA of the image
+            if (blockIdx.y == 0) {
+                const long long sg = seg0 + c;
+                if (cnt == 0u) {
+                    W.seg_kept[sg] = 0u;
+                } else if (cnt <= (unsigned)kTiny) {   // tiny segments fill the list from the front ...
+                    W.small_list[atomicAdd(&W.ctrl[2], 1u)] = (int)sg;
+                } else if (cnt <= 32u) {               // ... one-warp segments from the back
+                    W.small_list[n_img * C - 1 - (long long)atomicAdd(&W.ctrl[0], 1u)] = (int)sg;
+                } else {
+                    W.big_list[atomicAdd(&W.ctrl[1], 1u)] = (int)sg;
+                }
+            }
+        }
+        carry += total;
+    }
+    __syncthreads();   // this CTA's seg_start writes are visible to its own threads
+    for (long long row = r0 + (long long)blockIdx.y * blockDim.x + tid; row < r1; row += (long long)gridDim.y * blockDim.x) {
+        const int seg = W.row_seg[row];
         if (seg >= 0) {
             const long long pos = W.seg_start[seg] + atomicAdd(&W.seg_fill[seg], 1u);
-            W.members[pos] = (int)i;
-        }
-    }
-    for (long long s = tid; s < n_seg; s += nth) {
-        const unsigned c = W.seg_count[s];
-        if (c == 0u) {
-            W.seg_kept[s] = 0u;
-        } else if (c <= (unsigned)kTiny) {   // tiny segments fill the list from the front ...
-            W.small_list[atomicAdd(&W.ctrl[2], 1u)] = (int)s;
-        } else if (c <= 32u) {               // ... one-warp segments from the back
-            W.small_list[n_seg - 1 - (long long)atomicAdd(&W.ctrl[0], 1u)] = (int)s;
-        } else {
-            W.big_list[atomicAdd(&W.ctrl[1], 1u)] = (int)s;
+            W.members[pos] = (int)row;
         }
     }
 }
@@ -252,7 +271,7 @@ __device__ __forceinline__ BoxC shfl_box(const BoxC& b, int src, bool with_centr
 // largest segment of the warp), so the full-mask shuffles stay converged.
 template <int MODE, int GW>
 __device__ __forceinline__ void nms_group_segment(const double* __restrict__ rows, double thr, double conf_thr,
-                                                  double sigma, const NmsWs& W, int seg, bool pos_thr,
+                                                  double sigma, const NmsWs& W, int seg, bool pos_thr, int C,
                                                   unsigned char* __restrict__ keep) {
     constexpr unsigned GM = (GW == 32) ? 0xffffffffu : ((1u << GW) - 1u);
     const int lane = threadIdx.x & 31;
@@ -340,9 +359,12 @@ __device__ __forceinline__ void nms_group_segment(const double* __restrict__ row
     if (gl < n) {
         const bool kf = (alive >> gl) & 1u;
         keep[m] = kf ? 1 : 0;
-        W.local_rank[start + gl] = kf ? __popc(alive & ((1u << gl) - 1u)) : -1;
+        W.local_rank[m] = kf ? __popc(alive & ((1u << gl) - 1u)) : -1;
     }
-    if (gl == 0 && seg >= 0) W.seg_kept[seg] = (unsigned)__popc(alive);
+    if (gl == 0 && seg >= 0) {
+        W.seg_kept[seg] = (unsigned)__popc(alive);
+        atomicAdd(&W.img_kept[seg / C], (unsigned)__popc(alive));
+    }
 }
 
 // Work of one CTA on the warp-sized lists: tiny segments four to a warp, then 9..32-box segments
@@ -350,7 +372,7 @@ __device__ __forceinline__ void nms_group_segment(const double* __restrict__ row
 // costs more than the segment).
 template <int MODE>
 __device__ __forceinline__ void nms_small_work(const double* __restrict__ rows, double thr, double conf_thr, double sigma,
-                                               const NmsWs& W, long long n_seg, unsigned worker, unsigned n_workers,
+                                               const NmsWs& W, long long n_seg, int C, unsigned worker, unsigned n_workers,
                                                unsigned char* __restrict__ keep) {
     const int lane = threadIdx.x & 31;
     const bool pos_thr = thr > 0.0;
@@ -361,11 +383,11 @@ __device__ __forceinline__ void nms_small_work(const double* __restrict__ rows, 
     for (unsigned w = warp_id; w * kPerWarp < n_tiny; w += n_warps) {
         const unsigned e = w * kPerWarp + (lane / kTiny);
         const int seg = (e < n_tiny) ? W.small_list[e] : -1;
-        nms_group_segment<MODE, kTiny>(rows, thr, conf_thr, sigma, W, seg, pos_thr, keep);
+        nms_group_segment<MODE, kTiny>(rows, thr, conf_thr, sigma, W, seg, pos_thr, C, keep);
     }
     const unsigned n_small = W.ctrl[0];
     for (unsigned w = warp_id; w < n_small; w += n_warps)
-        nms_group_segment<MODE, 32>(rows, thr, conf_thr, sigma, W, W.small_list[n_seg - 1 - (long long)w], pos_thr, keep);
+        nms_group_segment<MODE, 32>(rows, thr, conf_thr, sigma, W, W.small_list[n_seg - 1 - (long long)w], pos_thr, C, keep);
 }
 
 // ---- big segments: one CTA each ---------------------------------------------------
@@ -406,7 +428,7 @@ struct BigShared {
 // pointers live in (the function is inlined once per space).
 template <int MODE, bool SMEM>
 __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, double thr, double conf_thr, double sigma,
-                                            const NmsWs& W, int seg, int n, long long start, int P, int* mem, int* ord,
+                                            const NmsWs& W, int seg, int n_class, int n, long long start, int P, int* mem, int* ord,
                                             double2* X, double2* Y, double2* C, double* A, unsigned char* rem,
                                             BigShared& S, unsigned char* __restrict__ keep) {
     constexpr int M = (MODE == 3) ? 1 : MODE;
@@ -579,12 +601,15 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
         long long total;
         const long long ex = block_exclusive_scan((long long)kf, S.scan, total);
         if (i < n) {
-            W.local_rank[start + i] = kf ? (int)(carry + ex) : -1;
+            W.local_rank[mem[i]] = kf ? (int)(carry + ex) : -1;
             keep[mem[i]] = (unsigned char)kf;
         }
         carry += total;
     }
-    if (tid == 0) W.seg_kept[seg] = (unsigned)carry;
+    if (tid == 0) {
+        W.seg_kept[seg] = (unsigned)carry;
+        atomicAdd(&W.img_kept[seg / n_class], (unsigned)carry);
+    }
 }
 
 // All suppression work of one yb_nms call in ONE launch: the first CTAs take the big segments
@@ -592,7 +617,7 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
 template <int MODE>
 __global__ void __launch_bounds__(kBigThreads, 2)
 nms_sweep_kernel(const double* __restrict__ rows, double thr, double conf_thr, double sigma, NmsWs W, long long R,
-                 long long n_seg, unsigned big_blocks, unsigned char* __restrict__ keep) {
+                 long long n_seg, int C, unsigned big_blocks, unsigned char* __restrict__ keep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* s_X = reinterpret_cast<double2*>(smem_raw);                  // [kBigCap] each
     double2* s_Y = s_X + kBigCap;
@@ -606,7 +631,7 @@ nms_sweep_kernel(const double* __restrict__ rows, double thr, double conf_thr, d
     const unsigned n_big = W.ctrl[1];
     const unsigned big_used = min(n_big, big_blocks);   // CTAs that have a big segment to start with
     if (blockIdx.x >= big_used) {
-        nms_small_work<MODE>(rows, thr, conf_thr, sigma, W, n_seg, blockIdx.x - big_used, gridDim.x - big_used, keep);
+        nms_small_work<MODE>(rows, thr, conf_thr, sigma, W, n_seg, C, blockIdx.x - big_used, gridDim.x - big_used, keep);
         return;
     }
     for (unsigned wi = blockIdx.x; wi < n_big; wi += big_used) {
@@ -617,37 +642,61 @@ nms_sweep_kernel(const double* __restrict__ rows, double thr, double conf_thr, d
         int P = 1;
         while (P < n) P <<= 1;
         if (n <= kBigCap) {
-            nms_segment<MODE, true>(rows, thr, conf_thr, sigma, W, seg, n, start, P, s_mem, s_ord, s_X, s_Y, s_C, s_A,
+            nms_segment<MODE, true>(rows, thr, conf_thr, sigma, W, seg, C, n, start, P, s_mem, s_ord, s_X, s_Y, s_C, s_A,
                                     s_rem, S, keep);
         } else {   // planes in the global scratch: [X 2R | Y 2R | C 2R | A R] doubles
             double2* gX = reinterpret_cast<double2*>(W.gbox) + start;
             double2* gY = reinterpret_cast<double2*>(W.gbox + 2 * R) + start;
             double2* gC = reinterpret_cast<double2*>(W.gbox + 4 * R) + start;
             double* gA = W.gbox + 6 * R + start;
-            nms_segment<MODE, false>(rows, thr, conf_thr, sigma, W, seg, n, start, P, W.gmem_pad + 2 * start,
+            nms_segment<MODE, false>(rows, thr, conf_thr, sigma, W, seg, C, n, start, P, W.gmem_pad + 2 * start,
                                      W.gord_pad + 2 * start, gX, gY, gC, gA, W.gremoved + start, S, keep);
         }
     }
 }
 
-__global__ void nms_emit_kernel(const double* __restrict__ rows, const long long* __restrict__ row_offsets,
-                                long long n_img, long long cap, int C, NmsWs W, double* __restrict__ out_rows,
-                                long long* __restrict__ out_offsets, long long* __restrict__ out_seg_offsets) {
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nth = (long long)gridDim.x * blockDim.x;
-    const long long n_seg = n_img * C;
-    if (out_offsets != nullptr)
-        for (long long i = tid; i <= n_img; i += nth) out_offsets[i] = W.out_start[i * C];
-    if (out_seg_offsets != nullptr)
-        for (long long i = tid; i <= n_seg; i += nth) out_seg_offsets[i] = W.out_start[i];
+// grid (n_img, Y): every CTA of image i sums the survivor counts of the earlier images, scans the
+// image's C segments (per-(image, class) output extents) and writes its share of the survivors.
+__global__ void __launch_bounds__(256)
+nms_emit_kernel(const double* __restrict__ rows, const long long* __restrict__ row_offsets, long long n_img,
+                long long cap, int C, NmsWs W, double* __restrict__ out_rows, long long* __restrict__ out_offsets,
+                long long* __restrict__ out_seg_offsets) {
+    __shared__ long long s_warp[32];
+    const long long n = device_row_count(row_offsets, n_img, cap);
+    const long long img = blockIdx.x, seg0 = img * C;
+    const int tid = threadIdx.x;
+    long long mine = 0;
+    for (long long j = tid; j < img; j += blockDim.x) mine += W.img_kept[j];
+    long long base;
+    block_exclusive_scan(mine, s_warp, base);   // block total = survivors of the earlier images
+    long long carry = 0;
+    for (int c0 = 0; c0 < C; c0 += blockDim.x) {
+        const int c = c0 + tid;
+        const unsigned cnt = (c < C) ? W.seg_kept[seg0 + c] : 0u;
+        long long total;
+        const long long ex = block_exclusive_scan((long long)cnt, s_warp, total);
+        if (c < C) {
+            W.out_start[seg0 + c] = base + carry + ex;   // same value from every CTA of the image
+            if (blockIdx.y == 0 && out_seg_offsets != nullptr) out_seg_offsets[seg0 + c] = base + carry + ex;
+        }
+        carry += total;
+    }
+    if (blockIdx.y == 0 && tid == 0) {
+        if (out_offsets != nullptr) out_offsets[img] = base;
+        if (img == n_img - 1) {
+            if (out_offsets != nullptr) out_offsets[n_img] = base + carry;
+            if (out_seg_offsets != nullptr) out_seg_offsets[n_img * C] = base + carry;
+        }
+    }
     if (out_rows == nullptr) return;
-    const long long n_grouped = W.seg_start[n_seg];
-    for (long long pos = tid; pos < n_grouped; pos += nth) {
-        const int r = W.local_rank[pos];
+    __syncthreads();   // this CTA's out_start writes are visible to its own threads
+    const long long r0 = min(row_offsets[img], n), r1 = min(row_offsets[img + 1], n);
+    for (long long row = r0 + (long long)blockIdx.y * blockDim.x + tid; row < r1; row += (long long)gridDim.y * blockDim.x) {
+        const int seg = W.row_seg[row];
+        if (seg < 0) continue;
+        const int r = W.local_rank[row];
         if (r < 0) continue;
-        const int m = W.members[pos];
-        const int seg = W.row_seg[m];
-        const double* src = rows + (long long)m * 7;
+        const double* src = rows + row * 7;
         double* dst = out_rows + (W.out_start[seg] + r) * 7;
 #pragma unroll
         for (int k = 0; k < 7; ++k) dst[k] = src[k];
@@ -698,6 +747,7 @@ static size_t nms_layout(long long R, long long n_seg, NmsWs* W, char* base) {
     YB_CARVE(seg_count, unsigned int, n_seg + 1)
     YB_CARVE(seg_fill, unsigned int, n_seg)
     YB_CARVE(ctrl, unsigned int, 8)
+    YB_CARVE(img_kept, unsigned int, n_seg + 1)   // n_img + 1 would do; n_seg bounds it without n_img here
     const size_t zero_bytes = off;
     YB_CARVE(seg_kept, unsigned int, n_seg + 1)
     YB_CARVE(row_seg, int, R)
@@ -712,8 +762,6 @@ static size_t nms_layout(long long R, long long n_seg, NmsWs* W, char* base) {
     YB_CARVE(gord_pad, int, 2 * R)
     YB_CARVE(gremoved, unsigned char, R)
 #undef YB_CARVE
-    const size_t at = carve(off, scan_workspace_bytes(n_seg + 1));
-    if (W) W->scan_ws = base + at;
     (void)zero_bytes;
     return off;
 }
@@ -739,7 +787,7 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
     if (n_rows < 0 || n_img < 0 || class_num <= 0) return YB_E_SHAPE;
     if (iou_mode != 1 && iou_mode != 2 && iou_mode != 3) return YB_E_PARAM;
     if (n_rows > 0 && (rows == nullptr || keep == nullptr)) return YB_E_NULL;
-    if (n_rows > (int64_t)INT_MAX / 2) return YB_E_SHAPE;
+    if (n_rows > (int64_t)INT_MAX / 2 || n_img > (int64_t)INT_MAX / 2) return YB_E_SHAPE;
     if (workspace_bytes < yb_nms_workspace_bytes(n_rows, n_img, class_num) || ((uintptr_t)workspace & 255))
         return YB_E_WORKSPACE;
     const long long n_seg = n_img * class_num;
@@ -759,10 +807,10 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
     const int row_blocks = (int)min((long long)kNumSMs * 8, ((long long)n_rows + threads - 1) / threads);
     nms_classify_kernel<<<row_blocks, threads, 0, stream>>>(rows, row_offsets, n_img, n_rows, class_num, W, keep);
     YB_CUDA_TRY(cudaGetLastError());
-    int rc = exclusive_scan_u32(W.seg_count, n_seg, W.seg_start, W.scan_ws, stream);
-    if (rc != 0) return rc;
-    const int sc_blocks = (int)min((long long)kNumSMs * 8, (max((long long)n_rows, (long long)n_seg) + threads - 1) / threads);
-    nms_scatter_kernel<<<sc_blocks, threads, 0, stream>>>(row_offsets, n_img, n_rows, n_seg, W);
+    // per-image kernels: grid (n_img, Y) with Y CTAs sharing the rows of one image
+    const long long per_img = (n_rows + n_img - 1) / n_img;
+    const dim3 img_grid((unsigned)n_img, (unsigned)max(1LL, min(64LL, (per_img + 2047) / 2048)));
+    nms_scatter_kernel<<<img_grid, threads, 0, stream>>>(row_offsets, n_img, n_rows, class_num, W);
     YB_CUDA_TRY(cudaGetLastError());
 
     // one launch: up to 2 CTAs/SM worth of big-segment CTAs first, then the warp-list workers
@@ -775,18 +823,16 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
         YB_CUDA_TRY(cudaFuncSetAttribute(nms_sweep_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                          (int)big_smem));                                                      \
         nms_sweep_kernel<M><<<big_blocks + small_blocks, kBigThreads, big_smem, stream>>>(                     \
-            rows, nms_threshold, conf_thr, sigma, W, n_rows, n_seg, big_blocks, keep);                         \
+            rows, nms_threshold, conf_thr, sigma, W, n_rows, n_seg, class_num, big_blocks, keep);                         \
     } while (0)
     if (iou_mode == 1) YB_NMS_LAUNCH(1);
     else if (iou_mode == 2) YB_NMS_LAUNCH(2);
     else YB_NMS_LAUNCH(3);
 #undef YB_NMS_LAUNCH
     YB_CUDA_TRY(cudaGetLastError());
-    rc = exclusive_scan_u32(W.seg_kept, n_seg, W.out_start, W.scan_ws, stream);
-    if (rc != 0) return rc;
     if (out_rows != nullptr || out_offsets != nullptr || out_seg_offsets != nullptr) {
-        nms_emit_kernel<<<row_blocks, threads, 0, stream>>>(rows, row_offsets, n_img, n_rows, class_num, W,
-                                                            out_rows, out_offsets, out_seg_offsets);
+        nms_emit_kernel<<<img_grid, threads, 0, stream>>>(rows, row_offsets, n_img, n_rows, class_num, W,
+                                                          out_rows, out_offsets, out_seg_offsets);
         YB_CUDA_TRY(cudaGetLastError());
     }
     return YB_OK;

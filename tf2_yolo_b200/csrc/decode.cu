@@ -288,7 +288,7 @@ int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double
     int rc = exclusive_scan_u32(ws.counts, ws.total_cells, ws.offsets, ws.scan_ws, stream);
     if (rc != 0) return rc;
     const int threads = 256;
-    const int blocks2 = kNumSMs * 8;
+    const int blocks2 = kNumSMs * 5;   // one wave (48 registers: 5 CTAs of 256 threads per SM)
     if (is_f64)
         decode_emit_kernel<double><<<blocks2, threads, 0, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
                                                                     row_offsets);

@@ -31,6 +31,7 @@ constexpr int kMaskParts = kBigThreads / 64;   // threads per row of the 64x64 b
 constexpr int kBigCap = 1536;      // boxes per segment held in shared memory
 constexpr int kBigP = 2048;        // power-of-two padding of the index arrays of such a segment
 constexpr int kSweep = 64;         // sweep block (one 64-bit mask word per box)
+constexpr int kCountSort = 128;    // segments up to this size are ordered by rank counting, not bitonic sorts
 constexpr int kTiny = 8;           // segments up to this size share a warp (one 8-lane group each)
 
 // np.maximum / np.minimum: NaN propagates (fmax/fmin would drop it)
@@ -437,25 +438,57 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
     const bool pos_thr = thr > 0.0;
     double* cf = A;
 
-    // 1. original order: sort row ids ascending
-    for (int i = tid; i < P; i += kBigThreads) mem[i] = (i < n) ? W.members[start + i] : INT_MAX;
-    __syncthreads();
-    block_bitonic(mem, P, [](int a, int b) { return a < b; });
-    for (int i = tid; i < n; i += kBigThreads) {
-        const int m = mem[i];
-        W.members[start + i] = m;
-        const double* r = rows + (long long)m * 7;
-        cf[i] = __dmul_rn(r[4], r[6]);
-        ord[i] = i;
+    if (n <= kCountSort) {
+        // short segment: both orders by all-pairs rank counting (2 barriers each instead of a
+        // barrier per bitonic pass - this path is the tail of every sparse-scene launch)
+        const int my = (tid < n) ? W.members[start + tid] : INT_MAX;
+        if (tid < n) ord[tid] = my;   // ord is scratch here
+        __syncthreads();
+        if (tid < n) {
+            int rk = 0;
+            for (int j = 0; j < n; ++j) rk += (ord[j] < my) ? 1 : 0;
+            mem[rk] = my;             // 1. original order: row ids ascending
+        }
+        __syncthreads();
+        double ck = 0.0;
+        if (tid < n) {
+            const double* r = rows + (long long)mem[tid] * 7;
+            ck = __dmul_rn(r[4], r[6]);
+            cf[tid] = ck;
+        }
+        __syncthreads();
+        if (tid < n) {
+            // 2. visit order: confidence descending, ties -> higher original index first (NaN
+            //    confidences order as +inf so that the ranks stay a permutation)
+            const double key = (ck != ck) ? INFINITY : ck;
+            int vis = 0;
+            for (int j = 0; j < n; ++j) {
+                const double cj = cf[j];
+                const double kj = (cj != cj) ? INFINITY : cj;
+                vis += (kj > key || (kj == key && j > tid)) ? 1 : 0;
+            }
+            ord[vis] = tid;
+        }
+        __syncthreads();
+    } else {
+        // 1. original order: sort row ids ascending
+        for (int i = tid; i < P; i += kBigThreads) mem[i] = (i < n) ? W.members[start + i] : INT_MAX;
+        __syncthreads();
+        block_bitonic(mem, P, [](int a, int b) { return a < b; });
+        for (int i = tid; i < n; i += kBigThreads) {
+            const double* r = rows + (long long)mem[i] * 7;
+            cf[i] = __dmul_rn(r[4], r[6]);
+            ord[i] = i;
+        }
+        for (int i = n + tid; i < P; i += kBigThreads) ord[i] = INT_MAX;
+        __syncthreads();
+        // 2. visit order: confidence descending, ties -> higher original index first
+        block_bitonic(ord, P, [cf, n](int a, int b) {
+            if (a >= n || b >= n) return a < b;
+            const double ca = cf[a], cb = cf[b];
+            return ca > cb || (ca == cb && a > b);
+        });
     }
-    for (int i = n + tid; i < P; i += kBigThreads) ord[i] = INT_MAX;
-    __syncthreads();
-    // 2. visit order: confidence descending, ties -> higher original index first
-    block_bitonic(ord, P, [cf, n](int a, int b) {
-        if (a >= n || b >= n) return a < b;
-        const double ca = cf[a], cb = cf[b];
-        return ca > cb || (ca == cb && a > b);
-    });
     if (MODE == 3) {
         // soft-NMS: every box multiplies its confidence by exp(-IoU^2/sigma) for each earlier-visited
         // box it overlaps (in visit order); deleted <=> it was decayed below conf_thr.

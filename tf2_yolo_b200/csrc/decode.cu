@@ -273,19 +273,22 @@ int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params
         if (L.n_img * L.cells[s] > 0xffffffffll || L.B[s] > 32 || (long long)L.B[s] * L.C >= (1 << 22))
             return YB_E_SHAPE;  // HotBox packs the cell index in 32 bits, box in 6, row offset in 22
     ws.total_cells = total;
+    // [n_hot | scan status] first: ONE memset clears both before the counting pass
     ws.n_hot = reinterpret_cast<unsigned int*>(workspace);
-    ws.counts = reinterpret_cast<unsigned int*>((char*)workspace + 256);
+    ws.scan_ws = (char*)workspace + 256;
+    ws.zero_bytes = 256 + scan_workspace_bytes(total > 0 ? total : 1);
+    ws.counts = reinterpret_cast<unsigned int*>((char*)workspace + ws.zero_bytes);
     ws.offsets = reinterpret_cast<long long*>((char*)ws.counts + decode_counts_bytes(total));
     long long total_boxes = 0;
     for (int s = 0; s < L.n_scales; ++s) total_boxes += L.n_img * L.cells[s] * L.B[s];
     ws.hot = reinterpret_cast<HotBox*>((char*)ws.offsets + decode_offsets_bytes(total));
-    ws.scan_ws = (char*)ws.hot + decode_hot_bytes(total_boxes);
+    (void)total_boxes;
     return YB_OK;
 }
 
 int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double* rows, long long cap,
-                  long long* row_offsets, cudaStream_t stream) {
-    int rc = exclusive_scan_u32(ws.counts, ws.total_cells, ws.offsets, ws.scan_ws, stream);
+                  long long* row_offsets, cudaStream_t stream, bool status_zeroed) {
+    int rc = exclusive_scan_u32(ws.counts, ws.total_cells, ws.offsets, ws.scan_ws, stream, status_zeroed);
     if (rc != 0) return rc;
     const int threads = 256;
     const int blocks2 = kNumSMs * 5;   // one wave (48 registers: 5 CTAs of 256 threads per SM)
@@ -338,7 +341,7 @@ extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decod
     const int ctas_per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 2048))));
     const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
     const int threads1 = (ncw + 1) * 32;
-    YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, sizeof(unsigned int), stream));
+    YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, ws.zero_bytes, stream));
     if (p->is_f64) {
         YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, ws.counts, ws.n_hot, ws.hot);
@@ -347,7 +350,7 @@ extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decod
         decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, ws.counts, ws.n_hot, ws.hot);
     }
     YB_CUDA_TRY(cudaGetLastError());
-    return decode_finish(L, ws, p->is_f64 != 0, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream);
+    return decode_finish(L, ws, p->is_f64 != 0, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream, true);
 }
 
 // Second half of a split decode: the per-cell counts and the hot-cell list are already in

@@ -42,6 +42,7 @@ struct DecodeWs {          // carved out of the caller's decode workspace
     long long* offsets;    // exclusive scan of counts (+ total)
     HotBox* hot;           // work list of boxes with hits
     void* scan_ws;
+    size_t zero_bytes;     // n_hot + scan status: cleared by one memset before the counting pass
     long long total_cells;
 };
 
@@ -50,6 +51,6 @@ int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params
                  size_t workspace_bytes, DecodeLaunch& L, DecodeWs& ws);
 // scan of the per-cell counts + emission of the rows (after counts / hot list are complete)
 int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double* rows, long long cap,
-                  long long* row_offsets, cudaStream_t stream);
+                  long long* row_offsets, cudaStream_t stream, bool status_zeroed = false);
 
 }  // namespace yb

@@ -1027,12 +1027,12 @@ extern "C" int yb_loss_decode_fused(const yb_loss_scale* scales, int n_scales, f
         return loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes,
                          stream_);
     }
-    YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, sizeof(unsigned int), stream));
+    YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, ws.zero_bytes, stream));
     FusedDecode fd{&DL, &ws};
     rc = loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes,
                    stream_, &fd);
     if (rc != YB_OK || count_only) return rc;
-    return decode_finish(DL, ws, false, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream);
+    return decode_finish(DL, ws, false, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream, true);
 }
 
 static int loss_single(int version, const float* y_true, const float* y_pred, int64_t n_cells,

@@ -191,8 +191,9 @@ static inline size_t scan_workspace_bytes(long long n) {
 }
 
 // out has n+1 entries; out[n] = total.  n >= 1.
+// status_zeroed: the caller has already cleared scan_workspace_bytes(n) bytes of the workspace.
 static inline int exclusive_scan_u32(const unsigned int* in, long long n, long long* out,
-                                     void* workspace, cudaStream_t stream) {
+                                     void* workspace, cudaStream_t stream, bool status_zeroed = false) {
     if (n <= 64 * 1024) {
         scan_single_block<<<1, 1024, 0, stream>>>(in, n, out);
         return (int)cudaGetLastError();
@@ -200,7 +201,8 @@ static inline int exclusive_scan_u32(const unsigned int* in, long long n, long l
     const int n_blocks = (int)((n + kLbTile - 1) / kLbTile);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(workspace);
     unsigned int* ticket = reinterpret_cast<unsigned int*>(status + n_blocks);
-    YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)(n_blocks + 1) * sizeof(long long), stream));
+    if (!status_zeroed)
+        YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)(n_blocks + 1) * sizeof(long long), stream));
     scan_lookback_kernel<<<n_blocks, kLbThreads, 0, stream>>>(in, n, out, status, ticket);
     return (int)cudaGetLastError();
 }

@@ -161,3 +161,73 @@ def test_label_helpers(golden):
     ref = big.astype(np.float64).reshape(-1, 85)[:, 5:].sum(axis=0)
     got = engine.column_sums(torch.from_numpy(big[..., 5:].reshape(-1, 80).copy()).cuda()).cpu().numpy()
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_nms_nonfinite_boxes_and_nonpositive_threshold(mode):
+    """NaN / Inf coordinates behave as in NumPy (np.maximum / np.minimum propagate NaN: such a box
+    neither suppresses nor is suppressed); thresholds <= 0 take the exact expression for every pair."""
+    rng = np.random.default_rng(77)
+    rows = synth.make_dense_candidates(rng, 400, 2)
+    rows[5, 0] = np.nan
+    rows[17, 3] = np.nan
+    rows[30, 2] = np.inf            # infinitely wide box
+    rows[31, 0] = np.inf            # centre at infinity: inf - inf inside the corners
+    rows[40:43, 2:4] = 0.0          # zero-size boxes ...
+    rows[41, :2] = rows[40, :2]     # ... two of them identical (0/0 in the DIoU term)
+    rows[50, 4] = np.nan            # NaN confidences are visited first, like np.argsort()[::-1];
+    rows[300, 6] = np.nan           # two of them: higher index first
+    rows[[60, 61], 4] = np.inf      # and infinite ones right after
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        for thr in (0.45, 0.0, -0.25):
+            ref = ot.nms_keep(rows, 2, thr, mode)
+            res = engine.nms_batch(torch.from_numpy(rows).cuda(),
+                                   torch.tensor([0, len(rows)], dtype=torch.int64, device="cuda"), 2, thr, mode)
+            got = res["keep"].cpu().numpy().astype(bool)
+            assert np.array_equal(got, ref), (mode, thr, np.nonzero(got != ref)[0][:10])
+
+
+def test_nms_class_counts_and_ragged_images():
+    """One class with thousands of rows (CTA + global-scratch paths), hundreds of classes with a few
+    rows each (chunked per-image scans), empty first / last images, 33..128-box segments (rank-counting
+    order) and >128 (bitonic)."""
+    rng = np.random.default_rng(78)
+    # (a) class_num = 1, the reference's default
+    rows = synth.make_dense_candidates(rng, 3000, 1)
+    parts = [rows[:0], rows[:40], rows[40:140], rows[140:3000], rows[:0]]
+    offs = np.cumsum([0] + [len(p) for p in parts])
+    res = engine.nms_batch(torch.from_numpy(rows).cuda(), torch.from_numpy(offs).cuda(), 1, 0.45, 1, want_seg_offsets=True)
+    keep = res["keep"].cpu().numpy().astype(bool)
+    out_rows, out_off = res["out_rows"].cpu().numpy(), res["out_offsets"].cpu().numpy()
+    for i, p in enumerate(parts):
+        want = ot.nms(p, 1, 0.45, 1) if len(p) else p
+        assert np.array_equal(keep[offs[i]:offs[i + 1]], ot.nms_keep(p, 1, 0.45, 1) if len(p) else keep[:0]), i
+        assert np.array_equal(out_rows[out_off[i]:out_off[i + 1]], want), i
+    assert np.array_equal(res["seg_offsets"].cpu().numpy(), out_off)     # C = 1: segments are images
+    # (b) 700 classes (more than one 256-thread chunk in the per-image scans), two images
+    rows = synth.make_dense_candidates(rng, 5000, 700)
+    offs = np.array([0, 2100, 5000])
+    res = engine.nms_batch(torch.from_numpy(rows).cuda(), torch.from_numpy(offs).cuda(), 700, 0.3, 2, want_seg_offsets=True)
+    out_rows, out_off = res["out_rows"].cpu().numpy(), res["out_offsets"].cpu().numpy()
+    seg = res["seg_offsets"].cpu().numpy()
+    for i in range(2):
+        p = rows[offs[i]:offs[i + 1]]
+        want = ot.nms(p, 700, 0.3, 2)
+        assert np.array_equal(out_rows[out_off[i]:out_off[i + 1]], want), i
+        per_class = np.bincount(want[:, 5].astype(int), minlength=700)
+        assert np.array_equal(np.diff(seg[i * 700:(i + 1) * 700 + 1]), per_class), i
+
+
+def test_decode_scan_sizes():
+    """Per-cell count scan: single-block path (<= 64k cells) and the chained look-back path with a
+    ragged last block, against the oracle's decode."""
+    rng = np.random.default_rng(79)
+    for n_img, S, thr in ((3, 13, 0.3), (420, 13, 0.6), (37, 52, 0.7)):     # 507 / 70,980 / 100,048 cells
+        B, C = 3, 7
+        yp = rng.uniform(0, 1, (n_img, S, S, B * (5 + C))).astype(np.float32)
+        rows, offs = engine.decode_batch_exact([torch.from_numpy(yp).cuda()], C, thr, 3)
+        rows_h, offs_h = rows.cpu().numpy(), offs.cpu().numpy()
+        for i in (0, n_img // 2, n_img - 1):
+            ref = ot.decode(yp[i], class_num=C, threshold=thr, version=3).reshape(-1, 7)
+            assert np.array_equal(rows_h[offs_h[i]:offs_h[i + 1]], ref), (n_img, S, i)
+        assert offs_h[-1] == len(rows_h)

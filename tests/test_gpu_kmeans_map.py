@@ -103,3 +103,30 @@ def test_map_match_vs_oracle(golden):
             else:
                 assert (best_gt[pos:pos + n] == -1).all()
             pos += n
+
+
+def test_kmeans_many_clusters_and_extreme_areas():
+    """k > 9 (counters in shared memory instead of packed registers), k = 1, areas outside the cell
+    table (below 2^-15 and above 2), non-finite boxes: assignments equal np.argmin bit for bit."""
+    rng = np.random.default_rng(51)
+    data = synth.make_kmeans_boxes(rng, 100_003, k=9)
+    data[:50] = rng.uniform(1e-4, 4e-3, (50, 2))            # areas down to 1e-8
+    data[50:60] = rng.uniform(1.5, 3.0, (10, 2))            # areas above 2
+    data[60] = [np.nan, 0.5]
+    data[61] = [np.inf, 0.5]
+    data[62] = [0.0, 0.5]
+    for k in (1, 2, 12, 16):
+        centers = rng.uniform(0.02, 0.9, (k, 2))
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ref = okm.assign(data, centers, okm.iou_dist)
+        a, sums, counts = engine.kmeans_assign(torch.from_numpy(data).cuda(), torch.from_numpy(centers).cuda(),
+                                               YB_DIST_IOU, want_assign=True)
+        assert np.array_equal(a.cpu().numpy(), ref), k
+        assert np.array_equal(counts.cpu().numpy(), np.bincount(ref, minlength=k)), k
+    # centroids 2^40 apart: the certainty window is clamped to ratios >= 2^-20, the rest is exact
+    centers = np.array([[1e-7, 1e-6], [0.5, 0.5], [1e3, 1e3]])
+    d2 = np.concatenate([data[:1000], rng.uniform(1e-7, 1e-3, (200, 2)), rng.uniform(10, 1e3, (200, 2))])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref = okm.assign(d2, centers, okm.iou_dist)
+    a, _, _ = engine.kmeans_assign(torch.from_numpy(d2).cuda(), torch.from_numpy(centers).cuda(), YB_DIST_IOU, True)
+    assert np.array_equal(a.cpu().numpy(), ref)

@@ -293,7 +293,7 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         const double* src = staged ? my_ring + (size_t)stage * tile_pts * D : L.data + p0 * D;
         mbar_wait(&my_full[stage], parity);
         if (kBoxes) {
-            if (np == tile_pts) {   // full tile: no bounds tests
+            if (np == tile_pts && (tile_pts % (32 * kU)) == 0) {   // full tile of whole batches: no bounds tests
                 const bool have[kU] = {true, true, true, true};
                 for (int base = 0; base < tile_pts; base += 32 * kU) {
                     double2 bx[kU];

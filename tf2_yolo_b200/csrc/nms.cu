@@ -34,6 +34,15 @@ constexpr int kSweep = 64;         // sweep block (one 64-bit mask word per box)
 constexpr int kCountSort = 128;    // segments up to this size are ordered by rank counting, not bitonic sorts
 constexpr int kTiny = 8;           // segments up to this size share a warp (one 8-lane group each)
 
+// Visit order of np.argsort(conf)[::-1] (tools.py:717): descending confidence, NaN first (NumPy
+// sorts NaN last), equal confidences -> higher original index first (documented tie rule).
+__device__ __forceinline__ bool visited_before(double ca, int a, double cb, int b) {
+    const bool na = ca != ca, nb = cb != cb;
+    if (na != nb) return na;
+    if (!na && ca != cb) return ca > cb;
+    return a > b;
+}
+
 // np.maximum / np.minimum: NaN propagates (fmax/fmin would drop it)
 __device__ __forceinline__ double np_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
 __device__ __forceinline__ double np_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
@@ -316,7 +325,7 @@ __device__ __forceinline__ void nms_group_segment(const double* __restrict__ row
     unsigned sup = 0;
     for (int j = 0; j < nmax; ++j) {
         const double cj = __shfl_sync(0xffffffffu, conf, j, GW);
-        vis += (j < n && (cj > conf || (cj == conf && j > gl))) ? 1 : 0;
+        vis += (j < n && j != gl && visited_before(cj, j, conf, gl)) ? 1 : 0;
         if (MODE != 3) {
             const BoxC other = shfl_box<GW>(mine, j, MODE == 2);
             const int mj = __shfl_sync(0xffffffffu, m, j, GW);
@@ -458,15 +467,9 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
         }
         __syncthreads();
         if (tid < n) {
-            // 2. visit order: confidence descending, ties -> higher original index first (NaN
-            //    confidences order as +inf so that the ranks stay a permutation)
-            const double key = (ck != ck) ? INFINITY : ck;
+            // 2. visit order: confidence descending, ties -> higher original index first
             int vis = 0;
-            for (int j = 0; j < n; ++j) {
-                const double cj = cf[j];
-                const double kj = (cj != cj) ? INFINITY : cj;
-                vis += (kj > key || (kj == key && j > tid)) ? 1 : 0;
-            }
+            for (int j = 0; j < n; ++j) vis += (j != tid && visited_before(cf[j], j, ck, tid)) ? 1 : 0;
             ord[vis] = tid;
         }
         __syncthreads();
@@ -485,8 +488,7 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
         // 2. visit order: confidence descending, ties -> higher original index first
         block_bitonic(ord, P, [cf, n](int a, int b) {
             if (a >= n || b >= n) return a < b;
-            const double ca = cf[a], cb = cf[b];
-            return ca > cb || (ca == cb && a > b);
+            return visited_before(cf[a], a, cf[b], b);
         });
     }
     if (MODE == 3) {

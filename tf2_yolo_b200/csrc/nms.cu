@@ -7,13 +7,15 @@
 //   classify  : row -> segment (image, class); per-segment counts (atomics)
 //   scatter   : per image: scan of its C segment counts (start offsets), row ids grouped by
 //               segment, segments binned into work lists
-//   small     : segments of <= 32 boxes, one WARP each: rank by confidence with
-//               shuffles, 32-bit suppression masks from warp-broadcast boxes,
-//               mask sweep in registers
-//   big       : larger segments, one CTA each: bitonic sorts (row id, confidence),
-//               boxes staged in shared memory in visit order, blocked greedy sweep
-//               (64x64 IoU bitmask per block, serial resolve of the block, kept
-//               boxes of the block suppress the rest of the segment in parallel)
+//   sweep     : ONE launch.  The first CTAs take the big segments (> 32 boxes, one CTA each):
+//               boxes ordered (rank counting up to 128 boxes, bitonic sorts above), corners
+//               and areas staged once in shared memory in visit order, blocked greedy sweep
+//               (64x64 suppression bitmask per block, serial resolve of the block, the
+//               block's kept boxes against every later box).  All other CTAs work through
+//               the warp lists: segments of <= 8 boxes four to a warp (8-lane groups),
+//               9..32 boxes one warp each - rank by confidence with shuffles, suppression
+//               masks from group-broadcast boxes, mask sweep in registers.
+//               The pair test is division-free (see suppresses_fast).
 //   emit      : per image: prefix of the survivor counts of earlier images + scan of its own C
 //               segments, survivors written in the reference's order (class-major, original
 //               order inside a class)

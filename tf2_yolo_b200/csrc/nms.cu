@@ -431,6 +431,7 @@ struct BigShared {
     int kept[kSweep];
     int krow[kSweep];
     int nkept;
+    int nlist;
     long long scan[32];
 };
 
@@ -442,7 +443,7 @@ template <int MODE, bool SMEM>
 __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, double thr, double conf_thr, double sigma,
                                             const NmsWs& W, int seg, int n_class, int n, long long start, int P, int* mem, int* ord,
                                             double2* X, double2* Y, double2* C, double* A, unsigned char* rem,
-                                            BigShared& S, unsigned char* __restrict__ keep) {
+                                            unsigned short* alist, BigShared& S, unsigned char* __restrict__ keep) {
     constexpr int M = (MODE == 3) ? 1 : MODE;
     constexpr int kJpt = (M == 2) ? 1 : 2;   // boxes a thread carries at once through the kept list
     const int tid = threadIdx.x;
@@ -539,7 +540,12 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
         if (M == 2) { const double2 c = C[v]; b.cx = c.x; b.cy = c.y; } else { b.cx = 0.0; b.cy = 0.0; }
         return b;
     };
-    // 3. blocked greedy sweep
+    // 3. blocked greedy sweep.  `alist` (shared-memory segments only) holds the visit positions
+    //    that are still alive behind the last finished block, compacted after every block, so the
+    //    threads share the remaining boxes evenly and no lane carries a dead box; without it the
+    //    threads stride over all positions behind the block.
+    unsigned short* cur_list = nullptr;   // nullptr: implicit list = every position behind the block
+    int n_list = 0;
     for (int blk = 0; MODE != 3 && blk < n; blk += kSweep) {
         const int m = min(kSweep, n - blk);
         if (tid < kSweep) S.mask[tid] = 0ull;
@@ -561,71 +567,109 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            unsigned long long dead = 0ull;
-            for (int i = 0; i < m; ++i) if (rem[blk + i]) dead |= 1ull << i;
-            int nk = 0;
-            for (int i = 0; i < m; ++i) {
-                if (!((dead >> i) & 1ull)) {
-                    dead |= S.mask[i];
-                    S.kept[nk++] = blk + i;
+        const bool last_block = blk + m >= n;
+        if (tid < 32) {
+            // resolve the block in warp 0: lane l owns rows l and l+32; the serial chain over the 64
+            // rows runs on register shuffles, replicated in every lane
+            const unsigned long long m0 = S.mask[tid], m1 = S.mask[tid + 32];
+            const bool d0 = (tid < m) ? (rem[blk + tid] != 0) : true;
+            const bool d1 = (tid + 32 < m) ? (rem[blk + tid + 32] != 0) : true;
+            unsigned long long dead = (unsigned long long)__ballot_sync(0xffffffffu, d0) |
+                                      ((unsigned long long)__ballot_sync(0xffffffffu, d1) << 32);
+#pragma unroll
+            for (int i = 0; i < kSweep; ++i) {
+                const unsigned long long mi = __shfl_sync(0xffffffffu, (i < 32) ? m0 : m1, i & 31);
+                if (!((dead >> i) & 1ull)) dead |= mi;
+            }
+            const unsigned long long kept_bits = ~dead;   // rows >= m were dead from the start
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int bpos = tid + 32 * h;
+                if (bpos < m) {
+                    const bool kf = (kept_bits >> bpos) & 1ull;
+                    rem[blk + bpos] = kf ? 0 : 1;
+                    if (kf && !last_block) {   // kept boxes of this block, compact
+                        const int q = __popcll(kept_bits & ((1ull << bpos) - 1ull));
+                        const int v = blk + bpos;
+                        S.kX[q] = X[v];
+                        S.kY[q] = Y[v];
+                        if (M == 2) S.kC[q] = C[v];
+                        S.kA[q] = A[v];
+                        S.krow[q] = mem[ord[v]];
+                    }
                 }
             }
-            for (int i = 0; i < m; ++i) rem[blk + i] = (unsigned char)((dead >> i) & 1ull);
-            S.nkept = nk;
+            if (tid == 0) {
+                S.nkept = __popcll(kept_bits);
+                S.nlist = 0;
+            }
         }
         __syncthreads();
+        if (last_block) break;   // nothing left to suppress (uniform)
         const int nk = S.nkept;
-        if (blk + m >= n) continue;   // last block: nothing left to suppress (uniform)
-        if (tid < nk) {               // kept boxes of this block, compact
-            const int v = S.kept[tid];
-            S.kX[tid] = X[v];
-            S.kY[tid] = Y[v];
-            if (M == 2) S.kC[tid] = C[v];
-            S.kA[tid] = A[v];
-            S.krow[tid] = mem[ord[v]];
-        }
-        __syncthreads();
+        const int first = blk + m;
+        const int n_items = (cur_list != nullptr) ? n_list : n - first;
+        unsigned short* next_list = (alist == nullptr) ? nullptr : ((cur_list == alist) ? alist + kBigCap : alist);
         // every surviving box behind the block against the block's kept boxes, kJpt boxes per
         // thread in flight (independent fp64 chains; the kept box is one broadcast load for all)
-        for (int base = blk + m; base < n; base += kBigThreads * kJpt) {
+        for (int base = 0; base < n_items; base += kBigThreads * kJpt) {
             BoxC bj[kJpt];
             int jj[kJpt];
             bool alive[kJpt];
             bool any = false;
 #pragma unroll
             for (int u = 0; u < kJpt; ++u) {
-                jj[u] = base + u * kBigThreads + tid;
-                alive[u] = jj[u] < n && !rem[jj[u]];
+                const int slot = base + u * kBigThreads + tid;
+                jj[u] = n;
+                if (slot < n_items) jj[u] = (cur_list != nullptr) ? (int)cur_list[slot] : first + slot;
+                alive[u] = jj[u] < n && jj[u] >= first && !rem[jj[u]];
                 if (alive[u]) bj[u] = load_box(jj[u]);
                 any |= alive[u];
             }
-            if (!any) continue;
-            for (int q = 0; q < nk; ++q) {
-                BoxC bi;
-                {
-                    const double2 x = S.kX[q], y = S.kY[q];
-                    bi.x0 = x.x; bi.x1 = x.y; bi.y0 = y.x; bi.y1 = y.y;
-                    bi.area = S.kA[q];
-                    if (M == 2) { const double2 c = S.kC[q]; bi.cx = c.x; bi.cy = c.y; } else { bi.cx = 0.0; bi.cy = 0.0; }
+            if (any) {
+                for (int q = 0; q < nk; ++q) {
+                    BoxC bi;
+                    {
+                        const double2 x = S.kX[q], y = S.kY[q];
+                        bi.x0 = x.x; bi.x1 = x.y; bi.y0 = y.x; bi.y1 = y.y;
+                        bi.area = S.kA[q];
+                        if (M == 2) { const double2 c = S.kC[q]; bi.cx = c.x; bi.cy = c.y; } else { bi.cx = 0.0; bi.cy = 0.0; }
+                    }
+                    any = false;
+#pragma unroll
+                    for (int u = 0; u < kJpt; ++u) {
+                        if (alive[u]) {
+                            int r = suppresses_fast<M>(bi, bj[u], thr, pos_thr);
+                            if (r < 0) r = suppresses_exact<M>(rows, S.krow[q], mem[ord[jj[u]]], thr) ? 1 : 0;
+                            if (r) {
+                                alive[u] = false;
+                                rem[jj[u]] = 1;
+                            }
+                        }
+                        any |= alive[u];
+                    }
+                    if (!any) break;
                 }
-                any = false;
+            }
+            if (next_list != nullptr) {   // survivors of this pass go to the next block's list (any order)
 #pragma unroll
                 for (int u = 0; u < kJpt; ++u) {
-                    if (alive[u]) {
-                        int r = suppresses_fast<M>(bi, bj[u], thr, pos_thr);
-                        if (r < 0) r = suppresses_exact<M>(rows, S.krow[q], mem[ord[jj[u]]], thr) ? 1 : 0;
-                        if (r) {
-                            alive[u] = false;
-                            rem[jj[u]] = 1;
-                        }
+                    const unsigned bal = __ballot_sync(0xffffffffu, alive[u]);
+                    if (bal) {
+                        const int lane = tid & 31;
+                        int pos0 = 0;
+                        if (lane == 0) pos0 = atomicAdd(&S.nlist, __popc(bal));
+                        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+                        if (alive[u]) next_list[pos0 + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)jj[u];
                     }
-                    any |= alive[u];
                 }
-                if (!any) break;
             }
         }
         __syncthreads();
+        if (next_list != nullptr) {
+            cur_list = next_list;
+            n_list = S.nlist;
+        }
     }
     // 4. survivors back in original order: keep flag per original position goes into
     //    the (now dead) confidence plane, then a block scan gives each survivor its rank
@@ -663,6 +707,7 @@ nms_sweep_kernel(const double* __restrict__ rows, double thr, double conf_thr, d
     int* s_mem = reinterpret_cast<int*>(s_A + kBigCap);                   // [kBigP]
     int* s_ord = s_mem + kBigP;                                           // [kBigP]
     unsigned char* s_rem = reinterpret_cast<unsigned char*>(s_ord + kBigP);  // [kBigCap]
+    unsigned short* s_alist = reinterpret_cast<unsigned short*>(s_rem + kBigCap);   // [2][kBigCap] alive lists
     __shared__ BigShared S;
 
     const unsigned n_big = W.ctrl[1];
@@ -680,14 +725,14 @@ nms_sweep_kernel(const double* __restrict__ rows, double thr, double conf_thr, d
         while (P < n) P <<= 1;
         if (n <= kBigCap) {
             nms_segment<MODE, true>(rows, thr, conf_thr, sigma, W, seg, C, n, start, P, s_mem, s_ord, s_X, s_Y, s_C, s_A,
-                                    s_rem, S, keep);
+                                    s_rem, s_alist, S, keep);
         } else {   // planes in the global scratch: [X 2R | Y 2R | C 2R | A R] doubles
             double2* gX = reinterpret_cast<double2*>(W.gbox) + start;
             double2* gY = reinterpret_cast<double2*>(W.gbox + 2 * R) + start;
             double2* gC = reinterpret_cast<double2*>(W.gbox + 4 * R) + start;
             double* gA = W.gbox + 6 * R + start;
             nms_segment<MODE, false>(rows, thr, conf_thr, sigma, W, seg, C, n, start, P, W.gmem_pad + 2 * start,
-                                     W.gord_pad + 2 * start, gX, gY, gC, gA, W.gremoved + start, S, keep);
+                                     W.gord_pad + 2 * start, gX, gY, gC, gA, W.gremoved + start, nullptr, S, keep);
         }
     }
 }
@@ -851,7 +896,7 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
     YB_CUDA_TRY(cudaGetLastError());
 
     // one launch: up to 2 CTAs/SM worth of big-segment CTAs first, then the warp-list workers
-    const size_t big_smem = sizeof(double) * 7 * kBigCap + sizeof(int) * 2 * kBigP + kBigCap;
+    const size_t big_smem = sizeof(double) * 7 * kBigCap + sizeof(int) * 2 * kBigP + kBigCap + 2 * sizeof(unsigned short) * kBigCap;
     const unsigned big_blocks = (unsigned)min((long long)kNumSMs * 2, n_seg);
     const long long warp_jobs = (min((long long)n_rows, n_seg) + 7) / 8;   // <= one job per 8 segments... per warp
     const unsigned small_blocks = (unsigned)max(1LL, min((long long)kNumSMs * 4, (warp_jobs + 7) / 8));

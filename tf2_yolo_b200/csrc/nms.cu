@@ -134,14 +134,14 @@ __device__ __forceinline__ bool suppresses_exact(const double* __restrict__ rows
 //     never >= thr.  This also covers NaN boxes (staged with negative overlap).
 //   * otherwise the cross-multiplied inequality is tested with a margin wider than every rounding
 //     error involved (x = inter/den real: x >= thr => fl(x) >= thr; x < thr(1-2^-51) => fl(x) < thr).
+// Second stage of the division-free test, for boxes that overlap (iw, ih > 0): 1 / 0 when
+// certain, -1 when the exact expression must be evaluated.  (ew, eh) = extent of the enclosing
+// box, (dx, dy) = centre distance (DIoU only).
 template <int MODE>
-__device__ __forceinline__ int suppresses_fast(const BoxC& a, const BoxC& b, double thr, bool pos_thr) {
-    const double iw = sel_min(a.x1, b.x1) - sel_max(a.x0, b.x0);
-    const double ih = sel_min(a.y1, b.y1) - sel_max(a.y0, b.y0);
-    if (!pos_thr) return -1;
-    if (!(iw > 0.0 && ih > 0.0)) return 0;
+__device__ __forceinline__ int decide_overlapping(double iw, double ih, double area_a, double area_b, double ew,
+                                                  double eh, double dx, double dy, double thr) {
     const double inter = iw * ih;
-    const double den = ((b.area + a.area) - inter) + kIouEps;
+    const double den = ((area_b + area_a) - inter) + kIouEps;
     if (!(den > 0.0)) return -1;
     if (MODE == 1) {
         const double P = thr * den;
@@ -149,9 +149,7 @@ __device__ __forceinline__ int suppresses_fast(const BoxC& a, const BoxC& b, dou
         if (inter <= P * (1.0 - 9.0e-16)) return 0;
         return -1;
     }
-    const double ew = sel_max(a.x1, b.x1) - sel_min(a.x0, b.x0), eh = sel_max(a.y1, b.y1) - sel_min(a.y0, b.y0);
     const double c2 = ew * ew + eh * eh;
-    const double dx = a.cx - b.cx, dy = a.cy - b.cy;
     const double rho2 = dx * dx + dy * dy;
     // y = inter/den - rho2/c2 (real); the computed value differs from y by < 4e-16 for
     // |terms| <= 1, so |y - thr| > 1e-15 decides.  y - thr = (A - B - thr*S) / S with
@@ -163,6 +161,20 @@ __device__ __forceinline__ int suppresses_fast(const BoxC& a, const BoxC& b, dou
     if (lhs - rhs > slack && sane) return 1;
     if (rhs - lhs > slack && sane) return 0;
     return -1;
+}
+
+template <int MODE>
+__device__ __forceinline__ int suppresses_fast(const BoxC& a, const BoxC& b, double thr, bool pos_thr) {
+    const double iw = sel_min(a.x1, b.x1) - sel_max(a.x0, b.x0);
+    const double ih = sel_min(a.y1, b.y1) - sel_max(a.y0, b.y0);
+    if (!pos_thr) return -1;
+    if (!(iw > 0.0 && ih > 0.0)) return 0;
+    double ew = 0.0, eh = 0.0;
+    if (MODE == 2) {
+        ew = sel_max(a.x1, b.x1) - sel_min(a.x0, b.x0);
+        eh = sel_max(a.y1, b.y1) - sel_min(a.y0, b.y0);
+    }
+    return decide_overlapping<MODE>(iw, ih, a.area, b.area, ew, eh, a.cx - b.cx, a.cy - b.cy, thr);
 }
 
 template <int MODE>
@@ -613,7 +625,7 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
         // every surviving box behind the block against the block's kept boxes, kJpt boxes per
         // thread in flight (independent fp64 chains; the kept box is one broadcast load for all)
         for (int base = 0; base < n_items; base += kBigThreads * kJpt) {
-            BoxC bj[kJpt];
+            double2 jx[kJpt], jy[kJpt];   // corners only: area / centre are fetched for overlapping pairs
             int jj[kJpt];
             bool alive[kJpt];
             bool any = false;
@@ -623,23 +635,36 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
                 jj[u] = n;
                 if (slot < n_items) jj[u] = (cur_list != nullptr) ? (int)cur_list[slot] : first + slot;
                 alive[u] = jj[u] < n && jj[u] >= first && !rem[jj[u]];
-                if (alive[u]) bj[u] = load_box(jj[u]);
+                if (alive[u]) {
+                    jx[u] = X[jj[u]];
+                    jy[u] = Y[jj[u]];
+                }
                 any |= alive[u];
             }
             if (any) {
                 for (int q = 0; q < nk; ++q) {
-                    BoxC bi;
-                    {
-                        const double2 x = S.kX[q], y = S.kY[q];
-                        bi.x0 = x.x; bi.x1 = x.y; bi.y0 = y.x; bi.y1 = y.y;
-                        bi.area = S.kA[q];
-                        if (M == 2) { const double2 c = S.kC[q]; bi.cx = c.x; bi.cy = c.y; } else { bi.cx = 0.0; bi.cy = 0.0; }
-                    }
+                    const double2 ix = S.kX[q], iy = S.kY[q];
                     any = false;
 #pragma unroll
                     for (int u = 0; u < kJpt; ++u) {
                         if (alive[u]) {
-                            int r = suppresses_fast<M>(bi, bj[u], thr, pos_thr);
+                            const double iw = sel_min(ix.y, jx[u].y) - sel_max(ix.x, jx[u].x);
+                            const double ih = sel_min(iy.y, jy[u].y) - sel_max(iy.x, jy[u].x);
+                            int r = -1;
+                            if (pos_thr) {
+                                r = 0;
+                                if (iw > 0.0 && ih > 0.0) {
+                                    double ew = 0.0, eh = 0.0, dx = 0.0, dy = 0.0;
+                                    if (M == 2) {
+                                        ew = sel_max(ix.y, jx[u].y) - sel_min(ix.x, jx[u].x);
+                                        eh = sel_max(iy.y, jy[u].y) - sel_min(iy.x, jy[u].x);
+                                        const double2 ic = S.kC[q], jc = C[jj[u]];
+                                        dx = ic.x - jc.x;
+                                        dy = ic.y - jc.y;
+                                    }
+                                    r = decide_overlapping<M>(iw, ih, S.kA[q], A[jj[u]], ew, eh, dx, dy, thr);
+                                }
+                            }
                             if (r < 0) r = suppresses_exact<M>(rows, S.krow[q], mem[ord[jj[u]]], thr) ? 1 : 0;
                             if (r) {
                                 alive[u] = false;

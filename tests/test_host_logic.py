@@ -111,6 +111,15 @@ def test_install_rebinds_reference_modules():
     from tf2_yolo_b200.yolov4.losses import wrap_yolo_loss
     assert fake_pkg.wrap_yolo_loss is wrap_yolo_loss and fake_losses.wrap_yolo_loss is wrap_yolo_loss
     assert "utils.tools.decode" in done and "yolov4.wrap_yolo_loss" in done
+    # the in-training metric wrappers follow the same rule (facade global + metrics module)
+    fake_pkg3 = types.ModuleType("yolov3")
+    fake_metrics3 = types.ModuleType("yolov3.metrics")
+    for m in (fake_pkg3, fake_metrics3):
+        m.wrap_obj_acc = m.wrap_mean_iou = m.wrap_class_acc = m.wrap_recall = lambda *a, **k: "reference"
+    done = tf2_yolo_b200.install({"yolov3": fake_pkg3, "yolov3.metrics": fake_metrics3})
+    from tf2_yolo_b200.yolov3.metrics import wrap_recall
+    assert fake_pkg3.wrap_recall is wrap_recall and fake_metrics3.wrap_recall is wrap_recall
+    assert "yolov3.metrics.wrap_obj_acc" in done and "yolov3.wrap_class_acc" in done
 
 
 def test_synth_shapes_and_invariants():

@@ -2,6 +2,7 @@
 behind the reference's own Python API.
 
     tf2_yolo_b200.yolov{1_5,2,3,4}.losses.wrap_yolo_loss / cal_iou
+    tf2_yolo_b200.yolov{1_5,2,3,4}.metrics.wrap_obj_acc / wrap_mean_iou / wrap_class_acc / wrap_recall
     tf2_yolo_b200.utils.tools.decode / nms / cal_iou          (+ decode_batch / nms_batch)
     tf2_yolo_b200.utils.kmeans.kmeans / iou_dist / euclidean_dist
     tf2_yolo_b200.utils.measurement.PRfunc / create_score_mat
@@ -42,6 +43,11 @@ HOT_PATH = {
     ("yolov1_5.losses", "wrap_yolo_loss"): ("tf2_yolo_b200.yolov1_5.losses", "wrap_yolo_loss"),
     ("yolov1_5.losses", "cal_iou"): ("tf2_yolo_b200.yolov1_5.losses", "cal_iou"),
 }
+# in-training metrics: yolov*/metrics/yolo_metrics.py, imported by the facades
+# as `from .metrics import wrap_obj_acc, ...` (yolov4/__init__.py:29-30)
+for _pkg in ("yolov1_5", "yolov2", "yolov3", "yolov4"):
+    for _fn in ("wrap_obj_acc", "wrap_mean_iou", "wrap_class_acc", "wrap_recall"):
+        HOT_PATH[(f"{_pkg}.metrics", _fn)] = (f"tf2_yolo_b200.{_pkg}.metrics", _fn)
 
 
 def install(modules=None):
@@ -53,7 +59,7 @@ def install(modules=None):
     done = []
     for (ref_mod, attr), (our_mod, our_attr) in HOT_PATH.items():
         target = getattr(importlib.import_module(our_mod), our_attr)
-        for name in (ref_mod, ref_mod.split(".")[0] if ref_mod.endswith(".losses") else None):
+        for name in (ref_mod, ref_mod.split(".")[0] if ref_mod.endswith((".losses", ".metrics")) else None):
             m = modules.get(name) if name else None
             if m is not None and hasattr(m, attr) and name != our_mod and not name.startswith("tf2_yolo_b200"):
                 setattr(m, attr, target)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Short driver for ncu captures of the non-loss kernels (k-means assignment, dense-scene NMS,
-PR matching):  python benchmarks/profile_targets.py [kmeans] [nms] [map]
+PR matching):  python benchmarks/profile_targets.py [kmeans] [nms] [iou]
 Each target runs warm-ups and a few launches; use with `ncu -k regex:<kernel> -s <skip> -c <n>`."""
 import os
 import sys
@@ -33,5 +33,13 @@ if "nms" in what:
     for mode in (1, 2):
         for _ in range(2):
             engine.nms_batch(dev, offs, C, 0.45, mode)
+    torch.cuda.synchronize()
+if "iou" in what:
+    rng = np.random.default_rng(5)
+    a = torch.from_numpy(synth.make_dense_candidates(rng, 8192, 1)).cuda()
+    b = torch.from_numpy(synth.make_dense_candidates(rng, 8192, 1)).cuda()
+    for mode in (1, 2):
+        for _ in range(3):
+            engine.pairwise_iou(a, b, mode)       # 67 M pair IoUs per launch, fp64, (n, n) matrix out
     torch.cuda.synchronize()
 print("ok")

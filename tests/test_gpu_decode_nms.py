@@ -231,3 +231,24 @@ def test_decode_scan_sizes():
             ref = ot.decode(yp[i], class_num=C, threshold=thr, version=3).reshape(-1, 7)
             assert np.array_equal(rows_h[offs_h[i]:offs_h[i + 1]], ref), (n_img, S, i)
         assert offs_h[-1] == len(rows_h)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_pairwise_iou_matrix(mode):
+    """(na, nb) IoU / DIoU matrix bit for bit: ragged tile sizes, zero-size and non-finite boxes."""
+    rng = np.random.default_rng(80)
+    a = synth.make_dense_candidates(rng, 131, 1)[:, :5]
+    b = synth.make_dense_candidates(rng, 517, 1)[:, :5]
+    a[3, 2:4] = 0.0
+    b[5] = a[3]                      # identical zero-size boxes: 0/0 in the DIoU term
+    a[7, 0] = np.nan
+    b[9, 3] = np.inf
+    b[11, 1] = -np.inf
+    a[13, 2] = np.inf                # inf - inf inside the overlap
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        ref = ot.pair_iou(a[:, None, :], b[None, :, :], mode=mode)
+    got = engine.pairwise_iou(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), mode).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref, equal_nan=True), np.argwhere(~((got == ref) | (np.isnan(got) & np.isnan(ref))))[:5]
+    one = engine.pairwise_iou(torch.from_numpy(a[:1]).cuda(), torch.from_numpy(b[:1]).cuda(), mode).cpu().numpy()
+    assert np.array_equal(one, ref[:1, :1], equal_nan=True)

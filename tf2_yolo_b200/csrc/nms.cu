@@ -810,17 +810,72 @@ nms_emit_kernel(const double* __restrict__ rows, const long long* __restrict__ r
     }
 }
 
+// (na x nb) IoU / DIoU matrix.  A block owns kPairRows rows x 256 columns: the row boxes are staged
+// in shared memory with their corners precomputed, each thread keeps one column box in registers,
+// so a pair costs the min/max/area arithmetic and the IEEE divisions only - no index division, no
+// reload.  Pairs with a non-finite corner or area take the NaN-propagating reference expression.
+constexpr int kPairRows = 64;
+struct PairRow {
+    double x, y, w, h;         // the original row (exact path)
+    double x0, x1, y0, y1, area;
+    int finite;
+};
+
+__device__ __forceinline__ bool box_finite(const BoxC& c) {
+    const double probe = ((c.x0 + c.x1) + (c.y0 + c.y1)) + c.area;   // inf or NaN anywhere -> not finite
+    return fabs(probe) < 1.7e308;
+}
+
 template <int MODE>
-__global__ void pairwise_iou_kernel(const double* __restrict__ a, long long na, int sa,
-                                    const double* __restrict__ b, long long nb, int sb,
-                                    double* __restrict__ out) {
-    const long long total = na * nb;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const long long ia = i / nb, ib = i - ia * nb;
-        const double* t = a + ia * sa;
-        const double* p = b + ib * sb;
-        out[i] = pair_iou<MODE>(t[0], t[1], t[2], t[3], p[0], p[1], p[2], p[3]);
+__global__ void __launch_bounds__(256)
+pairwise_iou_kernel(const double* __restrict__ a, long long na, int sa, const double* __restrict__ b,
+                    long long nb, int sb, double* __restrict__ out) {
+    __shared__ PairRow s_row[kPairRows];
+    const long long ia0 = (long long)blockIdx.y * kPairRows;
+    const int rows_here = (int)min((long long)kPairRows, na - ia0);
+    if ((int)threadIdx.x < rows_here) {
+        const double* t = a + (ia0 + threadIdx.x) * sa;
+        PairRow r;
+        r.x = t[0]; r.y = t[1]; r.w = t[2]; r.h = t[3];
+        const double hw = r.w / 2.0, hh = r.h / 2.0;
+        BoxC c;
+        c.x0 = r.x - hw; c.x1 = r.x + hw; c.y0 = r.y - hh; c.y1 = r.y + hh; c.area = r.w * r.h; c.cx = r.x; c.cy = r.y;
+        r.x0 = c.x0; r.x1 = c.x1; r.y0 = c.y0; r.y1 = c.y1; r.area = c.area;
+        r.finite = box_finite(c) ? 1 : 0;
+        s_row[threadIdx.x] = r;
+    }
+    __syncthreads();
+    const long long ib = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ib >= nb) return;
+    const double* p = b + ib * sb;
+    const double px = p[0], py = p[1], pw = p[2], ph = p[3];
+    BoxC pc;
+    {
+        const double hw = pw / 2.0, hh = ph / 2.0;
+        pc.x0 = px - hw; pc.x1 = px + hw; pc.y0 = py - hh; pc.y1 = py + hh; pc.area = pw * ph; pc.cx = px; pc.cy = py;
+    }
+    const bool p_finite = box_finite(pc);
+    double* o = out + ia0 * nb + ib;
+    for (int r = 0; r < rows_here; ++r, o += nb) {
+        const PairRow& t = s_row[r];
+        double v;
+        if (p_finite && t.finite) {
+            const double iw = sel_max(sel_min(pc.x1, t.x1) - sel_max(pc.x0, t.x0), 0.0);
+            const double ih = sel_max(sel_min(pc.y1, t.y1) - sel_max(pc.y0, t.y0), 0.0);
+            const double inter = iw * ih;
+            const double uni = pc.area + t.area - inter;
+            v = inter / (uni + kIouEps);
+            if (MODE == 2) {
+                const double ew = sel_max(pc.x1, t.x1) - sel_min(pc.x0, t.x0), eh = sel_max(pc.y1, t.y1) - sel_min(pc.y0, t.y0);
+                const double c2 = ew * ew + eh * eh;
+                const double dx = t.x - px, dy = t.y - py;
+                const double rho2 = dx * dx + dy * dy;
+                v = v - rho2 / c2;
+            }
+        } else {
+            v = pair_iou<MODE>(t.x, t.y, t.w, t.h, px, py, pw, ph);
+        }
+        *o = v;
     }
 }
 
@@ -971,11 +1026,13 @@ extern "C" int yb_pairwise_iou(const double* a, int64_t na, int stride_a, const 
     if (na == 0 || nb == 0) return YB_OK;
     if (a == nullptr || b == nullptr || out == nullptr) return YB_E_NULL;
     const int threads = 256;
-    const int blocks = (int)min((long long)kNumSMs * 8, ((long long)na * nb + threads - 1) / threads);
+    const long long gx = (nb + threads - 1) / threads, gy = (na + kPairRows - 1) / kPairRows;
+    if (gx > 0x7fffffffLL || gy > 65535) return YB_E_SHAPE;   // 4 M rows x 5e11 columns
+    const dim3 grid((unsigned)gx, (unsigned)gy);
     if (iou_mode == 1)
-        pairwise_iou_kernel<1><<<blocks, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
+        pairwise_iou_kernel<1><<<grid, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
     else
-        pairwise_iou_kernel<2><<<blocks, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
+        pairwise_iou_kernel<2><<<grid, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
     return (int)cudaGetLastError();
 }
 

@@ -125,6 +125,13 @@ __global__ void map_segment_sizes_kernel(const long long* __restrict__ seg_off, 
     }
 }
 
+constexpr int kTopCap = 1024;   // truncated segments up to this size are ranked by a warp-wide sort
+
+__device__ __forceinline__ unsigned long long orderable(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // ascending with value
+}
+
 // ---- B: one warp per segment: triples, per-image top-k, score counters ----------
 __global__ void __launch_bounds__(256)
 map_triples_kernel(const double* __restrict__ det, const long long* __restrict__ seg_off,
@@ -135,7 +142,13 @@ map_triples_kernel(const double* __restrict__ det, const long long* __restrict__
                    double* __restrict__ conf_out, long long* __restrict__ gtid_out,
                    unsigned char* __restrict__ flag_out, int* __restrict__ cls_out,
                    long long* __restrict__ class_offsets, unsigned long long* __restrict__ acc /* [3][C] pp,tpp,tp */) {
+    // per-warp sort scratch for the top-k of a truncated segment: kTopCap keys + indices
+    extern __shared__ __align__(16) unsigned char topk_smem[];
     const int lane = threadIdx.x & 31;
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(topk_smem) + (size_t)(threadIdx.x >> 5) * kTopCap;
+    unsigned short* s_idx = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned long long*>(topk_smem) +
+                                                              (size_t)(blockDim.x >> 5) * kTopCap) +
+                            (size_t)(threadIdx.x >> 5) * kTopCap;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long n_seg = n_img * C;
@@ -153,6 +166,54 @@ map_triples_kernel(const double* __restrict__ det, const long long* __restrict__
         // running ground-truth count of this class before this image (measurement.py:256-258)
         const long long gbase = gt_base[c] + (gt_pos_T[tpos] - gt_pos_T[(long long)c * n_img]);
         const bool trunc = max_per_img > 0 && n > max_per_img;
+        const bool sorted = trunc && n <= kTopCap;
+        if (sorted) {
+            // visit order of np.argsort(conf)[::-1][:max_per_img] (measurement.py:285-289): a warp-wide
+            // bitonic sort of (descending confidence, higher index first) in shared memory gives every
+            // detection its rank; the ranks below max_per_img are the output positions
+            int P = 32;
+            while (P < n) P <<= 1;
+            for (int j = lane; j < P; j += 32) {
+                unsigned long long k = ~0ull;   // padding sorts last
+                if (j < n) {
+                    const double* r = det + (d0 + j) * 7;
+                    k = ~orderable(__dmul_rn(r[4], r[6]));   // ascending key == descending confidence
+                }
+                s_key[j] = k;
+                s_idx[j] = (unsigned short)j;
+            }
+            __syncwarp();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int jj = k >> 1; jj > 0; jj >>= 1) {
+                    for (int t = lane; t < P; t += 32) {
+                        const int u = t ^ jj;
+                        if (u > t) {
+                            const unsigned long long ka = s_key[t], kb = s_key[u];
+                            const unsigned short ia = s_idx[t], ib = s_idx[u];
+                            // a before b: smaller key, ties -> higher index first
+                            const bool a_first = ka < kb || (ka == kb && ia > ib);
+                            const bool up = (t & k) == 0;
+                            if (up ? !a_first : a_first) {
+                                s_key[t] = kb; s_key[u] = ka;
+                                s_idx[t] = ib; s_idx[u] = ia;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            // rank -> position lookup by original index (the key array is dead now)
+            unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_key);
+            __syncwarp();
+            unsigned short mine[kTopCap / 32];
+#pragma unroll
+            for (int q = 0; q < kTopCap / 32; ++q) mine[q] = (lane + 32 * q < n) ? s_idx[lane + 32 * q] : (unsigned short)0;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < kTopCap / 32; ++q)
+                if (lane + 32 * q < n) s_rank[mine[q]] = (unsigned short)(lane + 32 * q);
+            __syncwarp();
+        }
         int tpp = 0, tp = 0;
         for (int j0 = 0; j0 < n; j0 += 32) {
             const int j = j0 + lane;
@@ -180,6 +241,9 @@ map_triples_kernel(const double* __restrict__ det, const long long* __restrict__
                 long long dst;
                 if (!trunc) {
                     dst = out0 + j;
+                } else if (sorted) {
+                    const int rank = (int)reinterpret_cast<const unsigned short*>(s_key)[j];
+                    dst = (rank < max_per_img) ? out0 + rank : -1;
                 } else {  // top max_per_img by confidence, in sorted order, ties: higher index first
                     int rank = 0;
                     for (int i = 0; i < n; ++i) {
@@ -197,6 +261,7 @@ map_triples_kernel(const double* __restrict__ det, const long long* __restrict__
                 }
             }
         }
+        __syncwarp();   // the sort scratch is reused by the warp's next segment
         if (lane == 0) {
             atomicAdd(&acc[c], (unsigned long long)n);
             if (n_gt > 0) {
@@ -209,10 +274,6 @@ map_triples_kernel(const double* __restrict__ det, const long long* __restrict__
 
 // ---- C: sort records (class asc, confidence desc, position desc) -----------------------
 // record = two u64 compared lexicographically: A = class<<32 | hi32(~key), B = lo32(~key)<<32 | ~pos
-__device__ __forceinline__ unsigned long long orderable(double v) {
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);  // ascending with value
-}
 __device__ __forceinline__ bool rec_less(const ulonglong2& a, const ulonglong2& b) {
     return a.x < b.x || (a.x == b.x && a.y < b.y);
 }
@@ -356,7 +417,9 @@ extern "C" int yb_map_accumulate(const double* det_rows, const int64_t* det_seg_
     rc = exclusive_scan_u32(gt_T, n, gt_pos_T, scan_ws, stream);
     if (rc != 0) return rc;
     const int wblocks = (int)min((long long)kNumSMs * 8, (n * 32 + threads - 1) / threads);
-    map_triples_kernel<<<wblocks, threads, 0, stream>>>(
+    const size_t topk_smem = (size_t)(threads / 32) * kTopCap * (sizeof(unsigned long long) + sizeof(unsigned short));
+    YB_CUDA_TRY(cudaFuncSetAttribute(map_triples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    map_triples_kernel<<<wblocks, threads, topk_smem, stream>>>(
         det_rows, reinterpret_cast<const long long*>(det_seg_offsets), best_iou, best_gt, gt_class_counts, n_img,
         class_num, iou_threshold, max_per_img, reinterpret_cast<const long long*>(gt_base), out_pos_T, gt_pos_T,
         conf, reinterpret_cast<long long*>(gt_id), flag, cls, reinterpret_cast<long long*>(class_offsets),

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-level measurements of the other BASELINE.json configs (not the driver's bench contract):
 
-    python benchmarks/bench_configs.py [v2 v3 v4 nms kmeans map] [--json out.json]
+    python benchmarks/bench_configs.py [v2 v3 v4 nms kmeans map cpu] [--json out.json]
 
 CUDA-event timings after warm-up, inputs resident in HBM; every number is printed with the
 algorithmic bytes / work it is measured against.
@@ -145,6 +145,46 @@ def map_bench(out, n_img=512):
     print("prfunc", json.dumps(out["prfunc_v4_608"]))
 
 
+def cpu_baselines(out):
+    """The CPU side of BASELINE.md section 3 for configs 4 and 5: the oracle port of the reference's
+    NumPy code (effectively one core: Python loops around NumPy) on bounded samples, with the law
+    used to extrapolate stated next to each number.  Test infrastructure used as a timed baseline
+    only (like bench.py's cpu_baseline)."""
+    from oracle import kmeans as okm
+    from oracle import measurement as om
+    from oracle import tools as ot
+    cores = os.cpu_count()
+    rng = np.random.default_rng(4)
+    rows = synth.make_dense_candidates(rng, 100_000, 80)
+    for mode in (1, 2):
+        t0 = time.perf_counter()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ot.nms(rows, 80, 0.45, mode)
+        dt = time.perf_counter() - t0
+        out[f"cpu_nms_dense_mode{mode}"] = {"images": 1, "seconds": dt, "images_per_s": 1 / dt, "cores_used": 1,
+                                            "host_cores": cores, "law": "linear in images"}
+        print(f"cpu_nms_dense_mode{mode}", json.dumps(out[f"cpu_nms_dense_mode{mode}"]))
+    n = 5_000_000
+    data = synth.make_kmeans_boxes(rng, n, 9)
+    centers = np.sort(rng.uniform(0.02, 0.8, (9, 2)), axis=0)
+    t0 = time.perf_counter()
+    okm.lloyd_step(data, centers, okm.iou_dist, data.min(), data.max())
+    dt = time.perf_counter() - t0
+    out["cpu_kmeans"] = {"boxes": n, "seconds_per_iteration": dt, "extrapolated_ms_per_iteration_50M": dt * 10 * 1e3,
+                         "cores_used": 1, "host_cores": cores, "law": "linear in boxes (x10 for 50 M)"}
+    print("cpu_kmeans", json.dumps(out["cpu_kmeans"]))
+    n_img = 4
+    cfg = synth.make_config("v4-608", batch=n_img, seed=5)
+    names = [str(i) for i in range(80)]
+    t0 = time.perf_counter()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        om.PRfunc(cfg["y_trues"][-1], *cfg["y_preds"], class_names=names, conf_threshold=0.05, version=4)
+    dt = time.perf_counter() - t0
+    out["cpu_prfunc"] = {"images": n_img, "seconds": dt, "images_per_s": n_img / dt, "cores_used": 1,
+                         "host_cores": cores, "law": "phase 1 (decode + NMS + match) linear in images"}
+    print("cpu_prfunc", json.dumps(out["cpu_prfunc"]))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", nargs="*", default=["v2", "v3", "v4", "nms", "kmeans", "map"])
@@ -163,5 +203,7 @@ if __name__ == "__main__":
         kmeans_bench(out)
     if "map" in a.what:
         map_bench(out)
+    if "cpu" in a.what:
+        cpu_baselines(out)
     if a.json:
         json.dump(out, open(a.json, "w"), indent=1)

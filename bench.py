@@ -34,6 +34,11 @@ sys.path.insert(0, ROOT)
 METRIC = "images/sec YOLOv4-608 loss+grad+decode+NMS"
 UNIT = "images/s"
 CONFIG_NAME = "v4-608"
+IMG_SIZE = (608, 608)
+MIN_TIMED_S = 0.5
+# both arms print this string (the driver compares the arms' configs)
+WORKLOAD = ("YOLOv4-608 (BASELINE configs[2]): 3 scales (19/38/76) x 3 anchors, 80 classes, batch 128 per GPU; "
+            "CIoU loss fwd+grad + decode(thr 0.5) + per-class DIoU-NMS(thr 0.45)")
 CONF_THR, NMS_THR, NMS_MODE = 0.5, 0.45, 2
 ROW_CAPACITY_PER_IMG = 4096
 # my kernels per step: fused loss + decode count 1 | decode: look-back scan, emit | nms: classify,
@@ -193,10 +198,9 @@ def run_reference(args):
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "YOLOv4-608, 3 scales x 3 anchors, 80 classes: CIoU loss fwd+grad + decode(0.5) + "
-                               "DIoU-NMS(0.45); CPU arm processes a bounded sample per step",
-                   "images_per_step": per_step},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "images_per_step": per_step,
+                   "sample": "the CPU arm processes a bounded sample of the workload per step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -205,11 +209,30 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # CUDA arm
 # ---------------------------------------------------------------------------
+def h2d_ceiling(host_tensors, dev_tensors, barrier, reps=4):
+    """Plain pinned cudaMemcpyAsync of the step's head outputs, nothing else on the GPU, every rank
+    at once: the fabric's ceiling for the e2e step (GB/s per GPU, slowest rank decides)."""
+    import torch
+    nbytes = sum(t.numel() * t.element_size() for t in host_tensors)
+    for d, h in zip(dev_tensors, host_tensors):
+        d.copy_(h, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for d, h in zip(dev_tensors, host_tensors):
+            d.copy_(h, non_blocking=True)
+    e1.record()
+    barrier()
+    return nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from tf2_yolo_b200 import engine, synth
     from tf2_yolo_b200.grid_loss import fused_losses
+    from tf2_yolo_b200.pipeline import HostBatchStep
     from tf2_yolo_b200.yolov4.losses import wrap_yolo_loss
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -222,18 +245,28 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    batch = args.batch
+    strong = args.scaling == "strong"
+    if strong and args.batch % world:
+        raise SystemExit("--scaling strong needs a batch divisible by the number of GPUs")
+    batch = args.batch // world if strong else args.batch     # images on this GPU
+    global_batch = batch * world
     cfg = synth.make_config(CONFIG_NAME, batch=batch, seed=2, rank=rank)
     B, C = cfg["bbox_num"], cfg["class_num"]
     fns = [wrap_yolo_loss((S, S), B, C, anchors=cfg["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1],
                           wh_reg_weight=0.01, ignore_thresh=0.6)
            for si, S in enumerate(cfg["grids"])]
-    global_batch = batch * world
     params = [f.params for f in fns]
-    host_t = [torch.from_numpy(a).pin_memory() for a in cfg["y_trues"]]
+    # the labels as the reference's reader holds them: box lists in pixels of the 608x608 image
+    boxes_np, offs_np = synth.boxes_from_labels(cfg["y_trues"][-1], IMG_SIZE)
+    host_boxes = torch.from_numpy(boxes_np).pin_memory()
+    host_offs = torch.from_numpy(offs_np).pin_memory()
+    max_per_img = int(np.diff(offs_np).max())
     host_p = [torch.from_numpy(a).pin_memory() for a in cfg["y_preds"]]
-    dev_t = [a.to(dev) for a in host_t]
     dev_p = [a.to(dev) for a in host_p]
+    # device-resident labels = the same box lists through yb_encode_labels (coarse grid first)
+    dev_t, n_bad = engine.encode_labels(host_boxes.to(dev), host_offs.to(dev), IMG_SIZE, (cfg["grids"][-1],) * 2, C,
+                                        n_levels=len(cfg["grids"]), max_boxes_per_img=max_per_img)
+    assert int(n_bad.item()) == 0
     dpreds = [torch.empty_like(a) for a in dev_p]
     cap = ROW_CAPACITY_PER_IMG * batch
     rows = torch.empty((cap, 7), dtype=torch.float64, device=dev)
@@ -268,6 +301,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def agree(x, op):   # one number every rank uses
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
     # ---- device-resident timing ---------------------------------------------------
     for _ in range(args.warmup):
         out = step(dev_t, dev_p)
@@ -283,90 +322,112 @@ def run_ours(args):
         clocks.wait_first_sample(lambda: (fused_losses(fns, dev_t, dev_p, global_batch=global_batch, dpreds=dpreds),
                                           torch.cuda.synchronize()))
     barrier()
+    # the timed region: rounds of exactly `steps` steps, repeated until >= MIN_TIMED_S have been
+    # measured; ms_per_step is the MEDIAN round (every rank runs the same number of rounds)
+    round_ms = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        out = step(dev_t, dev_p, record=True)
-    ev1.record()
-    barrier()
+    n_rounds = 1
+    while len(round_ms) < n_rounds:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out = step(dev_t, dev_p, record=True)
+        ev1.record()
+        barrier()
+        round_ms.append(agree(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None))
+        if len(round_ms) == 1:
+            n_rounds = int(min(200, max(1, np.ceil(MIN_TIMED_S * 1e3 / max(round_ms[0], 1e-3)))))
     t_end = time.perf_counter()
-    ms = ev0.elapsed_time(ev1) / args.steps
-    loss_ms = float(np.mean([a.elapsed_time(b) for a, b in loss_ev]))
-    clock_info = clocks.stop(t_begin, t_end) if rank == 0 else None   # samples inside the timed region
+    ms = float(np.median(round_ms)) / args.steps
+    loss_ms = float(np.median([a.elapsed_time(b) for a, b in loss_ev]))
     loss_vals = out[0].cpu().numpy().tolist()
 
     # ---- end to end through the host-buffer API -----------------------------------
-    h2d = sum(a.numel() * 4 for a in host_t + host_p)
-    stage_t = [torch.empty_like(a, device=dev) for a in host_t]
-    stage_p = [torch.empty_like(a, device=dev) for a in host_p]
-    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
-    offs_host = torch.empty(batch + 1, dtype=torch.int64).pin_memory()
-    rows_host = torch.empty((cap, 7), dtype=torch.float64).pin_memory()
-    d2h = [0]
-
-    def e2e_step():
-        for s, h in zip(stage_t + stage_p, host_t + host_p):
-            s.copy_(h, non_blocking=True)
-        loss, offs, res = step(stage_t, stage_p)
-        loss_host.copy_(loss, non_blocking=True)
-        offs_host.copy_(res["out_offsets"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()       # the row count sizes the result read
-        n = int(offs_host[-1])
-        rows_host[:n].copy_(res["out_rows"][:n], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        d2h[0] = 12 + 8 * (batch + 1) + 56 * n
-
+    pipe = HostBatchStep(fns, IMG_SIZE, batch, CONF_THR, NMS_THR, NMS_MODE, n_chunks=args.chunks,
+                         rows_per_img=ROW_CAPACITY_PER_IMG, max_boxes_per_img=max_per_img,
+                         max_boxes=boxes_np.shape[0], global_batch=global_batch)
+    h2d = sum(a.numel() * 4 for a in host_p) + boxes_np.nbytes + offs_np.nbytes
+    res = None
     for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
-    barrier()
-    e2e_steps = max(3, min(args.steps, 10))
-    ev0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    ev1.record()
-    barrier()
-    e2e_ms = ev0.elapsed_time(ev1) / e2e_steps
-
-    t = torch.tensor([ms, loss_ms, e2e_ms], dtype=torch.float64, device=dev)
+        res = pipe.run(host_p, host_boxes, host_offs)
+    # untimed check: the pipelined host-buffer step returns what the device-resident step computes
+    loss_e2e = torch.tensor(res["loss"], device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, loss_ms, e2e_ms = (float(x) for x in t.cpu())
+        dist.all_reduce(loss_e2e)
+    if not np.allclose(loss_e2e.cpu().numpy(), np.asarray(loss_vals), rtol=2e-6):
+        raise SystemExit(f"e2e loss {loss_e2e.tolist()} != device-resident loss {loss_vals}")
+    if res["n_rows"] != kept_rows:
+        raise SystemExit(f"e2e survivors {res['n_rows']} != device-resident survivors {kept_rows}")
+    kept_ref = out[2]["out_rows"][:kept_rows].cpu().numpy()
+    if not np.array_equal(np.concatenate([r for r, _ in res["rows"]], axis=0), kept_ref):
+        raise SystemExit("e2e survivors differ from the device-resident step's")
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_round_ms, e2e_wall_ms = [], []
+    n_rounds = 1
+    while len(e2e_round_ms) < n_rounds:
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(e2e_steps):
+            res = pipe.run(host_p, host_boxes, host_offs)
+        ev1.record(pipe.compute_stream)
+        barrier()
+        e2e_wall_ms.append((time.perf_counter() - t0) * 1e3)
+        e2e_round_ms.append(agree(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None))
+        if len(e2e_round_ms) == 1:
+            n_rounds = int(min(20, max(1, np.ceil(MIN_TIMED_S * 1e3 / max(e2e_round_ms[0], 1e-3)))))
+    t_end = time.perf_counter()
+    e2e_ms = float(np.median(e2e_round_ms)) / e2e_steps
+    clock_info = clocks.stop(t_begin, t_end) if rank == 0 else None   # samples inside both timed regions
+    ceiling = agree(h2d_ceiling(host_p, pipe.y_pred, barrier), dist.ReduceOp.MIN if world > 1 else None)
 
     if rank == 0:
         algo = loss_algorithmic_bytes(cfg, batch)
         peak, peak_src = peak_hbm()
         achieved = algo / (loss_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": batch * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": global_batch / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"YOLOv4-608 (BASELINE configs[2]): 3 scales (19/38/76) x 3 anchors, 80 classes, "
-                            f"batch {batch} per GPU; fused CIoU loss fwd+grad + decode(thr {CONF_THR}) + "
-                            f"per-class DIoU-NMS(thr {NMS_THR})",
+                "workload": WORKLOAD,
+                "per_gpu_batch": batch, "global_batch": global_batch,
                 "fusion": "separate loss and decode launches" if args.unfused else
                           "loss fwd+grad and the decode counting pass share one read of y_pred (yb_loss_decode_fused); "
                           "roofline counts only the loss's algorithmic bytes",
-                "global_batch": batch * world, "per_gpu_batch": batch,
-                "l2_policy": f"inputs larger than L2: {h2d / 1e6:.0f} MB read + {sum(d.numel() * 4 for d in dpreds) / 1e6:.0f} MB "
-                             "written per step vs 126 MB L2",
+                "timing": f"median of {len(round_ms)} rounds of {args.steps} steps (CUDA events, max over ranks, "
+                          f">= {MIN_TIMED_S} s measured)",
+                "l2_policy": f"inputs larger than L2: {sum(a.numel() * 4 for a in dev_p + dev_t) / 1e6:.0f} MB read + "
+                             f"{sum(d.numel() * 4 for d in dpreds) / 1e6:.0f} MB written per step vs 126 MB L2",
                 "decode_rows_per_image": total_rows / batch, "nms_kept_per_image": kept_rows / batch,
                 "loss_per_scale": loss_vals, "sharding": "batch split across ranks; all-reduce of 3 loss scalars",
                 "precision_note": "loss/decode fp32 (objectness, class, box terms of responsible boxes in fp64), "
                                   "NMS fp64 bit-exact",
             },
             "clocks": clock_info,
-            "e2e": {"value": batch * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h[0], "ms_per_step": e2e_ms,
-                    "note": "pinned H2D of labels+heads, loss scalars + NMS survivors D2H; gradient stays on device"},
-            "gpu_launches": (LAUNCHES_PER_STEP + (1 if args.unfused else 0)) * args.steps,
+            "e2e": {"value": global_batch / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": pipe.d2h_bytes(res["n_rows"]), "ms_per_step": e2e_ms,
+                    "wall_ms_per_step": float(np.median(e2e_wall_ms)) / e2e_steps,
+                    "h2d_gbs": h2d / (e2e_ms * 1e-3) / 1e9, "h2d_ceiling_gbs": ceiling,
+                    "frac_of_h2d_ceiling": (h2d / (e2e_ms * 1e-3) / 1e9) / ceiling,
+                    "chunks": len(pipe.chunks), "rounds": len(e2e_round_ms), "steps_per_round": e2e_steps,
+                    "note": "HostBatchStep: pinned head outputs + box lists in (labels encoded on the device), "
+                            "loss scalars + NMS survivors written to mapped host memory; H2D of chunk k+1 under the "
+                            "kernels of chunk k, one host sync per step; gradient stays on the device. "
+                            "h2d_ceiling_gbs = the same head outputs copied with plain pinned cudaMemcpyAsync, "
+                            "all ranks at once, nothing else running"},
+            "gpu_launches": (LAUNCHES_PER_STEP + (1 if args.unfused else 0)) * args.steps * len(round_ms)
+                            + pipe.launches_per_step * e2e_steps * len(e2e_round_ms),
+            "gpu_launches_per_step": LAUNCHES_PER_STEP + (1 if args.unfused else 0),
             "roofline": {"bound": "hbm",
                          "kernel": "loss_fwd_bwd_kernel<4,false,%s>" % ("false" if args.unfused else "true"),
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(),
+                         "traffic_source": "ncu --set full capture of this kernel (profiles/loss_kernel_traffic.json)",
                          "algorithmic_bytes_per_launch": algo, "ms_per_launch": loss_ms, "peak_source": peak_src,
-                         "kernel_share_of_step": loss_ms / ms},
+                         "kernel_share_of_step": loss_ms / ms,
+                         "step_frac": algo / (ms * 1e-3) / 1e9 / peak},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
@@ -410,6 +471,9 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="separate loss and decode launches (y_pred read twice)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images per GPU (default); strong: --batch images in total, split over the GPUs")
+    ap.add_argument("--chunks", type=int, default=8, help="image chunks of the pipelined end-to-end step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

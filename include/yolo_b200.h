@@ -28,6 +28,7 @@ typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
 #define YB_MAX_SCALES 4  /* FPN outputs per fused loss launch */
 #define YB_LOSS_TERMS 8  /* doubles per scale in terms_out */
 #define YB_LOSS_METRICS 10 /* doubles per scale in metrics_out */
+#define YB_ENCODE_MAX_BOXES 1024 /* boxes per image yb_encode_labels stages in shared memory */
 
 enum {
     YB_OK = 0,
@@ -41,6 +42,12 @@ enum {
 
 int yb_abi_version(void);
 const char* yb_status_string(int status);
+
+/* Device-side alias of a page-locked HOST allocation.  Output pointers of the entry points below
+ * may be such aliases where noted ("may be mapped host memory"): the kernel then writes its
+ * result straight into host memory and the caller needs no sized D2H copy (and no round trip to
+ * learn the size).  Returns the cudaError_t of cudaHostGetDevicePointer for pageable memory. */
+int yb_mapped_host_pointer(void* host_ptr_host, void** device_ptr_host);
 
 /* ------------------------------------------------------------------------
  * Grid losses: fused forward + gradient.
@@ -180,6 +187,7 @@ int yb_decode_finish(const void* const* preds_host, int64_t n_img, const yb_deco
  * n_img*class_num+1 int64) their per-(image, class) extents.  n_rows is the
  * capacity of rows/keep; the true count is read on the device from
  * row_offsets[n_img], so a decode -> NMS chain needs no host round trip.
+ * out_rows / out_offsets / out_seg_offsets are only ever written: they may be mapped host memory.
  * Ties: suppression on IoU >= threshold; equal confidences are visited
  * higher-original-index first.
  * ---------------------------------------------------------------------- */
@@ -287,6 +295,29 @@ int yb_pr_curve(const double* conf, const int32_t* cls, const int64_t* gt_id, co
  * yb_column_sums: per-column sums of a (rows, cols) matrix in fp64 - the data-sized part of
  * utils/tools.py:592-627 (get_class_weight).
  * ---------------------------------------------------------------------- */
+/* yb_encode_labels: box lists -> label grids, the `_encode_to_array` closure of
+ * YoloDataSequence.__getitem__ (utils/tools.py:179-209) followed, for n_levels > 1, by
+ * down2xlabel (utils/tools.py:342-367) once per extra level as _Yolov4DataSequence.__getitem__
+ * does (yolov4/__init__.py:47-53) - all levels in ONE launch, nothing dense is read.
+ * boxes: (n_boxes, 5) float64 [x1, y1, x2, y2, class index] in pixels of the resized image
+ * (what the closure reads from imgaug's BoundingBox and its `labels` list); box_offsets
+ * (n_img+1 int64, device): image i owns boxes [box_offsets[i], box_offsets[i+1]), applied in
+ * list order: a later box overwrites x, y, w, h of its cell, the class bits of earlier boxes of
+ * the cell stay set.  img_h, img_w = img.shape[0], img.shape[1]; grid_h x grid_w = the FINEST
+ * grid.  out_levels_host[l], l = 0..n_levels-1, coarse grid first (the reference's label_list
+ * order): (n_img, grid_h >> (n_levels-1-l), grid_w >> (n_levels-1-l), 5+class_num), float64
+ * (out_f64 = 1, what the reader returns) or float32 (the cast Keras applies before the loss);
+ * fully written (zero-filled) by the call.  Arithmetic is float64 in the reference's order with
+ * Python's floored // and %.  A centre at or beyond the last column / row is skipped (:199),
+ * negative cell indices wrap like NumPy's.  Inputs on which the reference raises (non-finite
+ * corners, class outside [0, class_num), cell index below -grid, more than max_boxes_per_img
+ * boxes in an image) are skipped and counted in *n_bad (device, ADDED to; may be NULL).
+ * max_boxes_per_img <= YB_ENCODE_MAX_BOXES bounds the per-image box count (shared-memory size). */
+int yb_encode_labels(const double* boxes, const int64_t* box_offsets, int64_t n_img,
+                     int max_boxes_per_img, double img_h, double img_w, int grid_h, int grid_w,
+                     int class_num, int n_levels, void* const* out_levels_host, int out_f64,
+                     unsigned long long* n_bad, yb_stream_t stream);
+
 int yb_down2x_labels(const void* labels, int is_f64, int64_t n_img, int grid_h, int grid_w,
                      int channels, double* out, yb_stream_t stream);
 

@@ -241,11 +241,67 @@ def gen_labels():
     print("labels.npz ok")
 
 
+def encode_case(rng, n_img, size, grid, C, mean_boxes, degenerate=True):
+    """Box lists in pixels of a (H, W) image: random boxes, several per cell, some centred outside."""
+    H, W = size
+    counts = rng.poisson(mean_boxes, n_img)
+    counts[rng.integers(0, n_img)] = 0                     # an image without boxes
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    nb = int(off[-1])
+    cx, cy = rng.uniform(0, W, nb), rng.uniform(0, H, nb)
+    w, h = rng.uniform(1, 0.5 * W, nb), rng.uniform(1, 0.5 * H, nb)
+    boxes = np.column_stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2,
+                             rng.integers(0, C, nb).astype(np.float64)])
+    if degenerate and nb >= 12:
+        gh, gw = grid
+        boxes[1, :4] = boxes[0, :4] + [0.25, 0.25, 0.5, 0.5]          # same cell, later box wins, both classes stay
+        boxes[1, 4] = (boxes[0, 4] + 1) % C
+        boxes[2, :4] = [W + 3.0, 10.0, W + 9.0, 20.0]                # centre beyond the last column: skipped
+        boxes[3, :4] = [10.0, H, 20.0, H + 2.0]                      # centre beyond the last row: skipped
+        boxes[4, :4] = [-9.0, 5.0, -1.0, 15.0]                       # negative centre: column index wraps
+        boxes[5, :4] = [W / gw * 3, H / gh * 2, W / gw * 3, H / gh * 2]   # zero size, exactly on a cell corner
+        boxes[6, :4] = [30.0, 40.0, 20.0, 60.0]                      # x2 < x1: negative width
+        boxes[7, :4] = [W / gw * 2 - 4.0, 8.0, W / gw * 2 + 4.0, 12.0]    # centre exactly on a column boundary
+        boxes[8, :4] = boxes[5, :4] + [W / gw, 0.0, W / gw, 0.0]     # zero-area neighbour in the same 2x2 block
+    return boxes, off
+
+
+def gen_encode():
+    """Label-grid encoding fixtures: the UNMODIFIED YoloDataSequence.__getitem__ (utils/tools.py:176-339)
+    reading labelme files, then down2xlabel (utils/tools.py:342-367) per extra level."""
+    tools, _, _ = refexec.load_numpy_half()
+    rng = np.random.default_rng(707)
+    pack = {}
+    names = []
+    for name, n_img, size, grid, C, mean, levels in (
+            ("small", 6, (100, 90), (8, 12), 5, 9.0, 3),
+            ("dense", 3, (64, 64), (8, 8), 3, 60.0, 4),
+            ("v4", 2, (608, 608), (76, 76), 80, 12.0, 3),
+            ("v2", 3, (416, 416), (13, 13), 20, 5.0, 1)):
+        boxes, off = encode_case(rng, n_img, size, grid, C, mean)
+        lab = refexec.reference_encode_labels(boxes, off, size, grid, C)
+        names.append(name)
+        pack[name + "/boxes"], pack[name + "/offsets"] = boxes, off
+        pack[name + "/meta"] = np.array(json.dumps(dict(size=size, grid=grid, C=C, levels=levels)))
+        pack[name + "/level0"] = lab
+        for l in range(1, levels):
+            lab = tools.down2xlabel(lab)
+            pack[name + f"/level{l}"] = lab
+    pack["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "encode.npz"), **pack)
+    print("encode.npz:", names)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_losses()
     gen_decode_nms()
     gen_kmeans()
     gen_map()
     gen_metrics()
     gen_labels()
+    gen_encode()

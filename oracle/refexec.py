@@ -247,3 +247,53 @@ def reference_metrics(version, y_true, y_pred, grid_shape, bbox_num, class_num, 
            mod.wrap_class_acc(grid_shape, class_num) if version == 1 else mod.wrap_class_acc(grid_shape, bbox_num, class_num),
            mod.wrap_recall(grid_shape, bbox_num, class_num, iou_threshold=iou_threshold)]
     return np.array([float(torch.as_tensor(f(yt, yp), dtype=dtype).mean()) for f in fns])
+
+
+class _RefBox:
+    """Stand-in for imgaug's BoundingBox: the reader only stores the four corners and
+    ``_encode_to_array`` (utils/tools.py:190-194) only reads them back."""
+
+    def __init__(self, x1, y1, x2, y2):
+        self.x1, self.y1, self.x2, self.y2 = x1, y1, x2, y2
+
+
+class _RefBoxes:
+    def __init__(self, bounding_boxes, shape=None):
+        self.bounding_boxes = bounding_boxes
+        self.shape = shape
+
+
+def reference_encode_labels(boxes, box_offsets, img_size, grid_shape, class_num):
+    """Label grid produced by the UNMODIFIED ``YoloDataSequence.__getitem__`` (utils/tools.py:176-339)
+    reading labelme files written to a temporary directory: blank PNGs of exactly ``img_size`` (so the
+    reader's zoom ratio is 1.0 and the corners reach ``_encode_to_array`` unchanged) and one JSON per
+    image whose rectangles are ``boxes`` ([x1, y1, x2, y2, class index], pixel units)."""
+    import json
+    import tempfile
+
+    from PIL import Image
+
+    tools, _, _ = load_numpy_half()
+    tools.BoundingBox, tools.BoundingBoxesOnImage = _RefBox, _RefBoxes
+    boxes = np.asarray(boxes, dtype=np.float64).reshape(-1, 5)
+    off = np.asarray(box_offsets, dtype=np.int64)
+    n_img = len(off) - 1
+    names = [f"c{k}" for k in range(class_num)]
+    with tempfile.TemporaryDirectory() as tmp:
+        img_dir, lab_dir = os.path.join(tmp, "img"), os.path.join(tmp, "lab")
+        os.makedirs(img_dir)
+        os.makedirs(lab_dir)
+        blank = Image.fromarray(np.zeros((int(img_size[0]), int(img_size[1]), 3), dtype=np.uint8))
+        for i in range(n_img):
+            blank.save(os.path.join(img_dir, f"im{i:05d}.png"))
+            shapes = [dict(label=names[int(b[4])], shape_type="rectangle",
+                           points=[[float(b[0]), float(b[1])], [float(b[2]), float(b[3])]])
+                      for b in boxes[off[i]:off[i + 1]]]
+            with open(os.path.join(lab_dir, f"im{i:05d}.json"), "w", encoding="big5") as f:
+                json.dump(dict(shapes=shapes), f)
+        seq = tools.YoloDataSequence(img_path=img_dir, label_path=lab_dir, reader="PIL", batch_size=max(n_img, 1),
+                                     label_format="labelme", size=(int(img_size[0]), int(img_size[1])),
+                                     rescale=None, grid_shape=tuple(grid_shape), class_names=names,
+                                     shuffle=False, thread_num=1)
+        _, label_data = seq[0]
+    return label_data

@@ -143,3 +143,72 @@ def soft_nms(rows, class_num=1, nms_threshold=0.45, conf_threshold=0.5, sigma=0.
                     dead[j] = True
         parts.append(sub[~dead])
     return np.vstack(parts) if parts else rows[:0]
+
+
+def encode_labels(boxes, box_offsets, img_size, grid_shape, class_num):
+    """Box lists -> label grid (n_img, gh, gw, 5+C) float64: the ``_encode_to_array`` closure of
+    ``YoloDataSequence.__getitem__`` (utils/tools.py:179-209), boxes given as pixel corners
+    ``[x1, y1, x2, y2, class index]`` (what the closure reads from imgaug's BoundingBox and the
+    ``labels`` list), ``img_size = img.shape[:2]`` of the resized image.
+
+    Kept from the reference: Python-float arithmetic (``//`` and ``%`` are Python's floored
+    division), boxes applied in list order so a later box overwrites x, y, w, h of a cell while
+    the class bits of earlier boxes in that cell stay set, a centre at or beyond the last
+    column / row is skipped (:199), negative cell indices wrap like NumPy indexing."""
+    boxes = np.asarray(boxes, dtype=np.float64).reshape(-1, 5)
+    off = np.asarray(box_offsets, dtype=np.int64)
+    gh, gw = int(grid_shape[0]), int(grid_shape[1])
+    img_height, img_width = int(img_size[0]), int(img_size[1])
+    label_data = np.zeros((len(off) - 1, gh, gw, 5 + class_num))
+    grid_height = img_height / gh
+    grid_width = img_width / gw
+    for pos in range(len(off) - 1):
+        for b in range(off[pos], off[pos + 1]):
+            x1, y1, x2, y2 = (float(v) for v in boxes[b, :4])
+            label = int(boxes[b, 4])
+            box_x = x1 + (x2 - x1) / 2
+            box_y = y1 + (y2 - y1) / 2
+            box_w = x2 - x1
+            box_h = y2 - y1
+            x_i = int(box_x // grid_width)
+            y_i = int(box_y // grid_height)
+            if x_i < gw and y_i < gh:
+                label_data[pos, y_i, x_i, 0] = box_x % grid_width / grid_width
+                label_data[pos, y_i, x_i, 1] = box_y % grid_height / grid_height
+                label_data[pos, y_i, x_i, 2] = box_w / img_width
+                label_data[pos, y_i, x_i, 3] = box_h / img_height
+                label_data[pos, y_i, x_i, 4] = 1
+                label_data[pos, y_i, x_i, 5 + label] = 1
+    return label_data
+
+
+def down2xlabel(label_data):
+    """2x label downsample, utils/tools.py:342-367: a 2x2 block whose largest obj flag equals 1
+    keeps its largest-area entry (np.argmax: first maximum in row-major order, areas in the input
+    dtype) with the xy offset re-expressed in the coarser cell; every other block stays zero.
+    Output float64."""
+    lab = np.asarray(label_data)
+    n, gh, gw, ch = lab.shape
+    if gh % 2 or gw % 2:
+        raise IndexError("down2xlabel: odd grid (the reference indexes out of bounds)")
+    blk = lab.reshape(n, gh // 2, 2, gw // 2, 2, ch).transpose(0, 1, 3, 2, 4, 5).reshape(n, gh // 2, gw // 2, 4, ch)
+    has = blk[..., 4].max(axis=-1) == 1
+    pick = (blk[..., 2] * blk[..., 3]).argmax(axis=-1)
+    sel = np.take_along_axis(blk, pick[..., None, None], axis=3)[..., 0, :].astype(np.float64)
+    out = np.zeros((n, gh // 2, gw // 2, ch))
+    sel[..., 0] = (sel[..., 0] + pick % 2) / 2
+    sel[..., 1] = (sel[..., 1] + pick // 2) / 2
+    out[has] = sel[has]
+    return out
+
+
+def encode_label_pyramid(boxes, box_offsets, img_size, grid_shape, class_num, n_levels=1, dtype=np.float64):
+    """encode_labels on the finest grid followed by (n_levels-1) down2xlabel passes, returned
+    coarse grid first like ``_Yolov4DataSequence.__getitem__`` (yolov4/__init__.py:47-53);
+    ``dtype=np.float32`` adds the cast Keras applies to y_true before the loss sees it."""
+    lab = encode_labels(boxes, box_offsets, img_size, grid_shape, class_num)
+    out = [lab]
+    for _ in range(n_levels - 1):
+        lab = down2xlabel(lab)
+        out.insert(0, lab)
+    return [o.astype(dtype) for o in out]

@@ -14,6 +14,7 @@ YB_MAX_BOXES = 16
 YB_MAX_SCALES = 4
 YB_LOSS_TERMS = 8
 YB_LOSS_METRICS = 10
+YB_ENCODE_MAX_BOXES = 1024
 YB_DIST_IOU, YB_DIST_EUCLID = 0, 1
 
 
@@ -71,6 +72,7 @@ _vp, _i64, _i32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_dou
 SIGNATURES = {
     "yb_abi_version": (C.c_int, []),
     "yb_status_string": (C.c_char_p, [C.c_int]),
+    "yb_mapped_host_pointer": (C.c_int, [_vp, C.POINTER(_vp)]),
     "yb_loss_workspace_bytes": (_sz, [_i32]),
     "yb_loss_fwd_bwd": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _vp, _sz, _vp]),
     "yb_loss_fwd_bwd_metrics": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _vp, _dbl, _vp, _sz, _vp]),
@@ -92,6 +94,8 @@ SIGNATURES = {
     "yb_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "yb_kmeans_assign": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_minmax_f64": (C.c_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
+    "yb_encode_labels": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _dbl, _i32, _i32, _i32, _i32, C.POINTER(_vp), _i32,
+                                   _vp, _vp]),
     "yb_down2x_labels": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _vp]),
     "yb_column_sums_workspace_bytes": (_sz, [_i32]),
     "yb_column_sums": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _sz, _vp]),

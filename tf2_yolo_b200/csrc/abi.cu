@@ -17,3 +17,11 @@ extern "C" const char* yb_status_string(int status) {
     if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
     return "unknown yolo_b200 status";
 }
+
+// Device-side alias of a page-locked HOST allocation (cudaHostAlloc / cudaHostRegister), so that a
+// kernel of this library can write its (small) result straight into host memory instead of the
+// caller issuing a sized D2H copy after a round trip for the count.
+extern "C" int yb_mapped_host_pointer(void* host_ptr, void** device_ptr) {
+    if (host_ptr == nullptr || device_ptr == nullptr) return YB_E_NULL;
+    return (int)cudaHostGetDevicePointer(device_ptr, host_ptr, 0);
+}

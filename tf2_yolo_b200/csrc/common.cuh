@@ -105,4 +105,20 @@ __host__ __device__ __forceinline__ size_t align_up(size_t x, size_t a) {
     return (x + a - 1) / a * a;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel that never
+// changes once raised: set it the first time a device sees the kernel instead of on every call
+// (the call costs ~1 us on the launch path).  `done` is one bit per device ordinal; setting the
+// attribute twice is harmless, so the guard needs no lock (idempotent cache, not state).
+template <typename K>
+inline cudaError_t raise_dynamic_smem_once(K kernel, int bytes, unsigned long long* done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+    return e;
+}
+
 }  // namespace yb

@@ -43,13 +43,16 @@ class _WorkspacePool:
 
     def get(self, tag, nbytes, device):
         key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+        nbytes = int(nbytes)
         buf = self._bufs.get(key)
-        if buf is None or buf.numel() < nbytes:
-            nbytes = int(max(nbytes, 4096))
-            buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        # usable capacity = what is left after aligning the base to 256 bytes
+        if buf is None or buf.numel() - ((-buf.data_ptr()) % 256) < nbytes:
+            buf = torch.empty(max(nbytes, 4096) + 256, dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         off = (-buf.data_ptr()) % 256
-        return buf[off:off + nbytes]
+        out = buf[off:off + nbytes]
+        assert out.numel() == nbytes
+        return out
 
     def clear(self):
         self._bufs.clear()
@@ -438,6 +441,44 @@ def pr_curve(conf, cls, gt_id, flag, gt_table_base, n_gt_total):
 # --------------------------------------------------------------------------
 # label-side helpers
 # --------------------------------------------------------------------------
+def encode_labels(boxes, box_offsets, img_size, grid_shape, class_num, n_levels=1, dtype=torch.float32,
+                  max_boxes_per_img=None, outs=None, n_bad=None):
+    """Box lists -> label grids on the device (yb_encode_labels; utils/tools.py:179-209 plus
+    down2xlabel :342-367 per extra level).  boxes (n_boxes, 5) f64 CUDA [x1, y1, x2, y2, class],
+    box_offsets (n_img+1) i64 CUDA; grid_shape = the FINEST grid.  Returns (list of n_levels
+    label tensors coarse grid first, n_bad u64[1] CUDA = boxes the reference would have raised on).
+    ``max_boxes_per_img`` bounds the boxes of one image (host knowledge; one sync to read it from
+    the offsets when omitted)."""
+    require_cuda(boxes, box_offsets)
+    if boxes.dtype != _F64 or box_offsets.dtype != _I64:
+        raise N.YoloB200Error("encode_labels needs float64 boxes and int64 offsets")
+    if boxes.dim() != 2 or boxes.shape[1] != 5:
+        raise ValueError("boxes must be (n_boxes, 5): x1, y1, x2, y2, class index")
+    if dtype not in (torch.float32, _F64):
+        raise N.YoloB200Error("label grids are float32 or float64")
+    dev = boxes.device
+    n_img = box_offsets.numel() - 1
+    gh, gw = int(grid_shape[0]), int(grid_shape[1])
+    if max_boxes_per_img is None:
+        max_boxes_per_img = int((box_offsets[1:] - box_offsets[:-1]).max().item()) if n_img > 0 else 0
+    if max_boxes_per_img > N.YB_ENCODE_MAX_BOXES:
+        raise ValueError(f"more than {N.YB_ENCODE_MAX_BOXES} boxes in one image")
+    with torch.cuda.device(dev):
+        if outs is None:
+            outs = [torch.empty((n_img, gh >> (n_levels - 1 - l), gw >> (n_levels - 1 - l), 5 + class_num),
+                                dtype=dtype, device=dev) for l in range(n_levels)]
+        else:
+            require_cuda(*outs)
+        if n_bad is None:
+            n_bad = torch.zeros(1, dtype=torch.int64, device=dev)
+        ptrs = (C.c_void_p * n_levels)(*[t.data_ptr() for t in outs])
+        N.check(N.lib.yb_encode_labels(_ptr(boxes), _ptr(box_offsets), n_img, int(max_boxes_per_img),
+                                       float(img_size[0]), float(img_size[1]), gh, gw, int(class_num),
+                                       int(n_levels), ptrs, int(dtype == _F64), _ptr(n_bad), _stream()),
+                "yb_encode_labels")
+    return outs, n_bad
+
+
 def down2x_labels(labels):
     """(N, gh, gw, ch) f32/f64 CUDA -> (N, gh/2, gw/2, ch) f64 CUDA (utils/tools.py:342-367)."""
     require_cuda(labels)

@@ -76,6 +76,24 @@ def make_labels(rng, n_img, grids, class_num, anchors, mean_boxes=8.0, dtype=np.
     return [o.astype(dtype) for o in out]
 
 
+def boxes_from_labels(fine_label, img_size):
+    """Box lists (pixels of an img_size = (H, W) image) of a finest-grid label tensor: the inverse
+    of the reference's grid encoding (utils/tools.py:185-209), i.e. what its file reader would
+    have parsed.  Returns (boxes (n, 5) float64 [x1, y1, x2, y2, class], offsets (n_img+1,) int64),
+    boxes in row-major cell order per image."""
+    lab = np.asarray(fine_label, dtype=np.float64)
+    n_img, gh, gw, _ = lab.shape
+    H, W = float(img_size[0]), float(img_size[1])
+    img, cy, cx = np.nonzero(lab[..., 4] == 1)
+    sel = lab[img, cy, cx]
+    bx, by = (cx + sel[:, 0]) * (W / gw), (cy + sel[:, 1]) * (H / gh)
+    bw, bh = sel[:, 2] * W, sel[:, 3] * H
+    boxes = np.column_stack([bx - bw / 2, by - bh / 2, bx + bw / 2, by + bh / 2,
+                             np.argmax(sel[:, 5:], axis=1).astype(np.float64)])
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(img, minlength=n_img))]).astype(np.int64)
+    return np.ascontiguousarray(boxes), offsets
+
+
 def make_head_outputs(rng, y_trues, grids, bbox_num, class_num, anchors,
                       det_per_gt=30, stray_frac=0.01, dtype=np.float32):
     """Activated head outputs per scale, (N, S, S, B*(5+C)), coarse first.

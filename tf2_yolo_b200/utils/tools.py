@@ -36,6 +36,32 @@ decode_batch = engine.decode_batch_exact
 nms_batch = engine.nms_batch
 
 
+def encode_labels(boxes, box_offsets, img_size, grid_shape, class_num, n_levels=1, dtype=np.float64):
+    """Label grids of a batch from its box lists: what ``YoloDataSequence.__getitem__`` builds in
+    its ``_encode_to_array`` closure (utils/tools.py:179-209), plus - for ``n_levels`` > 1 - the
+    ``down2xlabel`` pyramid of ``_Yolov4DataSequence`` (yolov4/__init__.py:47-53), coarse grid
+    first.  ``boxes``: (n_boxes, 5) [x1, y1, x2, y2, class index] in pixels of the resized image,
+    ``box_offsets``: (n_img+1,) first box of every image, ``img_size`` = (height, width),
+    ``grid_shape`` = the finest grid.  Returns a list of float64 (or ``dtype``) ndarrays.
+    Raises IndexError / ValueError where the reference would (non-finite corners, unknown class,
+    cell index below -grid)."""
+    dev = _device()
+    b = np.ascontiguousarray(np.asarray(boxes, dtype=np.float64).reshape(-1, 5))
+    off = np.ascontiguousarray(np.asarray(box_offsets, dtype=np.int64).reshape(-1))
+    if off.size < 1 or off[0] != 0 or off[-1] != b.shape[0] or np.any(np.diff(off) < 0):
+        raise ValueError("box_offsets must rise from 0 to len(boxes)")
+    most = int(np.diff(off).max()) if off.size > 1 else 0
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    outs, n_bad = engine.encode_labels(torch.from_numpy(b).to(dev), torch.from_numpy(off).to(dev), img_size,
+                                       grid_shape, class_num, n_levels, tdt, max_boxes_per_img=most)
+    res = [o.cpu().numpy() for o in outs]
+    if int(n_bad.item()):
+        if not np.all(np.isfinite(b[:, :4])):
+            raise ValueError("cannot convert float NaN to integer")       # int(nan // w) in the reference
+        raise IndexError("index out of bounds for the label grid (box class or cell index)")
+    return res
+
+
 def down2xlabel(label_data):
     """Downsample label by 2x (utils/tools.py:342-367): ndarray in, float64 ndarray out."""
     dev = _device()

@@ -5,23 +5,26 @@
 All four are sums over the same ``y_true`` / ``y_pred`` the loss reads, so the CUDA loss kernel
 accumulates them in its own pass (yb_loss_fwd_bwd_metrics): use
 ``fused_losses(..., want_metrics=True)`` in a train step for zero extra HBM traffic.  The
-closures below keep the reference's ``metric(y_true, y_pred)`` signature; the four metrics of
-one (y_true, y_pred) pair share a single forward-only launch (cached on tensor identity).
+closures below keep the reference's ``metric(y_true, y_pred)`` signature.  Keras calls the four
+closures of one output with the SAME two tensor objects, so the last result is remembered per
+thread against weak references to those objects (plus their in-place version counters): the four
+metrics of one (y_true, y_pred) pair share a single forward-only launch, and a new batch - even
+one the allocator places at the same address - is a different object and recomputes.  Host
+arrays (NumPy) carry no version counter and are never cached.
 
 ``obj_acc`` returns the mean over all cells (the reference returns the per-cell tensor that
 Keras then averages).
 """
+import threading
+import weakref
+
 import numpy as np
 import torch
 
 from . import engine
 
 _KINDS = {"obj_acc": 0, "mean_iou": 1, "class_acc": 2, "recall": 3}
-_cache = {}
-
-
-def _key(t):
-    return (t.data_ptr(), t._version, tuple(t.shape), t.device.index)
+_last = threading.local()   # .entry = (key, weakref(y_true), weakref(y_pred), versions, metrics)
 
 
 def _as_cuda(a):
@@ -38,15 +41,19 @@ def _as_cuda(a):
 
 def grid_metrics(version, y_true, y_pred, grid_shape, bbox_num, class_num, iou_threshold=0.5):
     """[obj_acc, mean_iou, class_acc, recall, 5 raw sums, n_cells] float64 CUDA (one launch)."""
+    key = (version, tuple(grid_shape), bbox_num, class_num, float(iou_threshold))
+    cacheable = torch.is_tensor(y_true) and torch.is_tensor(y_pred)
+    if cacheable:
+        hit = getattr(_last, "entry", None)
+        if (hit is not None and hit[0] == key and hit[1]() is y_true and hit[2]() is y_pred
+                and hit[3] == (y_true._version, y_pred._version)):
+            return hit[4]
     yt, yp = _as_cuda(y_true), _as_cuda(y_pred)
-    key = (version, tuple(grid_shape), bbox_num, class_num, float(iou_threshold), _key(yt), _key(yp))
-    hit = _cache.get("last")
-    if hit is not None and hit[0] == key:
-        return hit[1]
     params = engine.make_loss_params(version, grid_shape, bbox_num, class_num)
     _, _, _, metrics = engine.loss_fwd_bwd([params], [yt], [yp], want_grad=False, want_metrics=True,
                                            recall_iou_threshold=iou_threshold)
-    _cache["last"] = (key, metrics[0])
+    _last.entry = ((key, weakref.ref(y_true), weakref.ref(y_pred), (y_true._version, y_pred._version), metrics[0])
+                   if cacheable else None)
     return metrics[0]
 
 

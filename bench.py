@@ -40,10 +40,12 @@ MIN_TIMED_S = 0.5
 WORKLOAD = ("YOLOv4-608 (BASELINE configs[2]): 3 scales (19/38/76) x 3 anchors, 80 classes, batch 128 per GPU; "
             "CIoU loss fwd+grad + decode(thr 0.5) + per-class DIoU-NMS(thr 0.45)")
 CONF_THR, NMS_THR, NMS_MODE = 0.5, 0.45, 2
-ROW_CAPACITY_PER_IMG = 4096
-# my kernels per step: fused loss + decode count 1 | decode: look-back scan, emit | nms: classify,
-# scatter, sweep, emit   (--unfused: one more, the separate decode count)
-LAUNCHES_PER_STEP = 1 + 2 + 4
+ROW_CAPACITY_PER_IMG = 4096          # decode rows per image, general chain (--chain / --unfused)
+ROWS_PER_IMG_FUSED = 1024            # rows per image the one-CTA-per-image decode + NMS holds in shared memory
+# my kernels per step: loss fwd+grad with the decode counting pass | decode + NMS, one CTA per image
+#   --chain : loss + count 1 | decode: look-back scan, emit | nms: classify, scatter, sweep, emit
+#   --unfused: one more (separate decode counting pass)
+LAUNCHES_PER_STEP = {"fused": 2, "chain": 7, "unfused": 8}
 
 
 def loss_algorithmic_bytes(cfg, batch):
@@ -272,10 +274,27 @@ def run_ours(args):
     rows = torch.empty((cap, 7), dtype=torch.float64, device=dev)
     loss_ev = []
 
+    mode = "unfused" if args.unfused else ("chain" if args.chain else "fused")
+    fused_out = dict(out_rows=torch.empty((ROWS_PER_IMG_FUSED * batch, 7), dtype=torch.float64, device=dev),
+                     out_offsets=torch.empty(batch + 1, dtype=torch.int64, device=dev),
+                     n_overflow=torch.zeros(1, dtype=torch.int32, device=dev))
+
     def step(y_t, y_p, record=False):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        if mode == "fused":   # two launches: loss + counting pass, then decode + NMS with one CTA per image
+            def mark():
+                if record:
+                    e1.record()
+                    loss_ev.append((e0, e1))
+            loss, _, _, res = engine.loss_decode_nms_fused(params, y_t, y_p, CONF_THR, NMS_THR, NMS_MODE,
+                                                           rows_per_img_cap=ROWS_PER_IMG_FUSED,
+                                                           global_batch=global_batch, dpreds=dpreds, out=fused_out,
+                                                           split_hook=mark)
+            if world > 1:
+                dist.all_reduce(loss)            # the only collective: 3 scalars
+            return loss, None, res
         if args.unfused:
             loss, _, _ = fused_losses(fns, y_t, y_p, global_batch=global_batch, dpreds=dpreds)
         else:   # loss fwd+grad and the decode counting pass share one read of y_pred
@@ -311,9 +330,21 @@ def run_ours(args):
     for _ in range(args.warmup):
         out = step(dev_t, dev_p)
     barrier()
-    total_rows = int(out[1][-1].item())
-    if total_rows > cap:
-        raise SystemExit(f"decode produced {total_rows} rows > capacity {cap}")
+    if mode == "fused":
+        if int(out[2]["n_overflow"].item()):
+            raise SystemExit("an image exceeds ROWS_PER_IMG_FUSED decode rows: run with --chain")
+        # untimed: the general six-launch chain must give the same survivors, bit for bit
+        rows_c, offs_c = engine.decode_batch_exact(dev_p, C, CONF_THR, 4)
+        total_rows = int(offs_c[-1].item())
+        chain = engine.nms_batch(rows_c, offs_c, C, NMS_THR, NMS_MODE)
+        n_c = int(chain["out_offsets"][-1].item())
+        if not (torch.equal(chain["out_offsets"], out[2]["out_offsets"]) and
+                torch.equal(chain["out_rows"][:n_c], out[2]["out_rows"][:n_c])):
+            raise SystemExit("one-CTA-per-image decode+NMS differs from the general chain")
+    else:
+        total_rows = int(out[1][-1].item())
+        if total_rows > cap:
+            raise SystemExit(f"decode produced {total_rows} rows > capacity {cap}")
     kept_rows = int(out[2]["out_offsets"][-1].item())
     clocks = ClockSampler(local)
     if rank == 0:
@@ -345,7 +376,7 @@ def run_ours(args):
 
     # ---- end to end through the host-buffer API -----------------------------------
     pipe = HostBatchStep(fns, IMG_SIZE, batch, CONF_THR, NMS_THR, NMS_MODE, n_chunks=args.chunks,
-                         rows_per_img=ROW_CAPACITY_PER_IMG, max_boxes_per_img=max_per_img,
+                         rows_per_img=ROWS_PER_IMG_FUSED, max_boxes_per_img=max_per_img,
                          max_boxes=boxes_np.shape[0], global_batch=global_batch)
     h2d = sum(a.numel() * 4 for a in host_p) + boxes_np.nbytes + offs_np.nbytes
     res = None
@@ -393,9 +424,12 @@ def run_ours(args):
             "config": {
                 "workload": WORKLOAD,
                 "per_gpu_batch": batch, "global_batch": global_batch,
-                "fusion": "separate loss and decode launches" if args.unfused else
-                          "loss fwd+grad and the decode counting pass share one read of y_pred (yb_loss_decode_fused); "
-                          "roofline counts only the loss's algorithmic bytes",
+                "fusion": {"fused": "2 launches per step (yb_loss_decode_nms_fused): loss fwd+grad with the decode "
+                                    "counting pass riding on its read of y_pred, then decode + NMS with one CTA per "
+                                    "image; roofline counts only the loss's algorithmic bytes",
+                           "chain": "7 launches per step: loss fwd+grad + decode counting pass (yb_loss_decode_fused), "
+                                    "scan, emit, NMS classify / scatter / sweep / emit",
+                           "unfused": "separate loss and decode launches"}[mode],
                 "timing": f"median of {len(round_ms)} rounds of {args.steps} steps (CUDA events, max over ranks, "
                           f">= {MIN_TIMED_S} s measured)",
                 "l2_policy": f"inputs larger than L2: {sum(a.numel() * 4 for a in dev_p + dev_t) / 1e6:.0f} MB read + "
@@ -417,11 +451,12 @@ def run_ours(args):
                             "kernels of chunk k, one host sync per step; gradient stays on the device. "
                             "h2d_ceiling_gbs = the same head outputs copied with plain pinned cudaMemcpyAsync, "
                             "all ranks at once, nothing else running"},
-            "gpu_launches": (LAUNCHES_PER_STEP + (1 if args.unfused else 0)) * args.steps * len(round_ms)
+            "gpu_launches": LAUNCHES_PER_STEP[mode] * args.steps * len(round_ms)
                             + pipe.launches_per_step * e2e_steps * len(e2e_round_ms),
-            "gpu_launches_per_step": LAUNCHES_PER_STEP + (1 if args.unfused else 0),
+            "gpu_launches_per_step": LAUNCHES_PER_STEP[mode],
             "roofline": {"bound": "hbm",
                          "kernel": "loss_fwd_bwd_kernel<4,false,%s>" % ("false" if args.unfused else "true"),
+                         "tail_ms_per_step": ms - loss_ms,
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(),
                          "traffic_source": "ncu --set full capture of this kernel (profiles/loss_kernel_traffic.json)",
@@ -471,6 +506,8 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="separate loss and decode launches (y_pred read twice)")
+    ap.add_argument("--chain", action="store_true",
+                    help="decode and NMS as the general six-launch chain instead of the one-CTA-per-image kernel")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --batch images per GPU (default); strong: --batch images in total, split over the GPUs")
     ap.add_argument("--chunks", type=int, default=8, help="image chunks of the pipelined end-to-end step")

@@ -28,6 +28,7 @@ typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
 #define YB_MAX_SCALES 4  /* FPN outputs per fused loss launch */
 #define YB_LOSS_TERMS 8  /* doubles per scale in terms_out */
 #define YB_LOSS_METRICS 10 /* doubles per scale in metrics_out */
+#define YB_FUSED_MAX_ROWS 2048 /* decode rows per image the one-launch decode+NMS holds in shared memory */
 #define YB_ENCODE_MAX_BOXES 1024 /* boxes per image yb_encode_labels stages in shared memory */
 
 enum {
@@ -207,6 +208,39 @@ int yb_soft_nms(const double* rows, const int64_t* row_offsets, int64_t n_rows, 
                 int class_num, double nms_threshold, double conf_threshold, double sigma,
                 uint8_t* keep, double* out_rows, int64_t* out_offsets, int64_t* out_seg_offsets,
                 void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Decode + per-class NMS in ONE launch, one CTA per image (utils/tools.py:370-438 followed by
+ * :687-733): the counting pass files the boxes with hits per image, the image's CTA builds its
+ * float64 rows in shared memory, runs the greedy (D)IoU-NMS of every class on a warp and writes
+ * the survivors - same rows, same order, same bits as yb_decode followed by yb_nms (out_rows /
+ * out_offsets as there; they are only written and may be mapped host memory).  float32 heads,
+ * class_num <= 256.  An image with more than rows_per_img_cap (32..YB_FUSED_MAX_ROWS) decode rows
+ * is skipped (no survivors) and counted in *n_overflow (device, written by the call; may be
+ * NULL): the caller then falls back to yb_decode + yb_nms, like a too small row_capacity there.
+ * yb_loss_decode_nms_fused: the whole train-and-evaluate step in two launches - the loss
+ * forward + gradient (as yb_loss_fwd_bwd) with the counting pass riding on its read of y_pred,
+ * then the per-image kernel.  With out_offsets == NULL only the loss kernel runs (the buckets
+ * stay in fused_workspace); yb_decode_nms_finish then launches the per-image kernel.
+ * ---------------------------------------------------------------------- */
+size_t yb_decode_nms_workspace_bytes(const yb_decode_params* p, int64_t n_img, int rows_per_img_cap);
+
+int yb_decode_nms(const void* const* preds_host, int64_t n_img, const yb_decode_params* p,
+                  double nms_threshold, int iou_mode, int rows_per_img_cap, double* out_rows,
+                  int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                  void* workspace, size_t workspace_bytes, yb_stream_t stream);
+
+int yb_loss_decode_nms_fused(const yb_loss_scale* scales_host, int n_scales, float* loss_out,
+                             double* terms_out, double decode_threshold, double nms_threshold,
+                             int iou_mode, int rows_per_img_cap, double* out_rows,
+                             int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                             void* loss_workspace, size_t loss_workspace_bytes, void* fused_workspace,
+                             size_t fused_workspace_bytes, yb_stream_t stream);
+
+int yb_decode_nms_finish(const void* const* preds_host, int64_t n_img, const yb_decode_params* p,
+                         double nms_threshold, int iou_mode, int rows_per_img_cap, double* out_rows,
+                         int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                         void* workspace, size_t workspace_bytes, yb_stream_t stream);
 
 /* Pairwise IoU / DIoU matrix, utils/tools.py:630-684 on (g,1,.) x (1,d,.):
  * a: (na, stride_a) doubles, b: (nb, stride_b) doubles, out (na, nb). */

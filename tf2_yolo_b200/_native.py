@@ -15,6 +15,7 @@ YB_MAX_SCALES = 4
 YB_LOSS_TERMS = 8
 YB_LOSS_METRICS = 10
 YB_ENCODE_MAX_BOXES = 1024
+YB_FUSED_MAX_ROWS = 2048
 YB_DIST_IOU, YB_DIST_EUCLID = 0, 1
 
 
@@ -86,6 +87,13 @@ SIGNATURES = {
     "yb_loss_decode_fused": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _dbl, _vp, _i64, _vp, _vp, _sz,
                                        _vp, _sz, _vp]),
     "yb_decode_finish": (C.c_int, [C.POINTER(_vp), _i64, C.POINTER(DecodeParams), _vp, _i64, _vp, _vp, _sz, _vp]),
+    "yb_decode_nms_workspace_bytes": (_sz, [C.POINTER(DecodeParams), _i64, _i32]),
+    "yb_decode_nms": (C.c_int, [C.POINTER(_vp), _i64, C.POINTER(DecodeParams), _dbl, _i32, _i32, _vp, _i64, _vp, _vp,
+                                _vp, _sz, _vp]),
+    "yb_decode_nms_finish": (C.c_int, [C.POINTER(_vp), _i64, C.POINTER(DecodeParams), _dbl, _i32, _i32, _vp, _i64, _vp,
+                                       _vp, _vp, _sz, _vp]),
+    "yb_loss_decode_nms_fused": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _dbl, _dbl, _i32, _i32, _vp, _i64,
+                                           _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "yb_nms_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "yb_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_soft_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -38,7 +38,7 @@ constexpr int kDecStages = 3;
 template <typename T>
 __global__ void __launch_bounds__((kDecMaxConsumerWarps + 1) * 32)
 decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __restrict__ counts,
-                    unsigned int* __restrict__ n_hot, HotBox* __restrict__ hot_boxes) {
+                    unsigned int* __restrict__ n_hot, HotBox* __restrict__ hot_boxes, const HotBuckets K) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full[kDecStages], done[kDecStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -122,8 +122,15 @@ decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __rest
                     const long long g = cell0 + cell;
                     const long long img = g / L.cells[s];
                     const long long o = img * L.cell_base[L.n_scales] + L.cell_base[s] + (g - img * L.cells[s]);
-                    if (lb == 0) counts[o] = (unsigned)tot;
-                    if (n > 0) hot_boxes[atomicAdd(n_hot, 1u)] = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
+                    if (lb == 0 && counts != nullptr) counts[o] = (unsigned)tot;
+                    if (n > 0) {
+                        const HotBox hb = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
+                        if (hot_boxes != nullptr) hot_boxes[atomicAdd(n_hot, 1u)] = hb;
+                        if (K.n != nullptr) {
+                            const unsigned u = atomicAdd(&K.n[img], 1u);
+                            if (u < (unsigned)K.cap) K.box[img * K.cap + u] = hb;
+                        }
+                    }
                 }
             }
             mbar_arrive(&done[stage]);
@@ -204,7 +211,7 @@ decode_emit_kernel(const __grid_constant__ DecodeLaunch L, const unsigned int* _
     }
 }
 
-static int fill_decode(const void* const* preds, int64_t n_img, const yb_decode_params* p, DecodeLaunch& L) {
+int decode_fill(const void* const* preds, int64_t n_img, const yb_decode_params* p, DecodeLaunch& L) {
     if (preds == nullptr || p == nullptr) return YB_E_NULL;
     if (p->version < 1 || p->version > 4) return YB_E_PARAM;
     if (p->n_scales < 1 || p->n_scales > YB_MAX_SCALES || p->class_num <= 0 || n_img < 0) return YB_E_SHAPE;
@@ -231,6 +238,43 @@ static int fill_decode(const void* const* preds, int64_t n_img, const yb_decode_
         L.scale_base[s + 1] = L.scale_base[s] + n_img * L.cells[s];
     }
     return YB_OK;
+}
+
+// K1 geometry (3 stages of <= 24 KB, 3 CTAs per SM) + launch
+int decode_count(DecodeLaunch& L, bool is_f64, unsigned int* counts, unsigned int* n_hot, HotBox* hot,
+                 const HotBuckets& buckets, cudaStream_t stream) {
+    const size_t esz = is_f64 ? 8 : 4;
+    const int stage_budget = 24 * 1024;
+    int ncw = 1, stage_bytes = 0;
+    for (int s = 0; s < L.n_scales; ++s) {
+        const int cb = (int)(L.pcf[s] * esz);
+        if (4 * cb > 72 * 1024) return YB_E_SHAPE;
+        const int cpw = 32 / L.B[s];
+        int t = stage_budget / cb / 4 * 4;
+        t = min(t, kDecMaxConsumerWarps * cpw / 4 * 4);
+        t = max(4, t);
+        L.tile_cells[s] = t;
+        L.tile_base[s + 1] = L.tile_base[s] + (int)((L.n_img * L.cells[s] + t - 1) / t);
+        L.bulk_ok[s] = (((uintptr_t)L.preds[s] & 15) == 0) ? 1 : 0;
+        stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
+        ncw = max(ncw, min(kDecMaxConsumerWarps, (t + cpw - 1) / cpw));
+    }
+    const int n_tiles = L.tile_base[L.n_scales];
+    L.stage_bytes = stage_bytes;
+    const size_t smem = (size_t)kDecStages * stage_bytes;
+    const int ctas_per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 2048))));
+    const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
+    const int threads1 = (ncw + 1) * 32;
+    if (is_f64) {
+        static unsigned long long done = 0;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<double>, 100 * 1024, &done));
+        decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
+    } else {
+        static unsigned long long done = 0;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<float>, 100 * 1024, &done));
+        decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
+    }
+    return (int)cudaGetLastError();
 }
 
 }  // namespace yb
@@ -263,7 +307,7 @@ namespace yb {
 
 int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params* p, void* workspace,
                  size_t workspace_bytes, DecodeLaunch& L, DecodeWs& ws) {
-    int rc = fill_decode(preds, n_img, p, L);
+    int rc = decode_fill(preds, n_img, p, L);
     if (rc != YB_OK) return rc;
     if (workspace == nullptr) return YB_E_NULL;
     if (workspace_bytes < yb_decode_workspace_bytes(p, n_img) || ((uintptr_t)workspace & 255))
@@ -318,38 +362,9 @@ extern "C" int yb_decode(const void* const* preds, int64_t n_img, const yb_decod
         YB_CUDA_TRY(cudaMemsetAsync(row_offsets, 0, sizeof(int64_t) * (n_img + 1), stream));
         return YB_OK;
     }
-    // K1 geometry: 3 stages of <= 24 KB, 3 CTAs per SM
-    const size_t esz = p->is_f64 ? 8 : 4;
-    const int stage_budget = 24 * 1024;
-    int ncw = 1, stage_bytes = 0;
-    for (int s = 0; s < L.n_scales; ++s) {
-        const int cb = (int)(L.pcf[s] * esz);
-        if (4 * cb > 72 * 1024) return YB_E_SHAPE;
-        const int cpw = 32 / L.B[s];
-        int t = stage_budget / cb / 4 * 4;
-        t = min(t, kDecMaxConsumerWarps * cpw / 4 * 4);
-        t = max(4, t);
-        L.tile_cells[s] = t;
-        L.tile_base[s + 1] = L.tile_base[s] + (int)((L.n_img * L.cells[s] + t - 1) / t);
-        L.bulk_ok[s] = (((uintptr_t)L.preds[s] & 15) == 0) ? 1 : 0;
-        stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));
-        ncw = max(ncw, min(kDecMaxConsumerWarps, (t + cpw - 1) / cpw));
-    }
-    const int n_tiles = L.tile_base[L.n_scales];
-    L.stage_bytes = stage_bytes;
-    const size_t smem = (size_t)kDecStages * stage_bytes;
-    const int ctas_per_sm = max(1, min(4, (int)((227 * 1024) / (smem + 2048))));
-    const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
-    const int threads1 = (ncw + 1) * 32;
     YB_CUDA_TRY(cudaMemsetAsync(ws.n_hot, 0, ws.zero_bytes, stream));
-    if (p->is_f64) {
-        YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, ws.counts, ws.n_hot, ws.hot);
-    } else {
-        YB_CUDA_TRY(cudaFuncSetAttribute(decode_count_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, ws.counts, ws.n_hot, ws.hot);
-    }
-    YB_CUDA_TRY(cudaGetLastError());
+    rc = decode_count(L, p->is_f64 != 0, ws.counts, ws.n_hot, ws.hot, HotBuckets{}, stream);
+    if (rc != YB_OK) return rc;
     return decode_finish(L, ws, p->is_f64 != 0, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream, true);
 }
 

@@ -36,6 +36,14 @@ __host__ __device__ inline HotBox make_hot(long long o, unsigned mem_idx, int sc
     return h;
 }
 
+// Per-image lists of the boxes with hits, for the one-CTA-per-image decode+NMS kernel
+// (decode_nms.cu): image i owns box[i*cap .. i*cap + min(n[i], cap)); n[i] > cap = overflow.
+struct HotBuckets {
+    unsigned int* n = nullptr;   // [n_img], zero before the counting pass; nullptr = not collected
+    HotBox* box = nullptr;       // [n_img][cap]
+    int cap = 0;
+};
+
 struct DecodeWs {          // carved out of the caller's decode workspace
     unsigned int* n_hot;   // number of boxes with hits
     unsigned int* counts;  // hits per cell, OUTPUT order (image, scale, y, x)
@@ -44,13 +52,29 @@ struct DecodeWs {          // carved out of the caller's decode workspace
     void* scan_ws;
     size_t zero_bytes;     // n_hot + scan status: cleared by one memset before the counting pass
     long long total_cells;
+    HotBuckets buckets;    // optional second destination of the counting pass
 };
 
+// fill L from the public parameter struct (no workspace); YB_OK / YB_E_*
+int decode_fill(const void* const* preds, int64_t n_img, const yb_decode_params* p, DecodeLaunch& L);
+// counting pass alone: per-cell counts + flat work list (either may be null) and / or per-image buckets
+int decode_count(DecodeLaunch& L, bool is_f64, unsigned int* counts, unsigned int* n_hot, HotBox* hot,
+                 const HotBuckets& buckets, cudaStream_t stream);
 // validate + fill L and ws (no launches).  Returns YB_OK / YB_E_*.
 int decode_setup(const void* const* preds, int64_t n_img, const yb_decode_params* p, void* workspace,
                  size_t workspace_bytes, DecodeLaunch& L, DecodeWs& ws);
 // scan of the per-cell counts + emission of the rows (after counts / hot list are complete)
 int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double* rows, long long cap,
                   long long* row_offsets, cudaStream_t stream, bool status_zeroed = false);
+
+// One-CTA-per-image decode + NMS (decode_nms.cu), split so that the fused loss kernel can do the
+// counting pass: fused_prepare validates, carves the workspace, clears its control block (one
+// memset) and returns the per-image buckets the counting pass must fill; fused_finish launches
+// the per-image kernel.
+int fused_prepare(const void* const* preds, int64_t n_img, const yb_decode_params* p, int row_cap, void* workspace,
+                  size_t workspace_bytes, DecodeLaunch& D, HotBuckets& K, cudaStream_t stream);
+int fused_finish(const DecodeLaunch& D, int64_t n_img, int row_cap, void* workspace, double nms_threshold,
+                 int iou_mode, double* out_rows, int64_t out_capacity, int64_t* out_offsets,
+                 unsigned int* n_overflow, cudaStream_t stream);
 
 }  // namespace yb

@@ -426,11 +426,16 @@ static int launch_km(KmLaunch L, cudaStream_t stream) {
         if (need(tile, stages) > budget1) return YB_E_SHAPE;
     }
     int ctas = (need(tile, stages) <= budget2) ? 2 : 1;
-    {   // tuning hooks (debug): YB_KM_TILE / YB_KM_STAGES / YB_KM_CTAS
-        const char* e;
-        if ((e = getenv("YB_KM_TILE")) && atoi(e) >= 32) tile = atoi(e) / 32 * 32;
-        if ((e = getenv("YB_KM_STAGES")) && atoi(e) >= 2 && atoi(e) <= kKmMaxStages) stages = atoi(e);
-        if ((e = getenv("YB_KM_CTAS")) && atoi(e) >= 1 && atoi(e) <= 4) ctas = atoi(e);
+    {   // tuning hooks (debug): YB_KM_TILE / YB_KM_STAGES / YB_KM_CTAS, read once per process
+        struct Env {
+            int tile, stages, ctas;
+            static int get(const char* n) { const char* e = getenv(n); return (e && *e) ? atoi(e) : 0; }
+            Env() : tile(get("YB_KM_TILE")), stages(get("YB_KM_STAGES")), ctas(get("YB_KM_CTAS")) {}
+        };
+        static const Env env;
+        if (env.tile >= 32) tile = env.tile / 32 * 32;
+        if (env.stages >= 2 && env.stages <= kKmMaxStages) stages = env.stages;
+        if (env.ctas >= 1 && env.ctas <= 4) ctas = env.ctas;
         if (need(tile, stages) > budget1) return YB_E_SHAPE;
     }
     L.tile_pts = tile;
@@ -440,8 +445,8 @@ static int launch_km(KmLaunch L, cudaStream_t stream) {
     const int grid = (int)max(1LL, min((long long)kNumSMs * ctas, (n_tiles + kKmWarps - 1) / kKmWarps));
 #define YB_KM_LAUNCH(IOU, ASSIGN)                                                                          \
     do {                                                                                                   \
-        YB_CUDA_TRY(cudaFuncSetAttribute(kmeans_assign_kernel<K, D, IOU, ASSIGN>,                          \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        static unsigned long long done = 0;                                                                \
+        YB_CUDA_TRY(raise_dynamic_smem_once(kmeans_assign_kernel<K, D, IOU, ASSIGN>, 227 * 1024, &done));  \
         kmeans_assign_kernel<K, D, IOU, ASSIGN><<<grid, kKmThreads, smem, stream>>>(L);                    \
     } while (0)
     const bool iou = L.kind == YB_DIST_IOU, asg = L.assign != nullptr;

@@ -96,9 +96,11 @@ struct LossLaunch {
     double* metrics_out;   // [n_scales][YB_LOSS_METRICS] or null
     int from_logits;       // all scales: y_pred holds raw head outputs
     // fused decode counting (yb_loss_decode_fused): per-cell hit counts in decode OUTPUT order
-    unsigned int* dec_counts;
+    int dec_on;                              // select the counting variant of the kernel
+    unsigned int* dec_counts;                // may be null (per-image buckets only)
     unsigned int* dec_n_hot;
-    HotBox* dec_hot;
+    HotBox* dec_hot;                         // may be null
+    HotBuckets dec_buckets;                  // per-image lists for the fused decode+NMS kernel, or off
     long long dec_per_img;                   // cells per image over all scales
     long long dec_cell_base[YB_MAX_SCALES];  // first cell of a scale inside an image
     long long dec_cells[YB_MAX_SCALES];      // grid_h * grid_w
@@ -489,8 +491,15 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         const long long g = cell0 + cell;
                         const long long img = g / L.dec_cells[s];
                         const long long o = img * L.dec_per_img + L.dec_cell_base[s] + (g - img * L.dec_cells[s]);
-                        if (lb == 0) L.dec_counts[o] = (unsigned)tot;
-                        if (n > 0) L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
+                        if (lb == 0 && L.dec_counts != nullptr) L.dec_counts[o] = (unsigned)tot;
+                        if (n > 0) {
+                            const HotBox hb = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
+                            if (L.dec_hot != nullptr) L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = hb;
+                            if (L.dec_buckets.n != nullptr) {
+                                const unsigned u = atomicAdd(&L.dec_buckets.n[img], 1u);
+                                if (u < (unsigned)L.dec_buckets.cap) L.dec_buckets.box[img * L.dec_buckets.cap + u] = hb;
+                            }
+                        }
                     }
                 }
                 if (kMetrics) {
@@ -756,9 +765,20 @@ __global__ void grid_iou_kernel(const float* __restrict__ bt, int ts, const floa
 
 // ---- host side ----------------------------------------------------------------
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
+// Tuning knobs (YB_LOSS_STAGES, YB_LOSS_CTAS_PER_SM, YB_LOSS_TILE_CELLS, YB_LOSS_WARPS): read from the environment
+// ONCE per process (function-local statics, thread-safe), not on every launch.
+struct LossEnv {
+    int stages, ctas_per_sm, tile_cells, warps;
+    static int get(const char* name, int dflt) {
+        const char* v = getenv(name);
+        return (v && *v) ? atoi(v) : dflt;
+    }
+    LossEnv() : stages(get("YB_LOSS_STAGES", 2)), ctas_per_sm(get("YB_LOSS_CTAS_PER_SM", 4)),
+                tile_cells(get("YB_LOSS_TILE_CELLS", 0)), warps(get("YB_LOSS_WARPS", 0)) {}
+};
+static const LossEnv& loss_env() {
+    static const LossEnv e;
+    return e;
 }
 
 static size_t loss_gacc_bytes(int n_scales) {
@@ -814,23 +834,23 @@ static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
 
 template <int V, bool kMetrics, bool kDecode>
 static int launch_loss_variant(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
-    YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V, kMetrics, kDecode>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static unsigned long long done = 0;   // per template instance; the ring never needs more than one SM's worth
+    YB_CUDA_TRY(raise_dynamic_smem_once(loss_fwd_bwd_kernel<V, kMetrics, kDecode>, 227 * 1024, &done));
     loss_fwd_bwd_kernel<V, kMetrics, kDecode><<<grid, threads, smem, stream>>>(L);
     return (int)cudaGetLastError();
 }
 
 template <int V, bool kMetrics>
 static int launch_loss_logits(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
-    YB_CUDA_TRY(cudaFuncSetAttribute(loss_fwd_bwd_kernel<V, kMetrics, false, true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static unsigned long long done = 0;
+    YB_CUDA_TRY(raise_dynamic_smem_once(loss_fwd_bwd_kernel<V, kMetrics, false, true>, 227 * 1024, &done));
     loss_fwd_bwd_kernel<V, kMetrics, false, true><<<grid, threads, smem, stream>>>(L);
     return (int)cudaGetLastError();
 }
 
 template <int V>
 static int launch_loss(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
-    const bool m = L.metrics_out != nullptr, d = L.dec_counts != nullptr;
+    const bool m = L.metrics_out != nullptr, d = L.dec_on != 0;
     if (L.from_logits) {
         if (V != 3 && V != 4) return YB_E_PARAM;  // v1/v2 heads end in a softmax
         if (d) return YB_E_PARAM;                 // decode counting needs activated scores
@@ -893,10 +913,10 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     // Ring geometry: by default 2 stages and 4 CTAs per SM (for v3/v4 cells: 20 cells = 27.2 KB per
     // stage, two consumer warps of 10 cells); fat cells get fewer CTAs per SM.  An SM has 228 KB of
     // shared memory, every resident CTA costs its static + dynamic bytes + 1 KB.
-    int n_stages = env_int("YB_LOSS_STAGES", 2);
+    int n_stages = loss_env().stages;
     n_stages = max(2, min(kMaxStages, n_stages));
-    int ctas_per_sm = max(1, min(8, env_int("YB_LOSS_CTAS_PER_SM", 4)));
-    const int tile_env = env_int("YB_LOSS_TILE_CELLS", 0);
+    int ctas_per_sm = max(1, min(8, loss_env().ctas_per_sm));
+    const int tile_env = loss_env().tile_cells;
     const size_t sm_smem = 228 * 1024, static_smem = 192;
     auto acc_bytes = [&](int warps) { return sizeof(double) * warps * n_scales * kTerms * 2; };
     const size_t bar_bytes = 2 * kMaxStages * sizeof(uint64_t);
@@ -933,7 +953,7 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
             stage_bytes = max(stage_bytes, (int)align_up((size_t)t * cb, 128));  // 128 B-aligned stages
             warps = max(warps, min(kLossMaxConsumerWarps, (t + cpw - 1) / cpw));
         }
-        ncw = max(1, min(kLossMaxConsumerWarps, env_int("YB_LOSS_WARPS", warps)));
+        ncw = max(1, min(kLossMaxConsumerWarps, (loss_env().warps > 0 ? loss_env().warps : warps)));
     }
     L.total_tiles = total_tiles;
     L.stage_bytes = stage_bytes;
@@ -945,9 +965,11 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     L.metrics_out = metrics_out;
     for (int s = 0; s < n_scales; ++s) L.sc[s].recall_thr = (float)recall_iou_threshold;
     if (fd != nullptr) {
+        L.dec_on = 1;
         L.dec_counts = fd->ws->counts;
         L.dec_n_hot = fd->ws->n_hot;
         L.dec_hot = fd->ws->hot;
+        L.dec_buckets = fd->ws->buckets;
         L.dec_per_img = fd->L->cell_base[n_scales];
         for (int s = 0; s < n_scales; ++s) {
             L.dec_cell_base[s] = fd->L->cell_base[s];
@@ -1033,6 +1055,64 @@ extern "C" int yb_loss_decode_fused(const yb_loss_scale* scales, int n_scales, f
                    stream_, &fd);
     if (rc != YB_OK || count_only) return rc;
     return decode_finish(DL, ws, false, rows, row_capacity, reinterpret_cast<long long*>(row_offsets), stream, true);
+}
+
+// The whole train-and-evaluate step in TWO launches: the loss kernel (forward + gradient + the
+// decode counting pass into per-image buckets) and the one-CTA-per-image decode + NMS kernel.
+extern "C" int yb_loss_decode_nms_fused(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                                        double* terms_out, double decode_threshold, double nms_threshold,
+                                        int iou_mode, int rows_per_img_cap, double* out_rows,
+                                        int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                                        void* loss_workspace, size_t loss_workspace_bytes, void* fused_workspace,
+                                        size_t fused_workspace_bytes, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (scales == nullptr) return YB_E_NULL;
+    const bool count_only = out_offsets == nullptr;   // the per-image kernel comes later: yb_decode_nms_finish
+    if (n_scales < 1 || n_scales > YB_MAX_SCALES) return YB_E_SHAPE;
+    if (out_rows == nullptr && out_capacity > 0) return YB_E_NULL;
+    if (out_capacity < 0) return YB_E_CAPACITY;
+    if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
+    yb_decode_params dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.version = scales[0].p.version;
+    dp.class_num = scales[0].p.class_num;
+    dp.n_scales = n_scales;
+    dp.is_f64 = 0;
+    dp.threshold = decode_threshold;
+    const void* preds[YB_MAX_SCALES];
+    int64_t n_img = -1;
+    for (int s = 0; s < n_scales; ++s) {
+        const yb_loss_params& p = scales[s].p;
+        if (p.grid_h <= 0 || p.grid_w <= 0) return YB_E_SHAPE;
+        const int64_t cells = (int64_t)p.grid_h * p.grid_w;
+        if (scales[s].n_cells % cells != 0) return YB_E_SHAPE;
+        const int64_t n = scales[s].n_cells / cells;
+        if (n_img >= 0 && n != n_img) return YB_E_SHAPE;  // every scale must hold the same images
+        n_img = n;
+        if (p.class_num != dp.class_num || p.version != dp.version) return YB_E_PARAM;
+        dp.grid_h[s] = p.grid_h;
+        dp.grid_w[s] = p.grid_w;
+        dp.bbox_num[s] = p.bbox_num;
+        preds[s] = scales[s].y_pred;
+    }
+    if (n_img == 0) {
+        if (!count_only) YB_CUDA_TRY(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), stream));
+        if (n_overflow != nullptr) YB_CUDA_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(unsigned int), stream));
+        return loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes,
+                         stream_);
+    }
+    DecodeLaunch DL;
+    DecodeWs ws;
+    memset(&ws, 0, sizeof(ws));
+    int rc = fused_prepare(preds, n_img, &dp, rows_per_img_cap, fused_workspace, fused_workspace_bytes, DL, ws.buckets,
+                           stream);
+    if (rc != YB_OK) return rc;
+    FusedDecode fd{&DL, &ws};   // counts / flat list stay null: only the per-image buckets are filled
+    rc = loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes, stream_,
+                   &fd);
+    if (rc != YB_OK || count_only) return rc;
+    return fused_finish(DL, n_img, rows_per_img_cap, fused_workspace, nms_threshold, iou_mode, out_rows, out_capacity,
+                        out_offsets, n_overflow, stream);
 }
 
 static int loss_single(int version, const float* y_true, const float* y_pred, int64_t n_cells,

@@ -318,6 +318,112 @@ def nms_batch(rows, row_offsets, class_num=1, nms_threshold=0.45, iou_mode=1, wa
     return dict(keep=keep[:R], out_rows=out_rows, out_offsets=out_offsets, seg_offsets=seg)
 
 
+def _fused_outputs(dev, n_img, out_capacity, out):
+    if out is not None:
+        return out["out_rows"], out["out_offsets"], out["n_overflow"]
+    return (torch.empty((max(out_capacity, 1), 7), dtype=_F64, device=dev),
+            torch.empty(n_img + 1, dtype=_I64, device=dev), torch.empty(1, dtype=torch.int32, device=dev))
+
+
+def decode_nms_batch(preds, class_num=1, threshold=0.5, version=1, nms_threshold=0.45, iou_mode=1,
+                     rows_per_img_cap=1024, out_capacity=None, out=None):
+    """Decode + per-class NMS of a batch in one launch after the counting pass (yb_decode_nms), for
+    images of at most ``rows_per_img_cap`` decode rows.  Returns dict(out_rows (cap,7) f64,
+    out_offsets (n_img+1) i64, n_overflow i32[1]) - all CUDA; images that exceed the cap produce no
+    rows and are counted in n_overflow (see decode_nms_batch_exact for the checked form)."""
+    require_cuda(*preds)
+    p, n_img = make_decode_params(preds, class_num, threshold, version)
+    dev = preds[0].device
+    if out_capacity is None:
+        out_capacity = rows_per_img_cap * max(n_img, 1)
+    with torch.cuda.device(dev):
+        out_rows, out_offsets, n_overflow = _fused_outputs(dev, n_img, out_capacity, out)
+        ws_bytes = N.lib.yb_decode_nms_workspace_bytes(C.byref(p), n_img, int(rows_per_img_cap))
+        if ws_bytes == 0:
+            raise ValueError("yb_decode_nms: float32 heads, class_num <= 256, 32 <= rows_per_img_cap <= "
+                             f"{N.YB_FUSED_MAX_ROWS}")
+        ws = workspaces.get("decode_nms", ws_bytes, dev)
+        ptrs = (C.c_void_p * len(preds))(*[t.data_ptr() for t in preds])
+        N.check(N.lib.yb_decode_nms(ptrs, n_img, C.byref(p), float(nms_threshold), int(iou_mode),
+                                    int(rows_per_img_cap), _ptr(out_rows), out_rows.shape[0], _ptr(out_offsets),
+                                    _ptr(n_overflow), _ptr(ws), ws_bytes, _stream()), "yb_decode_nms")
+    return dict(out_rows=out_rows, out_offsets=out_offsets, n_overflow=n_overflow)
+
+
+def decode_nms_batch_exact(preds, class_num=1, threshold=0.5, version=1, nms_threshold=0.45, iou_mode=1,
+                           rows_per_img_cap=1024):
+    """decode_nms_batch with the overflow check (one host sync): falls back to the general chain
+    (yb_decode + yb_nms, any size) when an image exceeds the cap.  Returns (rows (K,7), offsets)."""
+    r = decode_nms_batch(preds, class_num, threshold, version, nms_threshold, iou_mode, rows_per_img_cap)
+    if int(r["n_overflow"].item()) == 0:
+        total = int(r["out_offsets"][-1].item())
+        if total <= r["out_rows"].shape[0]:
+            return r["out_rows"][:total], r["out_offsets"]
+    rows, offs = decode_batch_exact(preds, class_num, threshold, version)
+    g = nms_batch(rows, offs, class_num, nms_threshold, iou_mode)
+    return g["out_rows"][:int(g["out_offsets"][-1].item())], g["out_offsets"]
+
+
+def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold=0.45, iou_mode=1,
+                          rows_per_img_cap=1024, global_batch=None, dpreds=None, want_terms=False, out=None,
+                          out_capacity=None, split_hook=None):
+    """The train-and-evaluate step in two launches (yb_loss_decode_nms_fused): loss forward +
+    gradient with the decode counting pass riding on its read of y_pred, then decode + NMS with one
+    CTA per image.  Returns (loss [n], dpreds, terms, dict(out_rows, out_offsets, n_overflow))."""
+    n = len(params)
+    require_cuda(*y_trues, *y_preds)
+    dev = y_preds[0].device
+    scales = (N.LossScale * n)()
+    outs = []
+    n_img = y_preds[0].shape[0]
+    for i, (p, yt, yp) in enumerate(zip(params, y_trues, y_preds)):
+        if yt.dtype != torch.float32 or yp.dtype != torch.float32:
+            raise N.YoloB200Error("loss tensors must be float32")
+        cells_per_img = p.grid_h * p.grid_w
+        pcf = (5 * p.bbox_num + p.class_num) if p.version == 1 else p.bbox_num * (5 + p.class_num)
+        if yp.numel() != n_img * cells_per_img * pcf or yt.numel() != n_img * cells_per_img * (5 + p.class_num):
+            raise ValueError("every scale must hold the same images with matching grid / info sizes")
+        q = N.LossParams.from_buffer_copy(p)
+        q.inv_batch = 1.0 / float(global_batch if global_batch is not None else max(n_img, 1))
+        d = dpreds[i] if dpreds is not None else torch.empty_like(yp)
+        outs.append(d)
+        scales[i].y_true, scales[i].y_pred, scales[i].dpred = yt.data_ptr(), yp.data_ptr(), d.data_ptr()
+        scales[i].n_cells = n_img * cells_per_img
+        scales[i].p = q
+    dparams, _ = make_decode_params(y_preds, params[0].class_num, threshold, params[0].version)
+    if out_capacity is None:
+        out_capacity = rows_per_img_cap * max(n_img, 1)
+    with torch.cuda.device(dev):
+        out_rows, out_offsets, n_overflow = _fused_outputs(dev, n_img, out_capacity, out)
+        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        terms = torch.empty((n, N.YB_LOSS_TERMS), dtype=_F64, device=dev) if want_terms else None
+        lws_bytes = N.lib.yb_loss_workspace_bytes(n)
+        lws = workspaces.get("loss", lws_bytes, dev)
+        fws_bytes = N.lib.yb_decode_nms_workspace_bytes(C.byref(dparams), n_img, int(rows_per_img_cap))
+        if fws_bytes == 0:
+            raise ValueError("yb_loss_decode_nms_fused: class_num <= 256, 32 <= rows_per_img_cap <= "
+                             f"{N.YB_FUSED_MAX_ROWS}")
+        fws = workspaces.get("decode_nms", fws_bytes, dev)
+        if split_hook is None:
+            N.check(N.lib.yb_loss_decode_nms_fused(scales, n, _ptr(loss), _ptr(terms), float(threshold),
+                                                   float(nms_threshold), int(iou_mode), int(rows_per_img_cap),
+                                                   _ptr(out_rows), out_rows.shape[0], _ptr(out_offsets),
+                                                   _ptr(n_overflow), _ptr(lws), lws_bytes, _ptr(fws), fws_bytes,
+                                                   _stream()), "yb_loss_decode_nms_fused")
+        else:   # two calls so that a timer can bracket the loss kernel alone (bench.py roofline)
+            N.check(N.lib.yb_loss_decode_nms_fused(scales, n, _ptr(loss), _ptr(terms), float(threshold),
+                                                   float(nms_threshold), int(iou_mode), int(rows_per_img_cap),
+                                                   None, 0, None, None, _ptr(lws), lws_bytes, _ptr(fws), fws_bytes,
+                                                   _stream()), "yb_loss_decode_nms_fused(loss)")
+            split_hook()
+            ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in y_preds])
+            N.check(N.lib.yb_decode_nms_finish(ptrs, n_img, C.byref(dparams), float(nms_threshold), int(iou_mode),
+                                               int(rows_per_img_cap), _ptr(out_rows), out_rows.shape[0],
+                                               _ptr(out_offsets), _ptr(n_overflow), _ptr(fws), fws_bytes, _stream()),
+                    "yb_decode_nms_finish")
+    return loss, outs, terms, dict(out_rows=out_rows, out_offsets=out_offsets, n_overflow=n_overflow)
+
+
 def pairwise_iou(a, b, mode=1):
     """(na, >=4) x (nb, >=4) f64 CUDA -> (na, nb) f64; a plays xywh_true."""
     require_cuda(a, b)

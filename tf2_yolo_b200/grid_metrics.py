@@ -52,9 +52,10 @@ def grid_metrics(version, y_true, y_pred, grid_shape, bbox_num, class_num, iou_t
     params = engine.make_loss_params(version, grid_shape, bbox_num, class_num)
     _, _, _, metrics = engine.loss_fwd_bwd([params], [yt], [yp], want_grad=False, want_metrics=True,
                                            recall_iou_threshold=iou_threshold)
-    _last.entry = ((key, weakref.ref(y_true), weakref.ref(y_pred), (y_true._version, y_pred._version), metrics[0])
+    m = metrics[0]
+    _last.entry = ((key, weakref.ref(y_true), weakref.ref(y_pred), (y_true._version, y_pred._version), m)
                    if cacheable else None)
-    return metrics[0]
+    return m
 
 
 def _wrap(version, kind, grid_shape, bbox_num, class_num, iou_threshold=0.5):

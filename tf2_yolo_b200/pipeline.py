@@ -12,10 +12,12 @@ kernels straight into mapped host memory, so no sized D2H copy and no mid-step r
 The batch is cut into chunks of images: the H2D copy of chunk k+1 runs on a copy stream under
 the kernels of chunk k, and the host synchronises ONCE per step.
 
-Per chunk (all through the C ABI, include/yolo_b200.h): yb_encode_labels -> yb_loss_decode_fused
-(loss fwd+grad and the decode counting pass in one read of y_pred) -> yb_nms.  Chunk losses are
-partial sums with the divisor of the whole (global) batch, so their sum is the reference's
-``reduce_mean(axis=0)`` loss (yolov4/losses/loss.py:117).
+Per chunk (all through the C ABI, include/yolo_b200.h): yb_encode_labels ->
+yb_loss_decode_nms_fused (loss fwd+grad with the decode counting pass riding on its read of
+y_pred, then decode + NMS with one CTA per image): three launches.  A chunk in which an image
+exceeds ``rows_per_img`` decode rows is redone after the step's sync with the general chain
+(yb_decode + yb_nms).  Chunk losses are partial sums with the divisor of the whole (global) batch,
+so their sum is the reference's ``reduce_mean(axis=0)`` loss (yolov4/losses/loss.py:117).
 """
 import ctypes as C
 
@@ -35,7 +37,7 @@ def _mapped(t):
 
 class HostBatchStep:
     def __init__(self, loss_fns, img_size, batch, conf_threshold=0.5, nms_threshold=0.45, nms_mode=2,
-                 n_chunks=8, rows_per_img=4096, max_boxes_per_img=64, max_boxes=None, global_batch=None,
+                 n_chunks=8, rows_per_img=1024, max_boxes_per_img=64, max_boxes=None, global_batch=None,
                  device=None):
         if not torch.cuda.is_available():
             raise N.YoloB200Error("no CUDA device: tf2_yolo_b200 has no CPU fallback")
@@ -89,17 +91,20 @@ class HostBatchStep:
             dp = self._decode_params(most)
             dws = N.lib.yb_decode_workspace_bytes(C.byref(dp), most)
             nws = N.lib.yb_nms_workspace_bytes(cap, most, self.C)
-            self.ws = [torch.empty(int(b) + 256, dtype=torch.uint8, device=dev) for b in (lws, dws, nws)]
-            self.ws_bytes = (lws, dws, nws)
+            fws = N.lib.yb_decode_nms_workspace_bytes(C.byref(dp), most, self.rows_per_img)
+            if fws == 0:
+                raise ValueError(f"rows_per_img must be in [32, {N.YB_FUSED_MAX_ROWS}] and class_num <= 256")
+            self.ws = [torch.empty(int(b) + 256, dtype=torch.uint8, device=dev) for b in (lws, dws, nws, fws)]
+            self.ws_bytes = (lws, dws, nws, fws)
         # results, written by the kernels into mapped pinned host memory
         nc = len(self.chunks)
         self.loss_host = torch.zeros((nc, self.n_scales), dtype=torch.float32).pin_memory()
         self.out_offsets_host = torch.zeros((nc, most + 1), dtype=torch.int64).pin_memory()
         self.out_rows_host = torch.zeros((nc, cap, 7), dtype=torch.float64).pin_memory()
         self.n_bad_host = torch.zeros(1, dtype=torch.int64).pin_memory()
-        self.decoded_host = torch.zeros(nc, dtype=torch.int64).pin_memory()   # decode rows per chunk (overflow check)
+        self.overflow_host = torch.zeros(nc, dtype=torch.int32).pin_memory()  # images over rows_per_img, per chunk
         self._calls = [self._bind_chunk(ci, a, b) for ci, (a, b) in enumerate(self.chunks)]
-        self.launches_per_step = 8 * nc   # encode, loss+count, scan, emit, classify, scatter, sweep, emit
+        self.launches_per_step = 3 * nc   # encode, loss + count, decode + NMS
 
     # -- argument binding (once) ---------------------------------------------------------------
     def _decode_params(self, n_img):
@@ -129,9 +134,11 @@ class HostBatchStep:
             scales[s].p = q
             label_ptrs[s] = scales[s].y_true
         vp = C.c_void_p
-        lws, dws, nws = (vp(self._al(w)) for w in self.ws)
+        lws, dws, nws, fws = (vp(self._al(w)) for w in self.ws)
+        pred_ptrs = (C.c_void_p * self.n_scales)(*[scales[s].y_pred for s in range(self.n_scales)])
         return dict(
-            n=n, scales=scales, label_ptrs=label_ptrs, lws=lws, dws=dws, nws=nws,
+            n=n, scales=scales, label_ptrs=label_ptrs, lws=lws, dws=dws, nws=nws, fws=fws, pred_ptrs=pred_ptrs,
+            overflow=vp(_mapped(self.overflow_host) + 4 * ci),
             offs=vp(self.box_offsets.data_ptr() + 8 * a),
             loss=vp(_mapped(self.loss_host) + 4 * self.n_scales * ci),
             out_offsets=vp(_mapped(self.out_offsets_host) + 8 * self.out_offsets_host.shape[1] * ci),
@@ -161,41 +168,65 @@ class HostBatchStep:
                     ev.record(cs)
                     events.append(ev)
             k = vp(ks.cuda_stream)
-            lws_b, dws_b, nws_b = self.ws_bytes
-            boxes_p, rows_p, roff_p, keep_p = (vp(self.boxes.data_ptr()), vp(self.rows.data_ptr()),
-                                               vp(self.row_offsets.data_ptr()), vp(self.keep.data_ptr()))
+            lws_b, dws_b, nws_b, fws_b = self.ws_bytes
+            boxes_p = vp(self.boxes.data_ptr())
             gh, gw = self.fine_grid
-            for ci, (call, ev) in enumerate(zip(self._calls, events)):
+            for call, ev in zip(self._calls, events):
                 ks.wait_event(ev)
                 n = call["n"]
                 N.check(lib.yb_encode_labels(boxes_p, call["offs"], n, self.max_boxes_per_img, self.img_size[0],
                                              self.img_size[1], gh, gw, self.C, self.n_scales, call["label_ptrs"], 0,
                                              vp(self.n_bad.data_ptr()), k), "yb_encode_labels")
-                N.check(lib.yb_loss_decode_fused(call["scales"], self.n_scales, call["loss"], None, self.thr, rows_p,
-                                                 self.row_cap, roff_p, call["lws"], lws_b, call["dws"], dws_b, k),
-                        "yb_loss_decode_fused")
-                N.check(lib.yb_nms(rows_p, roff_p, self.row_cap, n, self.C, self.nms_thr, self.nms_mode, keep_p,
-                                   call["out_rows"], call["out_offsets"], None, call["nws"], nws_b, k), "yb_nms")
-                with torch.cuda.stream(ks):
-                    self.decoded_host[ci:ci + 1].copy_(self.row_offsets[n:n + 1], non_blocking=True)
+                N.check(lib.yb_loss_decode_nms_fused(call["scales"], self.n_scales, call["loss"], None, self.thr,
+                                                     self.nms_thr, self.nms_mode, self.rows_per_img, call["out_rows"],
+                                                     self.row_cap, call["out_offsets"], call["overflow"],
+                                                     call["lws"], lws_b, call["fws"], fws_b, k),
+                        "yb_loss_decode_nms_fused")
             with torch.cuda.stream(ks):
                 self.n_bad_host.copy_(self.n_bad, non_blocking=True)
             ks.synchronize()                                   # the ONE host sync of the step
+            for ci, call in enumerate(self._calls):
+                if int(self.overflow_host[ci]):                # an image beyond rows_per_img: general chain
+                    self._redo_chunk(call, k)
         if int(self.n_bad_host[0]):
             raise IndexError(f"{int(self.n_bad_host[0])} boxes the reference's label encoder raises on")
         loss = self.loss_host.numpy().sum(axis=0, dtype=np.float32)
         offs = self.out_offsets_host.numpy()
         rows = self.out_rows_host.numpy()
         out, total = [], 0
-        if int(self.decoded_host.max()) > self.row_cap:
-            raise N.YoloB200Error("decode produced more rows than rows_per_img allows; raise rows_per_img")
         for ci, (a, b) in enumerate(self.chunks):
             o = offs[ci, :b - a + 1]
             out.append((rows[ci, :o[-1]], o))
             total += int(o[-1])
         return dict(loss=loss, dpred=self.dpred, rows=out, n_rows=total)
 
+    def _redo_chunk(self, call, k):
+        """Decode + NMS of one chunk with the general chain (any number of rows per image)."""
+        lib, vp = N.lib, C.c_void_p
+        n = call["n"]
+        dp = self._decode_params(n)
+        cap = self.row_cap
+        while True:
+            rows = torch.empty((cap, 7), dtype=torch.float64, device=self.dev)
+            roff = torch.empty(n + 1, dtype=torch.int64, device=self.dev)
+            keep = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+            N.check(lib.yb_decode(call["pred_ptrs"], n, C.byref(dp), vp(rows.data_ptr()), cap, vp(roff.data_ptr()),
+                                  call["dws"], self.ws_bytes[1], k), "yb_decode")
+            self.compute_stream.synchronize()
+            total = int(roff[-1].item())
+            if total <= cap:
+                break
+            cap = total
+        if total > self.row_cap:
+            raise N.YoloB200Error("more survivors than the host result buffer holds; raise rows_per_img")
+        nws_bytes = N.lib.yb_nms_workspace_bytes(cap, n, self.C)
+        nws = torch.empty(int(nws_bytes) + 256, dtype=torch.uint8, device=self.dev)
+        N.check(lib.yb_nms(vp(rows.data_ptr()), vp(roff.data_ptr()), cap, n, self.C, self.nms_thr, self.nms_mode,
+                           vp(keep.data_ptr()), call["out_rows"], call["out_offsets"], None, vp(self._al(nws)),
+                           nws_bytes, k), "yb_nms")
+        self.compute_stream.synchronize()
+
     def d2h_bytes(self, n_rows):
         """Bytes the kernels wrote into host memory for a step with ``n_rows`` survivors."""
         return (4 * self.loss_host.numel() + 8 * sum(b - a + 1 for a, b in self.chunks) + 56 * n_rows + 8 +
-                8 * len(self.chunks))
+                4 * len(self.chunks))

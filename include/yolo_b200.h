@@ -43,6 +43,8 @@ enum {
 
 int yb_abi_version(void);
 const char* yb_status_string(int status);
+/* "file:line" of the CUDA runtime call behind the last positive status this THREAD received. */
+const char* yb_last_error_site(void);
 
 /* Device-side alias of a page-locked HOST allocation.  Output pointers of the entry points below
  * may be such aliases where noted ("may be mapped host memory"): the kernel then writes its

@@ -73,6 +73,7 @@ _vp, _i64, _i32, _sz, _dbl = C.c_void_p, C.c_int64, C.c_int, C.c_size_t, C.c_dou
 SIGNATURES = {
     "yb_abi_version": (C.c_int, []),
     "yb_status_string": (C.c_char_p, [C.c_int]),
+    "yb_last_error_site": (C.c_char_p, []),
     "yb_mapped_host_pointer": (C.c_int, [_vp, C.POINTER(_vp)]),
     "yb_loss_workspace_bytes": (_sz, [_i32]),
     "yb_loss_fwd_bwd": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _vp, _sz, _vp]),
@@ -138,4 +139,6 @@ def status_string(code):
 
 def check(code, what=""):
     if code != 0:
-        raise YoloB200Error(f"{what or 'yolo_b200 call'} failed: status {code} ({status_string(code)})")
+        site = lib.yb_last_error_site().decode() if code > 0 else ""
+        raise YoloB200Error(f"{what or 'yolo_b200 call'} failed: status {code} ({status_string(code)})"
+                            + (f" at {site}" if site else ""))

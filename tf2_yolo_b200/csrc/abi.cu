@@ -1,7 +1,16 @@
 // ABI version + status strings.
 #include "common.cuh"
 
+namespace yb {
+const char*& last_error_site() {
+    static thread_local const char* site = "";
+    return site;
+}
+}  // namespace yb
+
 extern "C" int yb_abi_version(void) { return YB_ABI_VERSION; }
+
+extern "C" const char* yb_last_error_site(void) { return yb::last_error_site(); }
 
 extern "C" const char* yb_status_string(int status) {
     switch (status) {

@@ -6,10 +6,21 @@
 
 #include "../../include/yolo_b200.h"
 
-#define YB_CUDA_TRY(expr)                              \
-    do {                                               \
-        cudaError_t _e = (expr);                       \
-        if (_e != cudaSuccess) return (int)_e;         \
+// Where the last failing CUDA runtime call of this thread was made ("file:line"), for
+// yb_last_error_site(): a positive status alone (a cudaError_t) does not say which call it was.
+namespace yb {
+const char*& last_error_site();
+}
+#define YB_STR2(x) #x
+#define YB_STR(x) YB_STR2(x)
+#define YB_CUDA_TRY(expr)                                          \
+    do {                                                           \
+        cudaError_t _e = (expr);                                   \
+        if (_e != cudaSuccess) {                                   \
+            yb::last_error_site() = __FILE__ ":" YB_STR(__LINE__); \
+            (void)cudaGetLastError(); /* leave no stale error for the caller's own runtime calls */ \
+            return (int)_e;                                        \
+        }                                                          \
     } while (0)
 
 namespace yb {
@@ -107,17 +118,20 @@ __host__ __device__ __forceinline__ size_t align_up(size_t x, size_t a) {
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel that never
 // changes once raised: set it the first time a device sees the kernel instead of on every call
-// (the call costs ~1 us on the launch path).  `done` is one bit per device ordinal; setting the
+// (the call costs ~1 us on the launch path), and again only when a launch needs more.  Setting the
 // attribute twice is harmless, so the guard needs no lock (idempotent cache, not state).
+struct SmemRaised {
+    int bytes[64];   // per device ordinal: the largest value set so far (zero-initialised static)
+};
 template <typename K>
-inline cudaError_t raise_dynamic_smem_once(K kernel, int bytes, unsigned long long* done) {
+inline cudaError_t raise_dynamic_smem_once(K kernel, int bytes, SmemRaised* state) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (__atomic_load_n(done, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+    int* slot = &state->bytes[dev & 63];
+    if (bytes <= __atomic_load_n(slot, __ATOMIC_ACQUIRE)) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) __atomic_fetch_or(done, bit, __ATOMIC_RELEASE);
+    if (e == cudaSuccess) __atomic_store_n(slot, bytes, __ATOMIC_RELEASE);   // racing raises are harmless
     return e;
 }
 

@@ -266,15 +266,16 @@ int decode_count(DecodeLaunch& L, bool is_f64, unsigned int* counts, unsigned in
     const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
     const int threads1 = (ncw + 1) * 32;
     if (is_f64) {
-        static unsigned long long done = 0;
-        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<double>, 100 * 1024, &done));
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<double>, (int)smem, &done));
         decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
     } else {
-        static unsigned long long done = 0;
-        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<float>, 100 * 1024, &done));
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<float>, (int)smem, &done));
         decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
     }
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 }  // namespace yb
@@ -342,7 +343,8 @@ int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double
     else
         decode_emit_kernel<float><<<blocks2, threads, 0, stream>>>(L, ws.n_hot, ws.hot, ws.offsets, rows, cap,
                                                                    row_offsets);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 }  // namespace yb

@@ -407,15 +407,16 @@ static int fused_launch(const DecodeLaunch& D, const FusedWs& W, int row_cap, do
     const FusedSmem lay(row_cap, D.C, F.cw);
     if (lay.total > 220 * 1024) return YB_E_SHAPE;
     if (iou_mode == 1) {
-        static unsigned long long done = 0;
-        YB_CUDA_TRY(raise_dynamic_smem_once(decode_nms_image_kernel<1>, 220 * 1024, &done));
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_nms_image_kernel<1>, (int)lay.total, &done));
         decode_nms_image_kernel<1><<<(unsigned)D.n_img, kFusedThreads, lay.total, stream>>>(F);
     } else {
-        static unsigned long long done = 0;
-        YB_CUDA_TRY(raise_dynamic_smem_once(decode_nms_image_kernel<2>, 220 * 1024, &done));
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_nms_image_kernel<2>, (int)lay.total, &done));
         decode_nms_image_kernel<2><<<(unsigned)D.n_img, kFusedThreads, lay.total, stream>>>(F);
     }
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 // Shared with loss.cu (yb_loss_decode_nms_fused): workspace carve-up + memset, then the launch.
@@ -464,15 +465,17 @@ extern "C" int yb_decode_nms(const void* const* preds, int64_t n_img, const yb_d
     if (out_rows == nullptr && out_capacity > 0) return YB_E_NULL;
     if (out_capacity < 0) return YB_E_CAPACITY;
     if (iou_mode != 1 && iou_mode != 2) return YB_E_PARAM;
-    DecodeLaunch D;
-    HotBuckets K;
-    int rc = fused_prepare(preds, n_img, p, rows_per_img_cap, workspace, workspace_bytes, D, K, stream);
-    if (rc != YB_OK) return rc;
     if (n_img == 0) {
+        int rc0 = fused_check(p, n_img, rows_per_img_cap);
+        if (rc0 != YB_OK) return rc0;
         YB_CUDA_TRY(cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), stream));
         if (n_overflow != nullptr) YB_CUDA_TRY(cudaMemsetAsync(n_overflow, 0, sizeof(unsigned int), stream));
         return YB_OK;
     }
+    DecodeLaunch D;
+    HotBuckets K;
+    int rc = fused_prepare(preds, n_img, p, rows_per_img_cap, workspace, workspace_bytes, D, K, stream);
+    if (rc != YB_OK) return rc;
     rc = decode_count(D, false, nullptr, nullptr, nullptr, K, stream);
     if (rc != YB_OK) return rc;
     return fused_finish(D, n_img, rows_per_img_cap, workspace, nms_threshold, iou_mode, out_rows, out_capacity,

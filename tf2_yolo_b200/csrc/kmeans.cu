@@ -445,8 +445,8 @@ static int launch_km(KmLaunch L, cudaStream_t stream) {
     const int grid = (int)max(1LL, min((long long)kNumSMs * ctas, (n_tiles + kKmWarps - 1) / kKmWarps));
 #define YB_KM_LAUNCH(IOU, ASSIGN)                                                                          \
     do {                                                                                                   \
-        static unsigned long long done = 0;                                                                \
-        YB_CUDA_TRY(raise_dynamic_smem_once(kmeans_assign_kernel<K, D, IOU, ASSIGN>, 227 * 1024, &done));  \
+        static SmemRaised done;                                                                \
+        YB_CUDA_TRY(raise_dynamic_smem_once(kmeans_assign_kernel<K, D, IOU, ASSIGN>, (int)smem, &done));  \
         kmeans_assign_kernel<K, D, IOU, ASSIGN><<<grid, kKmThreads, smem, stream>>>(L);                    \
     } while (0)
     const bool iou = L.kind == YB_DIST_IOU, asg = L.assign != nullptr;
@@ -455,7 +455,8 @@ static int launch_km(KmLaunch L, cudaStream_t stream) {
     else if (asg) YB_KM_LAUNCH(false, true);
     else YB_KM_LAUNCH(false, false);
 #undef YB_KM_LAUNCH
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 template <int D>
@@ -544,5 +545,6 @@ extern "C" int yb_minmax_f64(const double* data, int64_t n, double* out2, void* 
     unsigned int* counter = reinterpret_cast<unsigned int*>((char*)workspace + align_up((size_t)grid * 16, 256));
     YB_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
     minmax_kernel<<<grid, 256, 0, stream>>>(data, n, partials, counter, out2);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }

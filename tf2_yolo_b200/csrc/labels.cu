@@ -339,7 +339,8 @@ extern "C" int yb_down2x_labels(const void* labels, int is_f64, int64_t n_img, i
     else
         down2x_kernel<float><<<blocks, threads, 0, stream>>>(reinterpret_cast<const float*>(labels), n_img, grid_h,
                                                              grid_w, channels, out);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 extern "C" size_t yb_column_sums_workspace_bytes(int cols) {
@@ -369,7 +370,8 @@ extern "C" int yb_column_sums(const void* data, int is_f64, int64_t rows, int co
         column_sums_kernel<float><<<grid, threads, smem, stream>>>(reinterpret_cast<const float*>(data), rows, cols,
                                                                    partials, counter, out);
     }
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 extern "C" int yb_encode_labels(const double* boxes, const int64_t* box_offsets, int64_t n_img,
@@ -402,17 +404,18 @@ extern "C" int yb_encode_labels(const double* boxes, const int64_t* box_offsets,
     if (n_img * chunks > 0x7fffffffLL) return YB_E_SHAPE;
     const unsigned int grid = (unsigned int)(n_img * chunks);
     if (out_f64) {
-        static unsigned long long done = 0;
-        YB_CUDA_TRY(raise_dynamic_smem_once(encode_labels_kernel<double>, 200 * 1024, &done));
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(encode_labels_kernel<double>, (int)smem, &done));
         encode_labels_kernel<double><<<grid, 256, smem, stream>>>(
             boxes, box_offsets, cap, img_h, img_w, grid_h, grid_w, class_num, n_levels, (double*)outs[0],
             (double*)outs[1], (double*)outs[2], (double*)outs[3], (int)chunks, n_bad);
     } else {
-        static unsigned long long done = 0;
-        YB_CUDA_TRY(raise_dynamic_smem_once(encode_labels_kernel<float>, 200 * 1024, &done));
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(encode_labels_kernel<float>, (int)smem, &done));
         encode_labels_kernel<float><<<grid, 256, smem, stream>>>(
             boxes, box_offsets, cap, img_h, img_w, grid_h, grid_w, class_num, n_levels, (float*)outs[0],
             (float*)outs[1], (float*)outs[2], (float*)outs[3], (int)chunks, n_bad);
     }
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }

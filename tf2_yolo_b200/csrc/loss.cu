@@ -834,18 +834,20 @@ static int fill_scale(const yb_loss_scale& in, LossScaleDev& d) {
 
 template <int V, bool kMetrics, bool kDecode>
 static int launch_loss_variant(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
-    static unsigned long long done = 0;   // per template instance; the ring never needs more than one SM's worth
-    YB_CUDA_TRY(raise_dynamic_smem_once(loss_fwd_bwd_kernel<V, kMetrics, kDecode>, 227 * 1024, &done));
+    static SmemRaised done;   // per template instance
+    YB_CUDA_TRY(raise_dynamic_smem_once(loss_fwd_bwd_kernel<V, kMetrics, kDecode>, (int)smem, &done));
     loss_fwd_bwd_kernel<V, kMetrics, kDecode><<<grid, threads, smem, stream>>>(L);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 template <int V, bool kMetrics>
 static int launch_loss_logits(const LossLaunch& L, int grid, int threads, size_t smem, cudaStream_t stream) {
-    static unsigned long long done = 0;
-    YB_CUDA_TRY(raise_dynamic_smem_once(loss_fwd_bwd_kernel<V, kMetrics, false, true>, 227 * 1024, &done));
+    static SmemRaised done;
+    YB_CUDA_TRY(raise_dynamic_smem_once(loss_fwd_bwd_kernel<V, kMetrics, false, true>, (int)smem, &done));
     loss_fwd_bwd_kernel<V, kMetrics, false, true><<<grid, threads, smem, stream>>>(L);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 template <int V>
@@ -1156,5 +1158,6 @@ extern "C" int yb_grid_iou(const float* box_true, int true_stride, const float* 
     grid_iou_kernel<<<(unsigned)blocks, threads, 0, stream>>>(box_true, true_stride, box_pred, pred_stride,
                                                               n, bbox_num, (float)grid_w, (float)grid_h,
                                                               iou_out, ciou_out);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }

@@ -424,7 +424,8 @@ extern "C" int yb_map_accumulate(const double* det_rows, const int64_t* det_seg_
         class_num, iou_threshold, max_per_img, reinterpret_cast<const long long*>(gt_base), out_pos_T, gt_pos_T,
         conf, reinterpret_cast<long long*>(gt_id), flag, cls, reinterpret_cast<long long*>(class_offsets),
         reinterpret_cast<unsigned long long*>(score_acc));
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 extern "C" size_t yb_pr_curve_workspace_bytes(int64_t n_det, int64_t n_gt_total) {

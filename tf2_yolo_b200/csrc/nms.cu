@@ -833,7 +833,7 @@ static int nms_impl(const double* rows, const int64_t* row_offsets_, int64_t n_r
     const unsigned small_blocks = (unsigned)max(1LL, min((long long)kNumSMs * 4, (warp_jobs + 7) / 8));
 #define YB_NMS_LAUNCH(M)                                                                                       \
     do {                                                                                                       \
-        static unsigned long long done = 0;                                                                    \
+        static SmemRaised done;                                                                    \
         YB_CUDA_TRY(raise_dynamic_smem_once(nms_sweep_kernel<M>, (int)big_smem, &done));                       \
         nms_sweep_kernel<M><<<big_blocks + small_blocks, kBigThreads, big_smem, stream>>>(                     \
             rows, nms_threshold, conf_thr, sigma, W, n_rows, n_seg, class_num, big_blocks, keep);                         \
@@ -884,7 +884,8 @@ extern "C" int yb_pairwise_iou(const double* a, int64_t na, int stride_a, const 
         pairwise_iou_kernel<1><<<grid, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
     else
         pairwise_iou_kernel<2><<<grid, threads, 0, stream>>>(a, na, stride_a, b, nb, stride_b, out);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 extern "C" int yb_elementwise_iou(const double* a, int stride_a, const double* b, int stride_b, int64_t n,
@@ -900,5 +901,6 @@ extern "C" int yb_elementwise_iou(const double* a, int stride_a, const double* b
         elementwise_iou_kernel<1><<<blocks, threads, 0, stream>>>(a, stride_a, b, stride_b, n, out);
     else
         elementwise_iou_kernel<2><<<blocks, threads, 0, stream>>>(a, stride_a, b, stride_b, n, out);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }

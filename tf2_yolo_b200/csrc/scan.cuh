@@ -196,7 +196,8 @@ static inline int exclusive_scan_u32(const unsigned int* in, long long n, long l
                                      void* workspace, cudaStream_t stream, bool status_zeroed = false) {
     if (n <= 64 * 1024) {
         scan_single_block<<<1, 1024, 0, stream>>>(in, n, out);
-        return (int)cudaGetLastError();
+        YB_CUDA_TRY(cudaGetLastError());
+        return YB_OK;
     }
     const int n_blocks = (int)((n + kLbTile - 1) / kLbTile);
     unsigned long long* status = reinterpret_cast<unsigned long long*>(workspace);
@@ -204,7 +205,8 @@ static inline int exclusive_scan_u32(const unsigned int* in, long long n, long l
     if (!status_zeroed)
         YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)(n_blocks + 1) * sizeof(long long), stream));
     scan_lookback_kernel<<<n_blocks, kLbThreads, 0, stream>>>(in, n, out, status, ticket);
-    return (int)cudaGetLastError();
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 }  // namespace yb

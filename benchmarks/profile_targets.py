@@ -42,4 +42,17 @@ if "iou" in what:
         for _ in range(3):
             engine.pairwise_iou(a, b, mode)       # 67 M pair IoUs per launch, fp64, (n, n) matrix out
     torch.cuda.synchronize()
+if "step" in what:   # the two-launch train-and-evaluate step of bench.py (v4-608)
+    from tf2_yolo_b200.yolov4.losses import wrap_yolo_loss
+    batch = int(os.environ.get("YB_PROF_BATCH", 128))
+    cfg = synth.make_config("v4-608", batch=batch, seed=2)
+    B, C = 3, 80
+    fns = [wrap_yolo_loss((S, S), B, C, anchors=cfg["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1])
+           for si, S in enumerate(cfg["grids"])]
+    yts = [torch.from_numpy(a).cuda() for a in cfg["y_trues"]]
+    yps = [torch.from_numpy(a).cuda() for a in cfg["y_preds"]]
+    dps = [torch.empty_like(a) for a in yps]
+    for _ in range(4):
+        engine.loss_decode_nms_fused([f.params for f in fns], yts, yps, 0.5, 0.45, 2, rows_per_img_cap=1024, dpreds=dps)
+    torch.cuda.synchronize()
 print("ok")

@@ -268,6 +268,43 @@ int yb_kmeans_assign(const double* data, int64_t n_points, int n_dim, const doub
                      int k, int dist_kind, int32_t* assign, double* sums, int64_t* counts,
                      void* workspace, size_t workspace_bytes, yb_stream_t stream);
 
+/* utils/kmeans.py:9-40 evaluated directly (the module's iou / iou_dist / euclidean_dist on
+ * data-sized arrays): a (na, n_dim), b (nb, n_dim) float64.  outer != 0: out (na, nb), every a
+ * against every b (the (k,1,d) x (1,M,d) broadcast of kmeans.py:79); outer == 0: na == nb, out (nb).
+ * what: 0 iou (area ratio min/max), 1 iou_dist (1 - iou), 2 euclidean_dist. */
+int yb_kmeans_dist(const double* a, int64_t na, const double* b, int64_t nb, int n_dim, int what,
+                   int outer, double* out, yb_stream_t stream);
+
+/* The Lloyd loop of utils/kmeans.py:78-98 WITHOUT the host in it.  One call = one iteration:
+ * assignment pass over the resident boxes and - single rank, packed == NULL - the update of
+ * kmeans.py:84-97 by the last CTA of the same launch: cluster means, loss = mean(dist(center,
+ * new_center)) in NumPy's summation order, centres rewritten in place, the stop test
+ * `loss < stop_dist or epoch > max_iternum`.  Sharded (packed != NULL): the pass leaves
+ * [k*d sums | k counts as doubles] in `packed` for the caller's all-reduce on the same stream and
+ * yb_kmeans_lloyd_update applies the update on every rank (identical inputs, identical centres).
+ * `state` (device, yb_kmeans_state_bytes, zeroed by yb_kmeans_lloyd_init together with the
+ * workspace's counter) holds 8-byte words: [0] status 0 running | 1 converged | 2 iteration cap |
+ * 3 empty cluster, [1] completed updates, [4 + (e-1) % YB_KMEANS_HIST] the loss of update e
+ * (double), then the k*(d+1) global sums / counts of the iteration that met an empty cluster.
+ * A non-zero status FREEZES the loop: further steps return at once, so the host may queue
+ * iterations in batches and look at `state` once per batch; the result does not depend on the
+ * batch size.  On status 3 the centres are untouched: the host redraws the empty clusters with
+ * numpy.random in the reference's order (kmeans.py:89), finishes that update and clears the status.
+ * assign (optional) receives the assignments of the pass (against the centres BEFORE its update). */
+#define YB_KMEANS_HIST 64
+size_t yb_kmeans_state_bytes(int k, int n_dim);
+
+int yb_kmeans_lloyd_init(int64_t* state, int k, int n_dim, void* workspace, size_t workspace_bytes,
+                         yb_stream_t stream);
+
+int yb_kmeans_lloyd_step(const double* data, int64_t n_points, int n_dim, double* centers, int k,
+                         int dist_kind, double stop_dist, int64_t max_iternum, int64_t* state,
+                         double* packed, int32_t* assign, void* workspace, size_t workspace_bytes,
+                         yb_stream_t stream);
+
+int yb_kmeans_lloyd_update(const double* packed, double* centers, int k, int n_dim, int dist_kind,
+                           double stop_dist, int64_t max_iternum, int64_t* state, yb_stream_t stream);
+
 /* min / max over all elements of data (kmeans.py:68-69). out2 = {min,max}. */
 int yb_minmax_f64(const double* data, int64_t n, double* out2, void* workspace,
                   size_t workspace_bytes, yb_stream_t stream);

@@ -130,3 +130,66 @@ def test_kmeans_many_clusters_and_extreme_areas():
         ref = okm.assign(d2, centers, okm.iou_dist)
     a, _, _ = engine.kmeans_assign(torch.from_numpy(d2).cuda(), torch.from_numpy(centers).cuda(), YB_DIST_IOU, True)
     assert np.array_equal(a.cpu().numpy(), ref)
+
+
+def test_device_lloyd_loop_is_the_reference_loop(golden, capsys):
+    """The loop runs on the device (update, loss and stop test in the assignment launch) and the
+    host looks at it every `check_every` iterations: centres, iteration count and the printed losses
+    equal the reference's whatever the batch size, including an empty-cluster hand-back."""
+    z = golden("kmeans")
+    rng = np.random.default_rng(77)
+    data = synth.make_kmeans_boxes(rng, 20000, k=6)
+    for fn, ofn, k, stop in ((km.iou_dist, okm.iou_dist, 6, 1e-5), (km.euclidean_dist, okm.euclidean_dist, 4, 1e-4)):
+        np.random.seed(3)
+        trace = []
+        ref = okm.kmeans(data, k, ofn, stop, trace=trace)
+        lines = [f"epoch {e + 1:2d}: loss = {t[2]:.4f}" for e, t in enumerate(trace)]
+        for every in (1, 3, 8, 64):
+            np.random.seed(3)
+            got = km.kmeans(data, k, fn, stop, verbose=True, check_every=every)
+            out = capsys.readouterr().out.strip().split("\n")
+            assert np.array_equal(got, ref), (fn.__name__, every)
+            assert out == lines, (fn.__name__, every)
+    # iteration cap (kmeans.py:97: epoch > max_iternum)
+    for cap in (1, 2, 5):
+        np.random.seed(3)
+        ref = okm.kmeans(data, 6, okm.iou_dist, 0.0, max_iternum=cap)
+        np.random.seed(3)
+        assert np.array_equal(km.kmeans(data, 6, km.iou_dist, 0.0, max_iternum=cap, verbose=False), ref), cap
+    # empty clusters in several iterations (9 clusters over 50 boxes), every batch size
+    for every in (1, 2, 8):
+        np.random.seed(5)
+        c = km.kmeans(z["empty/data"], 9, km.iou_dist, 1e-5, verbose=False, check_every=every)
+        assert np.array_equal(c, z["empty/centers"]), every
+    # assignments refer to the returned centres (ADVICE r1: they were one update behind)
+    np.random.seed(3)
+    c, a = km.kmeans(data, 6, km.iou_dist, 1e-5, verbose=False, return_assignments=True)
+    np.random.seed(3)
+    tr = []
+    okm.kmeans(data, 6, okm.iou_dist, 1e-5, trace=tr)
+    assert np.array_equal(a.cpu().numpy(), okm.assign(data, tr[-1][0], okm.iou_dist))
+
+
+def test_reference_distance_functions_and_data_sized_helpers():
+    """dist_func may be the reference's own function object (recognised by behaviour); the distance
+    helpers take data-sized arrays (utils/kmeans.py:43-45 accepts both)."""
+    rng = np.random.default_rng(8)
+    data = synth.make_kmeans_boxes(rng, 70000, k=5)
+
+    def ref_iou_dist(center_boxes, data_boxes):          # utils/kmeans.py:9-33, as a user would pass it
+        ca = center_boxes[..., 0] * center_boxes[..., 1]
+        da = data_boxes[..., 0] * data_boxes[..., 1]
+        return 1 - np.minimum(ca, da) / np.maximum(ca, da)
+    np.random.seed(1)
+    a = km.kmeans(data, 5, ref_iou_dist, 1e-5, verbose=False)
+    np.random.seed(1)
+    assert np.array_equal(a, km.kmeans(data, 5, km.iou_dist, 1e-5, verbose=False))
+    with pytest.raises(Exception):
+        km.kmeans(data, 5, lambda c, d: np.abs(c - d).sum(-1), 1e-5, verbose=False)
+    c = rng.uniform(0.05, 0.7, (5, 1, 2))
+    assert np.array_equal(km.iou_dist(c, data[None]), okm.iou_dist(c, data[None]))           # (5, 70000) on the GPU
+    assert np.array_equal(km.iou(c, data[None]), okm.area_ratio(c, data[None]))
+    assert np.array_equal(km.euclidean_dist(c, data[None]), okm.euclidean_dist(c, data[None]))
+    assert np.array_equal(km.iou_dist(data, data[::-1]), okm.iou_dist(data, data[::-1]))     # element by element
+    x3 = rng.uniform(0, 1, (40000, 3))
+    assert np.array_equal(km.euclidean_dist(x3, x3[::-1]), okm.euclidean_dist(x3, x3[::-1]))

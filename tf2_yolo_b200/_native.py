@@ -16,6 +16,7 @@ YB_LOSS_TERMS = 8
 YB_LOSS_METRICS = 10
 YB_ENCODE_MAX_BOXES = 1024
 YB_FUSED_MAX_ROWS = 2048
+YB_KMEANS_HIST = 64
 YB_DIST_IOU, YB_DIST_EUCLID = 0, 1
 
 
@@ -102,6 +103,11 @@ SIGNATURES = {
     "yb_elementwise_iou": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _i32, _vp, _vp]),
     "yb_kmeans_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "yb_kmeans_assign": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "yb_kmeans_dist": (C.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "yb_kmeans_state_bytes": (_sz, [_i32, _i32]),
+    "yb_kmeans_lloyd_init": (C.c_int, [_vp, _i32, _i32, _vp, _sz, _vp]),
+    "yb_kmeans_lloyd_step": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _dbl, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "yb_kmeans_lloyd_update": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _dbl, _i64, _vp, _vp]),
     "yb_minmax_f64": (C.c_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "yb_encode_labels": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _dbl, _i32, _i32, _i32, _i32, C.POINTER(_vp), _i32,
                                    _vp, _vp]),

@@ -34,7 +34,79 @@ struct KmLaunch {
     long long* counts;  // [k]
     double* partials;   // [grid][K*(D+1)]
     unsigned int* counter;
+    // Lloyd loop on the device (yb_kmeans_lloyd_step): all optional
+    long long* state;   // Lloyd state words; a non-zero status freezes the loop: the kernel returns at once
+    double* packed;     // [k*d sums | k counts as doubles]: the payload of the all-reduce when sharded
+    double* centers_rw; // non-null: the last CTA applies the Lloyd update itself (single rank)
+    double stop_dist;
+    long long max_iter;
 };
+
+// ---- the Lloyd update, utils/kmeans.py:84-97, as device code -------------------------------------
+// state words (8 bytes each): [0] status 0 running | 1 loss < stop_dist | 2 iteration cap | 3 empty
+// cluster (the host redraws: numpy.random owns that, kmeans.py:89), [1] completed updates,
+// [2], [3] reserved, [4 .. 4+YB_KMEANS_HIST) loss of update e at slot (e-1) % YB_KMEANS_HIST,
+// then k*(d+1) doubles: the global sums / counts of the iteration that found an empty cluster.
+__device__ __forceinline__ double km_np_min(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a < b ? a : b)); }
+__device__ __forceinline__ double km_np_max(double a, double b) { return (a != a) ? a : ((b != b) ? b : (a > b ? a : b)); }
+
+// np.add.reduce over a contiguous float64 vector (NumPy's pairwise summation, n <= 128)
+__device__ inline double km_np_sum(const double* a, int n) {
+    if (n < 8) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+        return r;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+}
+
+// One thread.  fin: [c*(d+1)+j] sums, [c*(d+1)+d] counts (as doubles, exact).  Returns nothing;
+// leaves the centres untouched when it freezes on an empty cluster.
+__device__ inline void km_lloyd_update(int k, int d, int kind, const double* fin, double* centers,
+                                       long long* state, double stop_dist, long long max_iter) {
+    double* hist = reinterpret_cast<double*>(state + 4);
+    double* saved = hist + YB_KMEANS_HIST;
+    for (int c = 0; c < k; ++c)
+        if (!(fin[c * (d + 1) + d] > 0.0)) {            // kmeans.py:85: len(index) > 0
+            for (int i = 0; i < k * (d + 1); ++i) saved[i] = fin[i];
+            __threadfence();
+            state[0] = 3;
+            return;
+        }
+    double dist[16];
+    for (int c = 0; c < k; ++c) {
+        double nc[4];
+        for (int j = 0; j < d; ++j) nc[j] = fin[c * (d + 1) + j] / fin[c * (d + 1) + d];   // cluster mean
+        if (kind == YB_DIST_IOU) {                       // kmeans.py:12-22, 32
+            const double ca = __dmul_rn(centers[c * d], centers[c * d + 1]);
+            const double na = __dmul_rn(nc[0], nc[1]);
+            dist[c] = 1.0 - km_np_min(ca, na) / km_np_max(ca, na);
+        } else {                                         // kmeans.py:39
+            double sq = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double df = centers[c * d + j] - nc[j];
+                sq = __dadd_rn(sq, __dmul_rn(df, df));
+            }
+            dist[c] = sqrt(sq);
+        }
+        for (int j = 0; j < d; ++j) centers[c * d + j] = nc[j];
+    }
+    const double loss = km_np_sum(dist, k) / (double)k;  // np.mean, kmeans.py:92
+    const long long done = state[1] + 1;
+    hist[(done - 1) % YB_KMEANS_HIST] = loss;
+    state[1] = done;
+    __threadfence();
+    if (loss < stop_dist) state[0] = 1;                  // kmeans.py:97 (epoch = done + 1)
+    else if (done + 1 > max_iter) state[0] = 2;
+}
 
 // NumPy's argmin over the rounded iou_dist values (kmeans.py:12-22,32,80), first minimum wins;
 // returns the SORTED slot of the winner.  Cold path (near ties, degenerate centroids, NaN).
@@ -84,6 +156,7 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = L.k;  // <= K
     const int n_stages = L.n_stages, tile_pts = L.tile_pts;
+    if (L.state != nullptr && __ldcg(&L.state[0]) != 0) return;   // frozen Lloyd loop: nothing to do
 
     if (tid == 0) {
         for (int w = 0; w < kKmWarps; ++w)
@@ -353,19 +426,45 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     __syncthreads();
     if (!s_is_last) return;
     __threadfence();
+    double* s_fin = s_red;   // [K*(D+1)]: the global sums / counts (s_red is dead: partials are in global memory)
+    __syncthreads();
     for (int i = warp; i < NV; i += kKmWarps) {
         double sres = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) sres += __ldcg(&L.partials[(size_t)b * NV + i]);
         sres = warp_sum(sres);
         if (lane == 0) {
             const int c = i / (D + 1), j = i - c * (D + 1);
+            s_fin[i] = sres;
             if (c < k) {
-                if (j < D) L.sums[c * D + j] = sres;
-                else L.counts[c] = (long long)sres;
+                if (j < D) {
+                    if (L.sums != nullptr) L.sums[c * D + j] = sres;
+                    if (L.packed != nullptr) L.packed[c * D + j] = sres;
+                } else {
+                    if (L.counts != nullptr) L.counts[c] = (long long)sres;
+                    if (L.packed != nullptr) L.packed[k * D + c] = sres;
+                }
             }
         }
     }
-    if (tid == 0) *L.counter = 0u;
+    __syncthreads();
+    if (tid == 0) {
+        *L.counter = 0u;
+        if (L.centers_rw != nullptr)   // every CTA has long copied the centres: update them in place
+            km_lloyd_update(k, D, L.kind, s_fin, L.centers_rw, L.state, L.stop_dist, L.max_iter);
+    }
+}
+
+// sharded Lloyd loop: the update alone, on the all-reduced [sums | counts] (one thread)
+__global__ void kmeans_update_kernel(const double* __restrict__ packed, double* centers, int k, int d, int kind,
+                                     long long* state, double stop_dist, long long max_iter) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (state[0] != 0) return;
+    double fin[16 * 5];
+    for (int c = 0; c < k; ++c) {
+        for (int j = 0; j < d; ++j) fin[c * (d + 1) + j] = packed[c * d + j];
+        fin[c * (d + 1) + d] = packed[k * d + c];
+    }
+    km_lloyd_update(k, d, kind, fin, centers, state, stop_dist, max_iter);
 }
 
 __global__ void minmax_kernel(const double* __restrict__ x, long long n, double* __restrict__ partials,
@@ -404,6 +503,35 @@ __global__ void minmax_kernel(const double* __restrict__ x, long long n, double*
     out2[0] = lo;
     out2[1] = hi;
     *counter = 0u;
+}
+
+// utils/kmeans.py:9-40 as a plain distance evaluation (the module's iou / iou_dist /
+// euclidean_dist called directly on data-sized arrays): outer = every centre against every point
+// -> (k, M), the broadcast of kmeans.py:79; otherwise element by element -> (M).
+// what: 0 iou (area ratio), 1 iou_dist = 1 - iou, 2 euclidean
+__global__ void kmeans_dist_kernel(const double* __restrict__ a, long long na, const double* __restrict__ b,
+                                   long long nb, int d, int what, int outer, double* __restrict__ out) {
+    const long long total = outer ? na * nb : nb;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long ia = outer ? t / nb : t, ib = outer ? t - ia * nb : t;
+        const double* pa = a + ia * d;
+        const double* pb = b + ib * d;
+        double v;
+        if (what == 2) {
+            double sq = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double df = pa[j] - pb[j];
+                sq = __dadd_rn(sq, __dmul_rn(df, df));
+            }
+            v = sqrt(sq);
+        } else {
+            const double ca = __dmul_rn(pa[0], pa[1]), da = __dmul_rn(pb[0], pb[1]);
+            v = km_np_min(ca, da) / km_np_max(ca, da);
+            if (what == 1) v = 1.0 - v;
+        }
+        out[t] = v;
+    }
 }
 
 constexpr int kKmGrid = kNumSMs * 4;  // upper bound of the launch grid (partials sizing)
@@ -525,6 +653,11 @@ extern "C" int yb_kmeans_assign(const double* data, int64_t n_points, int n_dim,
     L.partials = reinterpret_cast<double*>(workspace);
     L.counter = reinterpret_cast<unsigned int*>(
         (char*)workspace + align_up((size_t)kKmGrid * 16 * (n_dim + 1) * sizeof(double), 256));
+    L.state = nullptr;
+    L.packed = nullptr;
+    L.centers_rw = nullptr;
+    L.stop_dist = 0.0;
+    L.max_iter = 0;
     YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
     switch (n_dim) {
         case 1: return launch_km_d<1>(L, stream);
@@ -532,6 +665,95 @@ extern "C" int yb_kmeans_assign(const double* data, int64_t n_points, int n_dim,
         case 3: return launch_km_d<3>(L, stream);
         default: return launch_km_d<4>(L, stream);
     }
+}
+
+extern "C" int yb_kmeans_dist(const double* a, int64_t na, const double* b, int64_t nb, int n_dim, int what,
+                              int outer, double* out, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (na < 0 || nb < 0 || n_dim < 1 || n_dim > 7) return YB_E_SHAPE;   // sums of < 8 terms: sequential in NumPy too
+    if (what < 0 || what > 2) return YB_E_PARAM;
+    if (what != 2 && n_dim < 2) return YB_E_SHAPE;
+    if (!outer && na != nb) return YB_E_SHAPE;
+    const long long total = outer ? na * nb : nb;
+    if (total == 0) return YB_OK;
+    if (a == nullptr || b == nullptr || out == nullptr) return YB_E_NULL;
+    const int blocks = (int)min((long long)kNumSMs * 8, (total + 255) / 256);
+    kmeans_dist_kernel<<<blocks, 256, 0, stream>>>(a, na, b, nb, n_dim, what, outer, out);
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
+}
+
+extern "C" size_t yb_kmeans_state_bytes(int k, int n_dim) {
+    if (k < 1 || k > 16 || n_dim < 1 || n_dim > 4) return 0;
+    return sizeof(long long) * (size_t)(4 + YB_KMEANS_HIST + k * (n_dim + 1));
+}
+
+extern "C" int yb_kmeans_lloyd_step(const double* data, int64_t n_points, int n_dim, double* centers, int k,
+                                    int dist_kind, double stop_dist, int64_t max_iternum, int64_t* state,
+                                    double* packed, int32_t* assign, void* workspace, size_t workspace_bytes,
+                                    yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (centers == nullptr || state == nullptr || workspace == nullptr) return YB_E_NULL;
+    if (n_points > 0 && data == nullptr) return YB_E_NULL;
+    if (n_points < 0 || k < 1 || k > 16 || n_dim < 1 || n_dim > 4) return YB_E_SHAPE;
+    if (dist_kind != YB_DIST_IOU && dist_kind != YB_DIST_EUCLID) return YB_E_PARAM;
+    if (dist_kind == YB_DIST_IOU && n_dim < 2) return YB_E_SHAPE;
+    if (((uintptr_t)data & 7) || ((uintptr_t)state & 7)) return YB_E_ALIGN;
+    if (workspace_bytes < yb_kmeans_workspace_bytes(n_points, k, n_dim) || ((uintptr_t)workspace & 255))
+        return YB_E_WORKSPACE;
+    KmLaunch L;
+    L.data = data;
+    L.n = n_points;
+    L.centers = centers;
+    L.k = k;
+    L.d = n_dim;
+    L.kind = dist_kind;
+    L.bulk_ok = (((uintptr_t)data & 15) == 0) ? 1 : 0;
+    L.assign = assign;
+    L.sums = nullptr;
+    L.counts = nullptr;
+    L.partials = reinterpret_cast<double*>(workspace);
+    // the last CTA of every launch leaves the counter at zero: the caller zeroes the workspace ONCE
+    // (yb_kmeans_lloyd_init) and the loop needs no memset between iterations
+    L.counter = reinterpret_cast<unsigned int*>(
+        (char*)workspace + align_up((size_t)kKmGrid * 16 * (n_dim + 1) * sizeof(double), 256));
+    L.state = reinterpret_cast<long long*>(state);
+    L.packed = packed;
+    L.centers_rw = (packed == nullptr) ? centers : nullptr;
+    L.stop_dist = stop_dist;
+    L.max_iter = max_iternum;
+    switch (n_dim) {
+        case 1: return launch_km_d<1>(L, stream);
+        case 2: return launch_km_boxes(L, stream);
+        case 3: return launch_km_d<3>(L, stream);
+        default: return launch_km_d<4>(L, stream);
+    }
+}
+
+extern "C" int yb_kmeans_lloyd_init(int64_t* state, int k, int n_dim, void* workspace, size_t workspace_bytes,
+                                    yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (state == nullptr || workspace == nullptr) return YB_E_NULL;
+    const size_t sb = yb_kmeans_state_bytes(k, n_dim);
+    if (sb == 0) return YB_E_SHAPE;
+    if (workspace_bytes < yb_kmeans_workspace_bytes(0, k, n_dim) || ((uintptr_t)workspace & 255)) return YB_E_WORKSPACE;
+    YB_CUDA_TRY(cudaMemsetAsync(state, 0, sb, stream));
+    unsigned int* counter = reinterpret_cast<unsigned int*>(
+        (char*)workspace + align_up((size_t)kKmGrid * 16 * (n_dim + 1) * sizeof(double), 256));
+    YB_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned int), stream));
+    return YB_OK;
+}
+
+extern "C" int yb_kmeans_lloyd_update(const double* packed, double* centers, int k, int n_dim, int dist_kind,
+                                      double stop_dist, int64_t max_iternum, int64_t* state, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (packed == nullptr || centers == nullptr || state == nullptr) return YB_E_NULL;
+    if (k < 1 || k > 16 || n_dim < 1 || n_dim > 4) return YB_E_SHAPE;
+    if (dist_kind != YB_DIST_IOU && dist_kind != YB_DIST_EUCLID) return YB_E_PARAM;
+    kmeans_update_kernel<<<1, 32, 0, stream>>>(packed, centers, k, n_dim, dist_kind,
+                                               reinterpret_cast<long long*>(state), stop_dist, max_iternum);
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
 }
 
 extern "C" int yb_minmax_f64(const double* data, int64_t n, double* out2, void* workspace,

@@ -471,6 +471,69 @@ def kmeans_assign(data, centers, dist_kind=N.YB_DIST_IOU, want_assign=False):
     return assign, sums, counts
 
 
+def kmeans_dist(a, b, what, outer):
+    """utils/kmeans.py:9-40 on CUDA tensors: a (na,d), b (nb,d) f64 -> (na,nb) if outer else (nb,).
+    what: 0 iou, 1 iou_dist, 2 euclidean_dist."""
+    require_cuda(a, b)
+    if a.dtype != _F64 or b.dtype != _F64:
+        raise N.YoloB200Error("kmeans distances need float64")
+    dev = a.device
+    with torch.cuda.device(dev):
+        out = torch.empty((a.shape[0], b.shape[0]) if outer else (b.shape[0],), dtype=_F64, device=dev)
+        N.check(N.lib.yb_kmeans_dist(_ptr(a), a.shape[0], _ptr(b), b.shape[0], a.shape[1], int(what), int(bool(outer)),
+                                     _ptr(out), _stream()), "yb_kmeans_dist")
+    return out
+
+
+class KMeansLloyd:
+    """Device-resident Lloyd loop (yb_kmeans_lloyd_init / _step / _update): the boxes, the centres and
+    the loop state stay on the GPU; ``step()`` queues one iteration without touching the host."""
+
+    def __init__(self, data, centers, dist_kind, stop_dist, max_iternum, sharded=False):
+        require_cuda(data, centers)
+        if data.dtype != _F64 or centers.dtype != _F64:
+            raise N.YoloB200Error("kmeans needs float64")
+        self.data, self.centers = data, centers
+        self.k, self.d = centers.shape
+        self.kind, self.stop, self.max_iter = int(dist_kind), float(stop_dist), int(max_iternum)
+        dev = data.device
+        with torch.cuda.device(dev):
+            sb = N.lib.yb_kmeans_state_bytes(self.k, self.d)
+            if sb == 0:
+                raise ValueError("unsupported k / n_dim (k <= 16, n_dim <= 4)")
+            self.state = torch.empty(sb // 8, dtype=_I64, device=dev)
+            self.ws_bytes = N.lib.yb_kmeans_workspace_bytes(data.shape[0], self.k, self.d)
+            self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=dev)
+            self.ws_ptr = self.ws.data_ptr() + ((-self.ws.data_ptr()) % 256)
+            self.packed = torch.zeros(self.k * (self.d + 1), dtype=_F64, device=dev) if sharded else None
+            N.check(N.lib.yb_kmeans_lloyd_init(_ptr(self.state), self.k, self.d, C.c_void_p(self.ws_ptr), self.ws_bytes,
+                                               _stream()), "yb_kmeans_lloyd_init")
+
+    def step(self, assign=None):
+        """The assignment pass (+ the update when not sharded) of one iteration."""
+        N.check(N.lib.yb_kmeans_lloyd_step(_ptr(self.data), self.data.shape[0], self.d, _ptr(self.centers), self.k,
+                                           self.kind, self.stop, self.max_iter, _ptr(self.state), _ptr(self.packed),
+                                           _ptr(assign), C.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
+                "yb_kmeans_lloyd_step")
+
+    def update(self):
+        """Sharded loop: the update on the all-reduced ``packed`` sums / counts."""
+        N.check(N.lib.yb_kmeans_lloyd_update(_ptr(self.packed), _ptr(self.centers), self.k, self.d, self.kind,
+                                             self.stop, self.max_iter, _ptr(self.state), _stream()),
+                "yb_kmeans_lloyd_update")
+
+    def read_state(self):
+        """(status, completed updates, loss history array, saved sums (k,d), saved counts (k,)) - one sync."""
+        host = self.state.cpu().numpy()
+        hist = host[4:4 + N.YB_KMEANS_HIST].view(np.float64)
+        saved = host[4 + N.YB_KMEANS_HIST:].view(np.float64).reshape(self.k, self.d + 1)
+        return int(host[0]), int(host[1]), hist, saved[:, :self.d].copy(), saved[:, self.d].copy()
+
+    def resume(self, status, completed):
+        """Host finished an update itself (empty-cluster redraw): write status / counter back."""
+        self.state[0:2].copy_(torch.tensor([status, completed], dtype=_I64), non_blocking=False)
+
+
 def minmax(data):
     require_cuda(data)
     if data.dtype != _F64:

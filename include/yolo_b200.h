@@ -23,7 +23,7 @@ extern "C" {
 
 typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
 
-#define YB_ABI_VERSION 1
+#define YB_ABI_VERSION 2
 #define YB_MAX_BOXES 16  /* anchors per cell */
 #define YB_MAX_SCALES 4  /* FPN outputs per fused loss launch */
 #define YB_LOSS_TERMS 8  /* doubles per scale in terms_out */
@@ -344,6 +344,17 @@ int yb_map_accumulate(const double* det_rows, const int64_t* det_seg_offsets, co
                       const int64_t* gt_base, double* conf, int64_t* gt_id, uint8_t* flag,
                       int32_t* cls, int64_t* class_offsets, uint64_t* score_acc, void* workspace,
                       size_t workspace_bytes, yb_stream_t stream);
+
+/* Append the records of one batch (the first *n_src entries of conf / gt_id / flag / cls as
+ * yb_map_accumulate left them; n_src = its class_offsets + class_num, on the device) to the
+ * caller's record arrays at position *total (device), then *total += *n_src - all on the device,
+ * so a stream of batches accumulates without a host round trip.  Entries beyond dst_capacity are
+ * dropped while *total keeps counting: the caller compares it with the capacity at the end.
+ * counter: one uint32, zero before the first call (left zero by every call). */
+int yb_map_append(const double* conf, const int64_t* gt_id, const uint8_t* flag, const int32_t* cls,
+                  const int64_t* n_src, int64_t src_capacity, double* conf_dst, int64_t* gt_id_dst,
+                  uint8_t* flag_dst, int32_t* cls_dst, int64_t dst_capacity, int64_t* total,
+                  uint32_t* counter, yb_stream_t stream);
 
 /* Final PR pass, utils/measurement.py:297-321: sort all triples by (class asc, confidence
  * desc, later position first), find the first occurrence of every matched ground truth and

@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_binding_covers_the_header(lib):
     from tf2_yolo_b200 import _native
     assert sorted(_native.SIGNATURES) == declared_symbols()
-    assert _native.lib.yb_abi_version() == 1
+    assert _native.lib.yb_abi_version() == 2
     assert _native.status_string(0) == "ok"
     assert "workspace" in _native.status_string(-4)
     assert _native.lib.yb_loss_workspace_bytes(3) > 0

@@ -99,3 +99,51 @@ def test_rank_offsets_and_varlen_gather():
         assert r[1] == [9, 0, 15]
         assert r[2] == [0, 1, 2, 3, 100, 101, 102, 103, 104, 105, 106]
         assert r[3] == [1, 1]
+
+
+def _route_rank(rank):
+    """Each rank holds records of 5 classes in two class-major chunks; class c must end on rank
+    c % 2 with its records in (rank, chunk, local) order."""
+    C = 5
+    rng = np.random.default_rng(100 + rank)
+    blocks, segs, base = [], [], 0
+    for chunk in range(2):
+        counts = rng.integers(0, 4, C)
+        counts[rank] = 0                       # an empty class per rank
+        co = np.concatenate([[0], np.cumsum(counts)])
+        segs.append(co + base)
+        for c in range(C):
+            for j in range(counts[c]):
+                blocks.append((c, 1000 * rank + 100 * chunk + 10 * c + j))
+        base += co[-1]
+    cls = torch.tensor([b[0] for b in blocks], dtype=torch.int32)
+    tag = torch.tensor([b[1] for b in blocks], dtype=torch.int64)
+    conf = tag.to(torch.float64) / 7.0
+    flag = (tag % 2).to(torch.uint8)
+    out = ydist.route_records_by_class((conf, tag, flag, cls), np.stack(segs), C)
+    return [t.tolist() for t in out]
+
+
+def test_records_are_routed_to_their_class_owner_in_image_order():
+    res = _run(_route_rank)
+    all_tags = {}
+    for rank in range(WORLD):
+        conf, tag, flag, cls, owned = res[rank]
+        assert all(c % WORLD == rank for c in cls)                      # only classes this rank owns
+        assert [t / 7.0 for t in tag] == conf and [t % 2 for t in tag] == flag   # the arrays travel together
+        for c in set(cls):
+            mine = [t for t, k in zip(tag, cls) if k == c]
+            assert mine == sorted(mine), (rank, c)                       # (rank, chunk, local) order kept
+            assert owned[c] == len(mine)
+            all_tags[c] = mine
+        assert all(owned[c] == 0 for c in range(5) if c % WORLD != rank)
+    # nothing lost: every record of every rank arrived exactly once
+    total = sum(len(v) for v in all_tags.values())
+    sent = 0
+    for rank in range(WORLD):
+        rng = np.random.default_rng(100 + rank)
+        for chunk in range(2):
+            counts = rng.integers(0, 4, 5)
+            counts[rank] = 0
+            sent += int(counts.sum())
+    assert total == sent

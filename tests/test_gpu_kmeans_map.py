@@ -193,3 +193,45 @@ def test_reference_distance_functions_and_data_sized_helpers():
     assert np.array_equal(km.iou_dist(data, data[::-1]), okm.iou_dist(data, data[::-1]))     # element by element
     x3 = rng.uniform(0, 1, (40000, 3))
     assert np.array_equal(km.euclidean_dist(x3, x3[::-1]), okm.euclidean_dist(x3, x3[::-1]))
+
+
+def test_map_match_non_finite_boxes():
+    """NaN / Inf / zero-size boxes: np.maximum / np.minimum propagate NaN into the IoU, np.max
+    then returns NaN (never >= threshold) and np.argmax the FIRST NaN (measurement.py:270-277)."""
+    rng = np.random.default_rng(9)
+    C, n_img = 3, 4
+    gts, dets, g_off, d_off = [], [], [0], [0]
+    for i in range(n_img):
+        g = np.column_stack([rng.uniform(0.2, 0.8, (6, 2)), rng.uniform(0.1, 0.4, (6, 2)), np.ones(6),
+                             rng.integers(0, C, 6), np.ones(6)])
+        d = np.column_stack([rng.uniform(0.2, 0.8, (12, 2)), rng.uniform(0.1, 0.4, (12, 2)), rng.uniform(0.3, 1, 12),
+                             rng.integers(0, C, 12), rng.uniform(0.3, 1, 12)])
+        gts.append(g)
+        dets.append(d)
+    gts[0][1, 2] = np.nan                 # NaN ground-truth width
+    gts[0][3, 0] = np.inf                 # infinite centre
+    gts[1][0, 2:4] = 0.0                  # zero-size ground truth
+    dets[1][2, 2:4] = 0.0                 # zero-size detection
+    dets[2][5, 1] = np.nan                # NaN detection
+    dets[3][0, 3] = np.inf
+    for g, d in zip(gts, dets):
+        g_off.append(g_off[-1] + len(g))
+        d_off.append(d_off[-1] + len(d))
+    gt_rows, det_rows = np.concatenate(gts), np.concatenate(dets)
+    dev = torch.device("cuda")
+    bi, bg, counts = engine.map_match(torch.from_numpy(gt_rows).to(dev), torch.tensor(g_off, device=dev),
+                                      torch.from_numpy(det_rows).to(dev), torch.tensor(d_off, device=dev), C)
+    bi, bg = bi.cpu().numpy(), bg.cpu().numpy()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(n_img):
+            for j in range(len(dets[i])):
+                d = dets[i][j]
+                same = gts[i][gts[i][:, 5].astype(int) == int(d[5])]
+                k = d_off[i] + j
+                if len(same) == 0:
+                    assert bg[k] == -1
+                    continue
+                iou = ot.pair_iou(same[:, None, :5], d[None, None, :5], 1)[:, 0]
+                want, arg = np.max(iou), int(np.argmax(iou))
+                assert bg[k] == arg, (i, j)
+                assert (np.isnan(want) and np.isnan(bi[k])) or bi[k] == want, (i, j)

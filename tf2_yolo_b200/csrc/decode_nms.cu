@@ -147,20 +147,46 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         box = cell + b * ((L.version == 1) ? 5 : 5 + C);
         prob = (L.version == 1) ? cell + 5 * L.B[s] : box + 5;
     };
-    for (int q = warp; q < nh; q += kFusedWarps) {
+    // Several boxes per warp iteration, every global load of all of them issued before the first use: the
+    // phase is a chain of HBM round trips (the head tensors were streamed long ago), so what counts
+    // is how many loads are in flight, not how few instructions run.
+    auto load_scores = [&](int q, float& c, float (&pv)[kFusedMaxClassWords]) {
         const float *box, *prob;
         int s;
         box_ptrs(q, box, prob, s);
-        const float c = box[4];
-        int cnt = 0;
-        for (int w = 0; w < CW; ++w) {
+#pragma unroll
+        for (int w = 0; w < kFusedMaxClassWords; ++w) {
             const int k = w * 32 + lane;
-            const bool hit = (k < C) && (__fmul_rn(c, prob[k]) >= thr);
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (lane == 0) s_mask[q * CW + w] = m;
-            cnt += __popc(m);
+            pv[w] = (w < CW && k < C) ? __ldg(prob + k) : 0.f;
+        }
+        c = __ldg(box + 4);
+    };
+    auto count_hits = [&](int q, float c, const float (&pv)[kFusedMaxClassWords]) {
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kFusedMaxClassWords; ++w) {
+            if (w < CW) {
+                const int k = w * 32 + lane;
+                const bool hit = (k < C) && (__fmul_rn(c, pv[w]) >= thr);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) s_mask[q * CW + w] = m;
+                cnt += __popc(m);
+            }
         }
         if (lane == 0) s_cnt[q] = (unsigned short)min(cnt, 65535);
+    };
+    for (int q0 = warp; q0 < nh; q0 += 4 * kFusedWarps) {     // four boxes of a warp in flight
+        const int q1 = q0 + kFusedWarps, q2 = q1 + kFusedWarps, q3 = q2 + kFusedWarps;
+        float c0, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+        float pv0[kFusedMaxClassWords], pv1[kFusedMaxClassWords], pv2[kFusedMaxClassWords], pv3[kFusedMaxClassWords];
+        load_scores(q0, c0, pv0);
+        if (q1 < nh) load_scores(q1, c1, pv1);
+        if (q2 < nh) load_scores(q2, c2, pv2);
+        if (q3 < nh) load_scores(q3, c3, pv3);
+        count_hits(q0, c0, pv0);
+        if (q1 < nh) count_hits(q1, c1, pv1);
+        if (q2 < nh) count_hits(q2, c2, pv2);
+        if (q3 < nh) count_hits(q3, c3, pv3);
     }
     __syncthreads();
     // ---- exclusive scan of the counts -> first row of every box ------------------------------------
@@ -196,25 +222,35 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
             const float *box, *prob;
             int s;
             box_ptrs(q, box, prob, s);
+            float pv[kFusedMaxClassWords];
+#pragma unroll
+            for (int w = 0; w < kFusedMaxClassWords; ++w) {
+                const int k = w * 32 + lane;
+                pv[w] = (w < CW && k < C) ? __ldg(prob + k) : 0.f;   // L1 / L2 hits: read a moment ago
+            }
+            const float f0 = __ldg(box), f1 = __ldg(box + 1), f2 = __ldg(box + 2), f3 = __ldg(box + 3), c = __ldg(box + 4);
             const unsigned cell = s_mem[s_ord[q]] % (unsigned)L.cells[s];
             const int yi = (int)(cell / (unsigned)L.gw[s]), xi = (int)(cell - (unsigned)yi * (unsigned)L.gw[s]);
-            const float c = box[4];
-            const double bx = ((double)xi + (double)box[0]) / (double)L.gw[s];
-            const double by = ((double)yi + (double)box[1]) / (double)L.gh[s];
-            const double bw = (double)box[2], bh = (double)box[3], bc = (double)c;
+            const double bx = ((double)xi + (double)f0) / (double)L.gw[s];
+            const double by = ((double)yi + (double)f1) / (double)L.gh[s];
+            const double bw = (double)f2, bh = (double)f3, bc = (double)c;
             unsigned r = s_off[q];
-            for (int w = 0; w < CW; ++w) {
-                const unsigned m = s_mask[q * CW + w];
-                if ((m >> lane) & 1u) {
-                    const int k = w * 32 + lane;
-                    double* o = s_rows + (size_t)(r + __popc(m & lt_mask)) * 7;
-                    o[0] = bx; o[1] = by; o[2] = bw; o[3] = bh; o[4] = bc;
-                    o[5] = (double)k;
-                    o[6] = (double)prob[k];
-                    s_cls[r + __popc(m & lt_mask)] = (unsigned short)k;
-                    atomicAdd(&s_ccount[k], 1u);
+#pragma unroll
+            for (int w = 0; w < kFusedMaxClassWords; ++w) {
+                if (w < CW) {
+                    const unsigned m = s_mask[q * CW + w];
+                    if ((m >> lane) & 1u) {
+                        const int k = w * 32 + lane;
+                        const unsigned at = r + __popc(m & lt_mask);
+                        double* o = s_rows + (size_t)at * 7;
+                        o[0] = bx; o[1] = by; o[2] = bw; o[3] = bh; o[4] = bc;
+                        o[5] = (double)k;
+                        o[6] = (double)pv[w];
+                        s_cls[at] = (unsigned short)k;
+                        atomicAdd(&s_ccount[k], 1u);
+                    }
+                    r += __popc(m);
                 }
-                r += __popc(m);
             }
         }
     }

@@ -3,20 +3,16 @@
 // (utils/measurement.py:252-283 PRfunc, :104-130 create_score_mat), float64 in the
 // reference's operation order (utils/tools.py:649-666; -fmad=false).
 #include "common.cuh"
+#include "nms_pair.cuh"
 #include "scan.cuh"
 
 namespace yb {
 
-constexpr double kMapEps = 1e-07;
-
+// the IoU of utils/tools.py:649-666 exactly as the NMS kernels evaluate it: np.maximum / np.minimum
+// PROPAGATE NaN (fmax / fmin would drop it), so a non-finite box yields the NaN NumPy yields
 __device__ __forceinline__ double map_iou(double tx, double ty, double tw, double th, double px,
                                           double py, double pw, double ph) {
-    const double thw = tw / 2.0, thh = th / 2.0, phw = pw / 2.0, phh = ph / 2.0;
-    const double iw = fmax(fmin(px + phw, tx + thw) - fmax(px - phw, tx - thw), 0.0);
-    const double ih = fmax(fmin(py + phh, ty + thh) - fmax(py - phh, ty - thh), 0.0);
-    const double inter = iw * ih;
-    const double uni = pw * ph + tw * th - inter;
-    return inter / (uni + kMapEps);
+    return pair_iou<1>(tx, ty, tw, th, px, py, pw, ph);
 }
 
 // one thread per detection row; ground truths of an image are few (tens)
@@ -37,11 +33,18 @@ __global__ void map_match_kernel(const double* __restrict__ gt, const long long*
         const long long cls = (long long)d[5];
         double best = -1.0;
         int arg = -1, seen = 0;
+        bool nan_seen = false;
         for (long long g = gt_off[lo]; g < gt_off[lo + 1]; ++g) {
             const double* t = gt + g * 7;
             if ((long long)t[5] != cls) continue;
             const double v = map_iou(t[0], t[1], t[2], t[3], d[0], d[1], d[2], d[3]);
-            if (arg < 0 || v > best) {  // first maximum, like np.argmax
+            if (v != v) {               // np.max -> NaN, np.argmax -> the FIRST NaN
+                if (!nan_seen) {
+                    nan_seen = true;
+                    best = v;
+                    arg = seen;
+                }
+            } else if (!nan_seen && (arg < 0 || v > best)) {  // first maximum, like np.argmax
                 best = v;
                 arg = seen;
             }
@@ -372,6 +375,34 @@ __global__ void pr_flags_kernel(const ulonglong2* __restrict__ rec, long long n,
     }
 }
 
+// Append the valid prefix of one chunk's records (count read on the device) to the rank's record
+// arrays at the running total (read and advanced on the device): no host round trip per chunk.
+__global__ void map_append_kernel(const double* __restrict__ conf, const long long* __restrict__ gid,
+                                  const unsigned char* __restrict__ flag, const int* __restrict__ cls,
+                                  const long long* __restrict__ n_src, double* __restrict__ conf_dst,
+                                  long long* __restrict__ gid_dst, unsigned char* __restrict__ flag_dst,
+                                  int* __restrict__ cls_dst, long long dst_cap, long long* __restrict__ total,
+                                  unsigned int* __restrict__ done) {
+    const long long n = *n_src, base = *total;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long d = base + i;
+        if (d < dst_cap) {
+            conf_dst[d] = conf[i];
+            gid_dst[d] = gid[i];
+            flag_dst[d] = flag[i];
+            cls_dst[d] = cls[i];
+        }
+    }
+    // the last CTA to finish advances the total (every CTA has read it by then)
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1) {
+        *total = base + n;   // may exceed dst_cap: the caller checks and regrows
+        *done = 0u;
+    }
+}
+
 static long long next_pow2(long long n) {
     long long p = kSortTile;
     while (p < n) p <<= 1;
@@ -418,12 +449,33 @@ extern "C" int yb_map_accumulate(const double* det_rows, const int64_t* det_seg_
     if (rc != 0) return rc;
     const int wblocks = (int)min((long long)kNumSMs * 8, (n * 32 + threads - 1) / threads);
     const size_t topk_smem = (size_t)(threads / 32) * kTopCap * (sizeof(unsigned long long) + sizeof(unsigned short));
-    YB_CUDA_TRY(cudaFuncSetAttribute(map_triples_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)topk_smem));
+    static SmemRaised done;
+    YB_CUDA_TRY(raise_dynamic_smem_once(map_triples_kernel, (int)topk_smem, &done));
     map_triples_kernel<<<wblocks, threads, topk_smem, stream>>>(
         det_rows, reinterpret_cast<const long long*>(det_seg_offsets), best_iou, best_gt, gt_class_counts, n_img,
         class_num, iou_threshold, max_per_img, reinterpret_cast<const long long*>(gt_base), out_pos_T, gt_pos_T,
         conf, reinterpret_cast<long long*>(gt_id), flag, cls, reinterpret_cast<long long*>(class_offsets),
         reinterpret_cast<unsigned long long*>(score_acc));
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
+}
+
+extern "C" int yb_map_append(const double* conf, const int64_t* gt_id, const uint8_t* flag, const int32_t* cls,
+                             const int64_t* n_src, int64_t src_capacity, double* conf_dst, int64_t* gt_id_dst,
+                             uint8_t* flag_dst, int32_t* cls_dst, int64_t dst_capacity, int64_t* total,
+                             uint32_t* counter, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_src == nullptr || total == nullptr || counter == nullptr) return YB_E_NULL;
+    if (src_capacity < 0 || dst_capacity < 0) return YB_E_SHAPE;
+    if (src_capacity > 0 && (conf == nullptr || gt_id == nullptr || flag == nullptr || cls == nullptr)) return YB_E_NULL;
+    if (dst_capacity > 0 && (conf_dst == nullptr || gt_id_dst == nullptr || flag_dst == nullptr || cls_dst == nullptr))
+        return YB_E_NULL;
+    const int threads = 256;
+    const int blocks = (int)max(1LL, min((long long)kNumSMs * 4, ((long long)src_capacity + threads - 1) / threads));
+    map_append_kernel<<<blocks, threads, 0, stream>>>(
+        conf, reinterpret_cast<const long long*>(gt_id), flag, cls, reinterpret_cast<const long long*>(n_src), conf_dst,
+        reinterpret_cast<long long*>(gt_id_dst), flag_dst, cls_dst, dst_capacity, reinterpret_cast<long long*>(total),
+        counter);
     YB_CUDA_TRY(cudaGetLastError());
     return YB_OK;
 }

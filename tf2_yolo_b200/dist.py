@@ -4,8 +4,9 @@ no data-path collective; these helpers carry the only exchanges there are (SURVE
 
 * loss      : all-reduce of the per-scale scalars (each rank divides by the GLOBAL batch)
 * k-means   : all-reduce of k*(d+1) partial sums per Lloyd iteration, min/max once
-* PR / mAP  : all-gather of per-class ground-truth counts (to offset gt ids) and of the
-              variable-length (conf, gt_id, flag, class) triples
+* PR / mAP  : all-gather of per-class ground-truth counts (to offset gt ids); the variable-length
+              (conf, gt_id, flag, class) records go to the rank that owns their class (class % world,
+              all-to-all), so the sort + scan of the PR curves is split 1/world per rank
 """
 import torch
 import torch.distributed as dist
@@ -78,3 +79,49 @@ def gather_varlen(t, group=None):
     bufs = [torch.zeros_like(pad) for _ in range(n)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+def route_records_by_class(arrays, segments, class_num, group=None):
+    """All-to-all of per-class records: class c goes to rank c % world.
+
+    ``arrays``: this rank's record arrays (same length), laid out as chunks whose blocks are
+    class-major; ``segments`` (n_chunks, C+1) int64 ndarray locates class c of chunk k at
+    [segments[k, c], segments[k, c+1]).  Returns (arrays of the records this rank owns, ordered
+    source rank -> class -> chunk, i.e. every class keeps the global image order of its records;
+    class_counts (C,) int64 tensor: global record count of the owned classes, 0 elsewhere)."""
+    n, r = world(group)
+    dev = arrays[0].device
+    C = class_num
+    # send order: destination rank, then class, then chunk
+    pieces = [[] for _ in arrays]
+    send_counts = []
+    per_class = torch.zeros(C, dtype=torch.int64)
+    for d in range(n):
+        cnt = 0
+        for c in range(d, C, n):
+            for k in range(segments.shape[0]):
+                a, b = int(segments[k, c]), int(segments[k, c + 1])
+                if b > a:
+                    for i, arr in enumerate(arrays):
+                        pieces[i].append(arr[a:b])
+                    cnt += b - a
+                    per_class[c] += b - a
+        send_counts.append(cnt)
+    send = [torch.cat(p) if p else arr[:0] for p, arr in zip(pieces, arrays)]
+    per_class = per_class.to(dev)
+    if n == 1:
+        return (*send, per_class)
+    dist.all_reduce(per_class, group=group)            # global records per class
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
+    rc = torch.empty_like(sc)
+    dist.all_to_all_single(rc, sc, group=group)
+    recv_counts = [int(x) for x in rc.cpu()]
+    out = []
+    for t in send:
+        buf = torch.empty(sum(recv_counts), dtype=t.dtype, device=dev)
+        dist.all_to_all_single(buf, t.contiguous(), output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                               group=group)
+        out.append(buf)
+    owned = torch.zeros(C, dtype=torch.int64, device=dev)
+    owned[r::n] = per_class[r::n]
+    return (*out, owned)

@@ -589,6 +589,17 @@ def map_accumulate(det_rows, seg_offsets, best_iou, best_gt, gt_counts, class_nu
     return conf, gid, flag, cls, coff
 
 
+def map_append(chunk, n_src, dst, total, counter):
+    """Append the first ``*n_src`` records of ``chunk`` = (conf, gid, flag, cls) to ``dst`` (same
+    four arrays, larger) at the device-side running ``total`` and advance it (yb_map_append)."""
+    conf, gid, flag, cls = chunk
+    dconf, dgid, dflag, dcls = dst
+    with torch.cuda.device(conf.device):
+        N.check(N.lib.yb_map_append(_ptr(conf), _ptr(gid), _ptr(flag), _ptr(cls), _ptr(n_src), conf.shape[0],
+                                    _ptr(dconf), _ptr(dgid), _ptr(dflag), _ptr(dcls), dconf.shape[0], _ptr(total),
+                                    _ptr(counter), _stream()), "yb_map_append")
+
+
 def pr_curve(conf, cls, gt_id, flag, gt_table_base, n_gt_total):
     """Sort by (class, confidence desc, later position first) and count distinct true positives.
     Returns (order i64[D], tp_cum i64[D+1], tpp_cum i64[D+1])."""

@@ -59,73 +59,185 @@ def _nms_args(nms_mode, nms_threshold):
 
 
 class _Accumulated:
-    __slots__ = ("conf", "gid", "flag", "cls", "class_counts", "gts", "score")
+    __slots__ = ("conf", "gid", "flag", "cls", "class_counts", "gts", "score", "owned")
+
+
+class _Phase1:
+    """Per-rank accumulation over chunks of images (utils/measurement.py:210-292, batched): decode
+    ground truth and predictions, NMS, per-class IoU matching, per-image top-k; the records
+    (confidence, ground-truth id, true-positive flag, class) of every chunk are appended to
+    rank-level arrays ON THE DEVICE.  After the first chunk (which measures the row density) no
+    chunk makes the host wait: row capacities come from the measured density and every
+    "did it fit" question is answered once, in ``finish``."""
+
+    def __init__(self, class_num, conf_threshold, nms_mode, nms_threshold, iou_threshold, max_per_img, version,
+                 nms_sigma, dev, gt_base):
+        self.C, self.conf_thr, self.nms_mode, self.iou_thr = class_num, conf_threshold, nms_mode, iou_threshold
+        self.thr, self.iou_mode = _nms_args(nms_mode, nms_threshold)
+        self.max_per_img, self.version, self.sigma, self.dev = max_per_img, version, nms_sigma, dev
+        self.score = torch.zeros(3 * class_num, dtype=torch.int64, device=dev)
+        self.gt_base = gt_base.clone()
+        self.class_counts = torch.zeros(class_num, dtype=torch.int64, device=dev)
+        self.total = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.dst = None
+        self.coffs = []            # per chunk: class offsets of its records (device, C+1)
+        self.checks = []           # (device scalar, capacity, what): verified in finish()
+        self.det_density = None    # decode rows per image of the first chunk
+        self.n_img = 0
+
+    def _grow(self, need):
+        cap = 0 if self.dst is None else self.dst[0].shape[0]
+        if need <= cap:
+            return
+        new_cap = max(need, 2 * cap, 1 << 16)
+        dev = self.dev
+        new = (torch.empty(new_cap, dtype=torch.float64, device=dev), torch.empty(new_cap, dtype=torch.int64, device=dev),
+               torch.empty(new_cap, dtype=torch.uint8, device=dev), torch.empty(new_cap, dtype=torch.int32, device=dev))
+        if self.dst is not None:   # the prefix written so far (all of it: capacity never shrinks)
+            for d, o in zip(new, self.dst):
+                d[:cap].copy_(o)
+        self.dst = new
+
+    def add(self, yt, preds):
+        """One chunk: ``yt`` (n, gh, gw, 5+C) and ``preds`` (list of head tensors), on the device."""
+        C, dev = self.C, self.dev
+        n = yt.shape[0]
+        cells = yt.shape[1] * yt.shape[2]
+        # ground truth: at most one box per cell and class bit; labels are one-hot -> cells bound the rows
+        gt_cap = n * cells
+        gt_rows, gt_off = engine.decode_batch([yt], C, 0.5, self.version, capacity=gt_cap)
+        self.checks.append((gt_off[-1:], gt_cap, "ground-truth rows"))
+        if self.det_density is None:       # first chunk: exact (one sync), measures the density
+            det_rows, det_off = engine.decode_batch_exact(preds, C, self.conf_thr, self.version)
+            self.det_density = max(det_rows.shape[0] / max(n, 1), 1.0)
+            if det_rows.shape[0] == 0:
+                det_rows = torch.empty((1, 7), dtype=torch.float64, device=dev)
+        else:
+            det_cap = int(2.0 * self.det_density * n) + 4096
+            det_rows, det_off = engine.decode_batch(preds, C, self.conf_thr, self.version, capacity=det_cap)
+            self.checks.append((det_off[-1:], det_cap, "decode rows"))
+        res = engine.nms_batch(det_rows, det_off, C, self.thr, self.iou_mode, want_seg_offsets=True,
+                               soft=(self.conf_thr, self.sigma) if self.nms_mode == 2 else None)
+        dets = res["out_rows"]              # capacity-sized; every consumer reads the counts on the device
+        best_iou, best_gt, counts = engine.map_match(gt_rows, gt_off, dets, res["out_offsets"], C)
+        conf, gid, flag, cls, coff = engine.map_accumulate(
+            dets, res["seg_offsets"], best_iou, best_gt, counts, C, self.iou_thr, self.max_per_img, self.gt_base,
+            self.score)
+        # records of this chunk: at most max_per_img per (image, class), never more than the survivors
+        bound = dets.shape[0] if not self.max_per_img else min(dets.shape[0], n * C * int(self.max_per_img))
+        self.n_img += n
+        self.upper = getattr(self, "upper", 0) + bound
+        self._grow(self.upper)
+        engine.map_append((conf, gid, flag, cls), coff[C:C + 1], self.dst, self.total, self.counter)
+        self.coffs.append(coff)
+        self.class_counts += coff[1:] - coff[:-1]
+        self.gt_base = self.gt_base + counts.sum(dim=0, dtype=torch.int64)
+
+    def finish(self):
+        """One sync: capacities respected? -> (conf, gid, flag, cls) of this rank, class counts."""
+        if self.checks:
+            got = torch.cat([c[0] for c in self.checks]).cpu().numpy()
+            for v, (_, cap, what) in zip(got, self.checks):
+                if v > cap:
+                    raise _CapacityExceeded(f"{what}: {int(v)} > capacity {cap}")
+        n = int(self.total.item())
+        if self.dst is None:
+            self._grow(1)
+        return tuple(t[:n] for t in self.dst)
+
+    def class_segments(self):
+        """(n_chunks, C+1) int64 ndarray: where the records of class c of chunk k sit in this rank's
+        arrays - [seg[k, c], seg[k, c+1]) (every chunk's block is class-major)."""
+        if not self.coffs:
+            return np.zeros((0, self.C + 1), dtype=np.int64)
+        co = torch.stack(self.coffs).cpu().numpy()
+        base = np.concatenate([[0], np.cumsum(co[:, -1])[:-1]])
+        return co + base[:, None]
+
+
+class _CapacityExceeded(RuntimeError):
+    pass
+
+
+def _chunks_of(y_trues, y_preds, dev):
+    """Device chunks of whole arrays (host or device), sized to _CHUNK_BYTES of head tensors."""
+    n_img = _n_images(y_trues)
+    per_img = sum(int(np.prod(p.shape[1:])) * 4 for p in y_preds) + int(np.prod(y_trues.shape[1:])) * 8
+    chunk = max(1, min(n_img, _CHUNK_BYTES // max(per_img, 1)))
+    for s in range(0, n_img, chunk):
+        sl = slice(s, min(n_img, s + chunk))
+        yield _to_dev(y_trues, sl, dev, True), [_to_dev(p, sl, dev, False) for p in y_preds]
+
+
+def _local_gt_counts(chunks, C, version, dev):
+    local = torch.zeros(C, dtype=torch.int64, device=dev)
+    for yt, _ in chunks:
+        rows, off = engine.decode_batch_exact([yt], C, 0.5, version)
+        if rows.shape[0]:
+            local += torch.bincount(rows[:, 5].long(), minlength=C)[:C]
+    return local
 
 
 def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold, iou_threshold,
-                max_per_img, version, process_group=None, nms_sigma=0.5):
+                max_per_img, version, process_group=None, nms_sigma=0.5, chunk_source=None, partition=False):
+    """Phase 1 on this rank's images, then the exchange of SURVEY.md 8(e): per-class ground-truth
+    counts are all-gathered (gt ids need the counts of earlier ranks: rank order = image order) and
+    the records travel to the rank that OWNS their class (class % world: all-to-all, not an
+    all-gather of everything), so the sort + scan of phase 2 runs on 1/world of the records per rank.
+    ``chunk_source``: a callable returning an iterator of (y_true chunk, [pred chunks]) on the
+    device, for inputs that never exist as whole arrays (it is called twice when sharded)."""
     if not torch.cuda.is_available():
         raise YoloB200Error("no CUDA device: tf2_yolo_b200 has no CPU fallback")
-    if len(y_preds) == 0:
-        raise ValueError("at least one prediction array is needed")
     dev = torch.device("cuda", torch.cuda.current_device())
-    n_img = _n_images(y_trues)
-    thr, iou_mode = _nms_args(nms_mode, nms_threshold)
-    per_img = sum(int(np.prod(p.shape[1:])) * 4 for p in y_preds) + int(np.prod(y_trues.shape[1:])) * 8
-    chunk = max(1, min(n_img, _CHUNK_BYTES // max(per_img, 1)))
-    gt_is_f64 = (y_trues.dtype == torch.float64) if torch.is_tensor(y_trues) else (np.asarray(y_trues[:0]).dtype == np.float64)
-
+    if chunk_source is None:
+        if len(y_preds) == 0:
+            raise ValueError("at least one prediction array is needed")
+        chunk_source = lambda: _chunks_of(y_trues, y_preds, dev)   # noqa: E731
     C = class_num
-    score = torch.zeros(3 * C, dtype=torch.int64, device=dev)
+    world, rank = dist_util.world(process_group) if process_group is not None else (1, 0)
     gt_base = torch.zeros(C, dtype=torch.int64, device=dev)
     gts_total = None
     if process_group is not None:
-        # ground-truth counts of every rank first: gt_id = local argmax + counts of earlier ranks/images
-        local = torch.zeros(C, dtype=torch.int64, device=dev)
-        for s in range(0, n_img, chunk):
-            yt = _to_dev(y_trues, slice(s, s + chunk), dev, True)
-            rows, off = engine.decode_batch_exact([yt], C, 0.5, version)
-            if rows.shape[0]:
-                local += torch.bincount(rows[:, 5].long(), minlength=C)[:C]
+        local = _local_gt_counts(chunk_source(), C, version, dev)
         before, gts_total = dist_util.rank_offsets(local, process_group)
         gt_base = gt_base + before
-    parts = []
-    counts_total = np.zeros(C, dtype=np.int64)
-    for s in range(0, n_img, chunk):
-        sl = slice(s, min(n_img, s + chunk))
-        yt = _to_dev(y_trues, sl, dev, True)
-        preds = [_to_dev(p, sl, dev, False) for p in y_preds]
-        gt_rows, gt_off = engine.decode_batch_exact([yt], C, 0.5, version)
-        det_rows, det_off = engine.decode_batch_exact(preds, C, conf_threshold, version)
-        res = engine.nms_batch(det_rows, det_off, C, thr, iou_mode, want_seg_offsets=True,
-                               soft=(conf_threshold, nms_sigma) if nms_mode == 2 else None)
-        n_keep = int(res["out_offsets"][-1].item())
-        dets = res["out_rows"][:n_keep].contiguous()
-        best_iou, best_gt, counts = engine.map_match(gt_rows, gt_off, dets, res["out_offsets"], C)
-        conf, gid, flag, cls, coff = engine.map_accumulate(
-            dets, res["seg_offsets"], best_iou, best_gt, counts, C, iou_threshold, max_per_img, gt_base, score)
-        coff_h = coff.cpu().numpy()
-        n_out = int(coff_h[-1])
-        parts.append((conf[:n_out], gid[:n_out], flag[:n_out], cls[:n_out]))
-        counts_total += np.diff(coff_h)
-        gt_base = gt_base + counts.sum(dim=0, dtype=torch.int64)
+    for attempt in range(2):
+        ph = _Phase1(C, conf_threshold, nms_mode, nms_threshold, iou_threshold, max_per_img, version, nms_sigma, dev,
+                     gt_base)
+        if attempt == 1:
+            ph.det_density = float("inf")      # capacities from exact counts (one sync per chunk)
+        try:
+            for yt, preds in chunk_source():
+                if attempt == 1:
+                    ph.det_density = None
+                ph.add(yt, preds)
+            conf, gid, flag, cls = ph.finish()
+            break
+        except _CapacityExceeded:
+            if attempt == 1:
+                raise
     out = _Accumulated()
-    out.conf = torch.cat([p[0] for p in parts])
-    out.gid = torch.cat([p[1] for p in parts])
-    out.flag = torch.cat([p[2] for p in parts])
-    out.cls = torch.cat([p[3] for p in parts])
-    out.class_counts = counts_total
-    out.score = score
+    out.score = ph.score
+    out.owned = None
+    class_counts = ph.class_counts
     if process_group is None:
-        out.gts = gt_base.cpu().numpy()
+        out.gts = ph.gt_base.cpu().numpy()
     else:
         out.gts = gts_total.cpu().numpy()
-        out.conf = dist_util.gather_varlen(out.conf, process_group)
-        out.gid = dist_util.gather_varlen(out.gid, process_group)
-        out.flag = dist_util.gather_varlen(out.flag, process_group)
-        out.cls = dist_util.gather_varlen(out.cls, process_group)
-        out.class_counts = dist_util.allreduce_sum(torch.from_numpy(counts_total).to(dev), process_group).cpu().numpy()
         dist_util.allreduce_sum(out.score, process_group)
+        if partition:
+            conf, gid, flag, cls, class_counts = dist_util.route_records_by_class(
+                (conf, gid, flag, cls), ph.class_segments(), C, process_group)
+            out.owned = [c for c in range(C) if c % world == rank]
+        else:
+            conf = dist_util.gather_varlen(conf, process_group)
+            gid = dist_util.gather_varlen(gid, process_group)
+            flag = dist_util.gather_varlen(flag, process_group)
+            cls = dist_util.gather_varlen(cls, process_group)
+            class_counts = dist_util.allreduce_sum(class_counts, process_group)
+    out.conf, out.gid, out.flag, out.cls = conf, gid, flag, cls
+    out.class_counts = class_counts.cpu().numpy()
     return out
 
 
@@ -187,13 +299,24 @@ class PRfunc(object):
                  precision_mode=2,
                  max_per_img=100,
                  version=3,
-                 process_group=None):
+                 process_group=None,
+                 partition_classes=False,
+                 chunk_source=None):
+        """Keywords as the reference (utils/measurement.py:198-208).  Extensions for sharded / very
+        large evaluations: ``process_group`` (the arrays are this rank's images, rank order = image
+        order), ``partition_classes`` (phase 2 per class owner, class % world: ``precisions[c]`` /
+        ``recalls[c]`` exist on the owner only, ``get_map`` is the same on every rank),
+        ``chunk_source`` (callable -> iterator of device chunks ``(y_true, [preds])`` instead of
+        whole arrays; pass ``None`` for ``y_trues``)."""
         class_num = len(class_names)
         self.class_num = class_num
         self.class_names = class_names
+        self._group = process_group if partition_classes else None
 
         acc = _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold,
-                          iou_threshold, max_per_img, version, process_group, nms_sigma)
+                          iou_threshold, max_per_img, version, process_group, nms_sigma,
+                          chunk_source=chunk_source, partition=partition_classes and process_group is not None)
+        self.owned = acc.owned          # None: every class lives here
         gts = [int(g) for g in acc.gts]
         dev = acc.conf.device
         table = np.concatenate([[0], np.cumsum(acc.gts)]).astype(np.int64)
@@ -205,6 +328,10 @@ class PRfunc(object):
 
         precisions, recalls = [], []
         for class_i in range(class_num):
+            if self.owned is not None and class_i not in self.owned:
+                precisions.append(None)
+                recalls.append(None)
+                continue
             num_gts = gts[class_i]
             if num_gts == 0:
                 raise ZeroDivisionError(f"class {class_i} has no ground truth (the reference fails here too)")
@@ -232,6 +359,8 @@ class PRfunc(object):
             raise IndexError("Class index out of range")
         precisions = self.precisions[class_idx]
         recalls = self.recalls[class_idx]
+        if precisions is None:
+            raise KeyError(f"class {class_idx} is owned by another rank (partition_classes=True)")
         pc_idx = (recalls > recall).sum()
         if pc_idx == 0:
             precision = 0
@@ -263,9 +392,10 @@ class PRfunc(object):
     def get_map(self, mode="voc2012"):
         """mAP table: "voc2007" (11 points), "voc2012" (7 points), "area", "smootharea"."""
         aps = [0 for _ in range(self.class_num)]
+        mine = range(self.class_num) if self.owned is None else self.owned
 
         if mode == "area" or mode == "smootharea":
-            for class_i in range(self.class_num):
+            for class_i in mine:
                 precisions = self.precisions[class_i]
                 if mode == "smootharea":
                     precisions = np.maximum.accumulate(precisions[::-1])[::-1]
@@ -282,10 +412,14 @@ class PRfunc(object):
                 recall_list = [i/10 for i in range(0, 11)]
             else:
                 raise UnboundLocalError("recall_list")  # the reference's failure for an unknown mode
-            for class_i in range(self.class_num):
+            for class_i in mine:
                 for rc in recall_list:
                     aps[class_i] += self(rc, class_i)
             aps = [ap/len(recall_list) for ap in aps]
+        if self.owned is not None:      # every class has exactly one owner: the sum is a gather
+            t = torch.tensor([float(a) for a in aps], dtype=torch.float64, device="cuda")
+            dist_util.allreduce_sum(t, self._group)
+            aps = [float(a) for a in t.cpu()]
         aps.append(sum(aps)/len(aps))
 
         ap_table = pd.DataFrame(aps)

@@ -118,17 +118,51 @@ decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __rest
                     tot += nq;
                     before += (q < lb) ? nq : 0;
                 }
+                unsigned my_img = 0, my_cellpos = 0, my_cis = 0;
                 if (valid) {
                     const long long g = cell0 + cell;
                     const long long img = g / L.cells[s];
                     const long long o = img * L.cell_base[L.n_scales] + L.cell_base[s] + (g - img * L.cells[s]);
                     if (lb == 0 && counts != nullptr) counts[o] = (unsigned)tot;
-                    if (n > 0) {
-                        const HotBox hb = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
-                        if (hot_boxes != nullptr) hot_boxes[atomicAdd(n_hot, 1u)] = hb;
-                        if (K.n != nullptr) {
-                            const unsigned u = atomicAdd(&K.n[img], 1u);
-                            if (u < (unsigned)K.cap) K.box[img * K.cap + u] = hb;
+                    if (n > 0 && hot_boxes != nullptr)
+                        hot_boxes[atomicAdd(n_hot, 1u)] = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
+                    my_img = (unsigned)img;
+                    my_cellpos = (unsigned)(o - img * L.cell_base[L.n_scales]);
+                    my_cis = ((unsigned)s << 28) | (unsigned)(g - img * L.cells[s]);
+                }
+                if (K.n != nullptr) {
+                    // rows of the boxes with hits into their image's bucket, the warp serving one hot
+                    // box at a time (see the fused loss kernel)
+                    unsigned hot = __ballot_sync(0xffffffffu, valid && n > 0);
+                    unsigned my_base = 0;   // every hot lane reserves its rows first: the round trips overlap
+                    if (valid && n > 0) my_base = atomicAdd(&K.n[my_img], (unsigned)n);
+                    while (hot) {
+                        const int src = __ffs(hot) - 1;
+                        hot &= hot - 1;
+                        const int hcell = __shfl_sync(0xffffffffu, cell, src), hlb = __shfl_sync(0xffffffffu, lb, src);
+                        const unsigned himg = __shfl_sync(0xffffffffu, my_img, src);
+                        const unsigned hpos = __shfl_sync(0xffffffffu, my_cellpos, src);
+                        const unsigned hcis = __shfl_sync(0xffffffffu, my_cis, src);
+                        unsigned u = __shfl_sync(0xffffffffu, my_base, src);
+                        const T* hbox = sp + (size_t)hcell * pcf + hlb * ((L.version == 1) ? 5 : 5 + C);
+                        const T* hprob = (L.version == 1) ? sp + (size_t)hcell * pcf + 5 * B : hbox + 5;
+                        const T hc = hbox[4];
+                        FusedRow* dst = K.row + (size_t)himg * K.cap;
+                        for (int k0 = 0; k0 < C; k0 += 32) {
+                            const int k = k0 + lane;
+                            const T p = (k < C) ? hprob[k] : (T)0;
+                            const bool hit = (k < C) && (mul_rn<T>(hc, p) >= thr);
+                            const unsigned m = __ballot_sync(0xffffffffu, hit);
+                            const unsigned at = u + __popc(m & ((1u << lane) - 1u));
+                            if (hit && at < (unsigned)K.cap) {
+                                FusedRow fr;
+                                fr.key = fused_key(hpos, hlb, k);
+                                fr.x = (float)hbox[0]; fr.y = (float)hbox[1]; fr.w = (float)hbox[2]; fr.h = (float)hbox[3];
+                                fr.c = (float)hc; fr.p = (float)p;
+                                fr.cell = hcis;
+                                dst[at] = fr;
+                            }
+                            u += __popc(m);
                         }
                     }
                 }

@@ -36,13 +36,25 @@ __host__ __device__ inline HotBox make_hot(long long o, unsigned mem_idx, int sc
     return h;
 }
 
-// Per-image lists of the boxes with hits, for the one-CTA-per-image decode+NMS kernel
-// (decode_nms.cu): image i owns box[i*cap .. i*cap + min(n[i], cap)); n[i] > cap = overflow.
+// Per-image row buckets for the one-CTA-per-image decode + NMS kernel (decode_nms.cu): the
+// counting pass files every (box, class) hit of image i - the values it has in registers and
+// shared memory anyway - at row[i*cap + slot], slots handed out by an atomic on n[i], so the
+// per-image kernel reads a few KB of compact rows instead of gathering the hot cells back from
+// the head tensors.  n[i] > cap = overflow.  key orders the rows like the reference's decode:
+// ((cell position in output order (scale, y, x)) * 32 + box) * 256 + class.
+struct __align__(16) FusedRow {
+    unsigned int key;
+    float x, y, w, h, c, p;    // the head's values for the box (cell-relative x, y) and the class score
+    unsigned int cell;         // scale << 28 | cell index inside the scale (y * grid_w + x)
+};
 struct HotBuckets {
     unsigned int* n = nullptr;   // [n_img], zero before the counting pass; nullptr = not collected
-    HotBox* box = nullptr;       // [n_img][cap]
+    FusedRow* row = nullptr;     // [n_img][cap]
     int cap = 0;
 };
+__device__ __forceinline__ unsigned fused_key(unsigned cellpos, int box, int cls) {
+    return ((cellpos * 32u + (unsigned)box) << 8) | (unsigned)cls;
+}
 
 struct DecodeWs {          // carved out of the caller's decode workspace
     unsigned int* n_hot;   // number of boxes with hits

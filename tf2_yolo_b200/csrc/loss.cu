@@ -487,17 +487,53 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         tot += nq;
                         before += (q < lb) ? nq : 0;
                     }
+                    unsigned my_img = 0, my_cellpos = 0, my_cis = 0;
                     if (valid) {
                         const long long g = cell0 + cell;
                         const long long img = g / L.dec_cells[s];
                         const long long o = img * L.dec_per_img + L.dec_cell_base[s] + (g - img * L.dec_cells[s]);
                         if (lb == 0 && L.dec_counts != nullptr) L.dec_counts[o] = (unsigned)tot;
-                        if (n > 0) {
-                            const HotBox hb = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
-                            if (L.dec_hot != nullptr) L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = hb;
-                            if (L.dec_buckets.n != nullptr) {
-                                const unsigned u = atomicAdd(&L.dec_buckets.n[img], 1u);
-                                if (u < (unsigned)L.dec_buckets.cap) L.dec_buckets.box[img * L.dec_buckets.cap + u] = hb;
+                        if (n > 0 && L.dec_hot != nullptr)
+                            L.dec_hot[atomicAdd(L.dec_n_hot, 1u)] = make_hot(o, (unsigned)g, s, lb, (unsigned)before);
+                        my_img = (unsigned)img;
+                        my_cellpos = (unsigned)(o - img * L.dec_per_img);
+                        my_cis = ((unsigned)s << 28) | (unsigned)(g - img * L.dec_cells[s]);
+                    }
+                    if (L.dec_buckets.n != nullptr) {
+                        // rows of the boxes with hits into their image's bucket: the WARP serves one hot
+                        // box at a time (32 class scores per step, ballot, lane-parallel row writes) -
+                        // a lane walking its own C scores again would stall the other 31 for C steps
+                        unsigned hot = __ballot_sync(0xffffffffu, valid && n > 0);
+                        // every hot lane reserves its rows first: the atomics' round trips overlap
+                        unsigned my_base = 0;
+                        if (valid && n > 0) my_base = atomicAdd(&L.dec_buckets.n[my_img], (unsigned)n);
+                        while (hot) {
+                            const int src = __ffs(hot) - 1;
+                            hot &= hot - 1;
+                            const int hcell = __shfl_sync(0xffffffffu, cell, src), hlb = __shfl_sync(0xffffffffu, lb, src);
+                            const float hc = __shfl_sync(0xffffffffu, c, src);
+                            const float hx = __shfl_sync(0xffffffffu, px, src), hy = __shfl_sync(0xffffffffu, py, src);
+                            const float hw = __shfl_sync(0xffffffffu, pw, src), hh = __shfl_sync(0xffffffffu, ph, src);
+                            const unsigned himg = __shfl_sync(0xffffffffu, my_img, src);
+                            const unsigned hpos = __shfl_sync(0xffffffffu, my_cellpos, src);
+                            const unsigned hcis = __shfl_sync(0xffffffffu, my_cis, src);
+                            unsigned u = __shfl_sync(0xffffffffu, my_base, src);
+                            const float* hprob = (V == 1) ? sp + hcell * S.pcf + 5 * B : sp + hcell * S.pcf + hlb * bstride + 5;
+                            FusedRow* dst = L.dec_buckets.row + (size_t)himg * L.dec_buckets.cap;
+                            for (int k0 = 0; k0 < C; k0 += 32) {
+                                const int k = k0 + lane;
+                                const float p = (k < C) ? hprob[k] : 0.f;
+                                const bool hit = (k < C) && (__fmul_rn(hc, p) >= L.dec_thr);
+                                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                                const unsigned at = u + __popc(m & ((1u << lane) - 1u));
+                                if (hit && at < (unsigned)L.dec_buckets.cap) {
+                                    FusedRow fr;
+                                    fr.key = fused_key(hpos, hlb, k);
+                                    fr.x = hx; fr.y = hy; fr.w = hw; fr.h = hh; fr.c = hc; fr.p = p;
+                                    fr.cell = hcis;
+                                    dst[at] = fr;
+                                }
+                                u += __popc(m);
                             }
                         }
                     }

@@ -75,8 +75,36 @@ def grid_config(name, version, out):
     t_loss, t_loss_min = timed(lambda: fused_losses(fns, yt, yp, dpreds=dp), flush=flush, burst=burst)
     t_dec, _ = timed(lambda: engine.decode_batch(yp, C, 0.5, version, rows=rows), flush=flush, burst=burst)
     _, offs = engine.decode_batch(yp, C, 0.5, version, rows=rows)
-    t_nms, _ = timed(lambda: engine.nms_batch(rows, offs, C, 0.45, 2 if version == 4 else 1))
+    mode = 2 if version == 4 else 1
+    t_nms, _ = timed(lambda: engine.nms_batch(rows, offs, C, 0.45, mode))
+    # the train-and-evaluate step in two launches, and inference decode + NMS in two (count, per-image kernel)
+    params = [f.params for f in fns]
+    fout = dict(out_rows=torch.empty((2048 * batch, 7), dtype=torch.float64, device="cuda"),
+                out_offsets=torch.empty(batch + 1, dtype=torch.int64, device="cuda"),
+                n_overflow=torch.zeros(1, dtype=torch.int32, device="cuda"))
+    step = lambda: engine.loss_decode_nms_fused(params, yt, yp, 0.5, 0.45, mode, rows_per_img_cap=2048, dpreds=dp, out=fout)  # noqa: E731
+    t_step, _ = timed(step, flush=flush, burst=burst)
+    assert int(fout["n_overflow"].item()) == 0
+    t_inf, _ = timed(lambda: engine.decode_nms_batch(yp, C, 0.5, version, 0.45, mode, rows_per_img_cap=2048, out=fout),
+                     flush=flush, burst=burst)
+    # the same step replayed from a CUDA graph (what a training loop would do with static shapes)
+    t_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            step()
+            with torch.cuda.graph(g, stream=side):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        t_graph, _ = timed(g.replay, flush=flush, burst=burst)
+    except Exception as e:  # noqa: BLE001
+        t_graph = f"graph capture failed: {type(e).__name__}: {e}"
+        torch.cuda.synchronize()
     out[name] = {
+        "step_two_launches_ms": t_step, "step_graph_replay_ms": t_graph, "decode_nms_two_launches_ms": t_inf,
+        "step_images_per_s": batch / (t_step * 1e-3), "step_frac_of_measured_hbm": loss_bytes / t_step / 1e6 / PEAK,
         "batch": batch, "loss_ms": t_loss, "loss_GBps": loss_bytes / t_loss / 1e6,
         "loss_frac_of_measured_hbm": loss_bytes / t_loss / 1e6 / PEAK, "loss_bytes": loss_bytes,
         "decode_ms": t_dec, "decode_GBps": dec_bytes / t_dec / 1e6, "decode_frac": dec_bytes / t_dec / 1e6 / PEAK,
@@ -109,15 +137,27 @@ def kmeans_bench(out, n=50_000_000, k=9):
     centers = torch.from_numpy(np.sort(rng.uniform(0.02, 0.8, (k, 2)), axis=0)).cuda()
     t, tmin = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU), burst=8)
     t2, _ = timed(lambda: engine.kmeans_assign(data, centers, YB_DIST_IOU, want_assign=True), burst=8)
+    # one iteration of the device Lloyd loop (assignment + update + stop test in one launch)
+    loop = engine.KMeansLloyd(data, centers.clone(), YB_DIST_IOU, 0.0, 1 << 40)
+    t3, _ = timed(loop.step, burst=8)
     out["kmeans_50M"] = {"boxes": n, "k": k, "ms_per_iteration": t, "GBps": 16 * n / t / 1e6,
-                         "frac_of_measured_hbm": 16 * n / t / 1e6 / PEAK, "ms_with_assignments": t2}
-    print("kmeans_50M", json.dumps(out["kmeans_50M"]))
+                         "frac_of_measured_hbm": 16 * n / t / 1e6 / PEAK, "ms_with_assignments": t2,
+                         "ms_per_lloyd_iteration_device_loop": t3,
+                         "lloyd_frac_of_measured_hbm": 16 * n / t3 / 1e6 / PEAK}
     from tf2_yolo_b200.utils import kmeans as km
+    import contextlib
+    import io
+    km.kmeans(data[:100_000], k, km.iou_dist, 1e-5, verbose=False)     # warm
     np.random.seed(4)
+    buf = io.StringIO()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    c = km.kmeans(data[:5_000_000], k, km.iou_dist, 1e-5, verbose=False)
-    out["kmeans_5M_full_run_s"] = time.perf_counter() - t0
-    print("kmeans full run on 5M boxes:", out["kmeans_5M_full_run_s"], "s", c[:3].tolist())
+    with contextlib.redirect_stdout(buf):
+        c = km.kmeans(data, k, km.iou_dist, 1e-5, verbose=True)
+    dt = time.perf_counter() - t0
+    iters = len([ln for ln in buf.getvalue().split("\n") if ln.startswith("epoch")])
+    out["kmeans_50M"].update(full_run_s=dt, full_run_iterations=iters, full_run_ms_per_iteration=1e3 * dt / max(iters, 1))
+    print("kmeans_50M", json.dumps(out["kmeans_50M"]), c[:3].tolist())
 
 
 def map_bench(out, n_img=512):

@@ -35,7 +35,7 @@ __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __
 constexpr int kDecMaxConsumerWarps = 8;
 constexpr int kDecStages = 3;
 
-template <typename T>
+template <typename T, bool kBuckets>
 __global__ void __launch_bounds__((kDecMaxConsumerWarps + 1) * 32)
 decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __restrict__ counts,
                     unsigned int* __restrict__ n_hot, HotBox* __restrict__ hot_boxes, const HotBuckets K) {
@@ -130,7 +130,7 @@ decode_count_kernel(const __grid_constant__ DecodeLaunch L, unsigned int* __rest
                     my_cellpos = (unsigned)(o - img * L.cell_base[L.n_scales]);
                     my_cis = ((unsigned)s << 28) | (unsigned)(g - img * L.cells[s]);
                 }
-                if (K.n != nullptr) {
+                if (kBuckets) {
                     // rows of the boxes with hits into their image's bucket, the warp serving one hot
                     // box at a time (see the fused loss kernel)
                     unsigned hot = __ballot_sync(0xffffffffu, valid && n > 0);
@@ -300,13 +300,18 @@ int decode_count(DecodeLaunch& L, bool is_f64, unsigned int* counts, unsigned in
     const int grid = max(1, min(n_tiles, kNumSMs * ctas_per_sm));
     const int threads1 = (ncw + 1) * 32;
     if (is_f64) {
+        if (buckets.n != nullptr) return YB_E_PARAM;   // row buckets hold the float32 head values
         static SmemRaised done;
-        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<double>, (int)smem, &done));
-        decode_count_kernel<double><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<double, false>, (int)smem, &done));
+        decode_count_kernel<double, false><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
+    } else if (buckets.n != nullptr) {
+        static SmemRaised done;
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<float, true>, (int)smem, &done));
+        decode_count_kernel<float, true><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
     } else {
         static SmemRaised done;
-        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<float>, (int)smem, &done));
-        decode_count_kernel<float><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
+        YB_CUDA_TRY(raise_dynamic_smem_once(decode_count_kernel<float, false>, (int)smem, &done));
+        decode_count_kernel<float, false><<<grid, threads1, smem, stream>>>(L, counts, n_hot, hot, buckets);
     }
     YB_CUDA_TRY(cudaGetLastError());
     return YB_OK;

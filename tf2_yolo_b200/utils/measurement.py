@@ -419,7 +419,9 @@ class PRfunc(object):
         if self.owned is not None:      # every class has exactly one owner: the sum is a gather
             t = torch.tensor([float(a) for a in aps], dtype=torch.float64, device="cuda")
             dist_util.allreduce_sum(t, self._group)
-            aps = [float(a) for a in t.cpu()]
+            # numpy scalars, like the unsharded path: Python 3.12's sum() is compensated for exact
+            # floats only, so the final mean would otherwise differ from the reference's by an ulp
+            aps = [np.float64(a) for a in t.cpu().numpy()]
         aps.append(sum(aps)/len(aps))
 
         ap_table = pd.DataFrame(aps)

@@ -275,6 +275,7 @@ def run_ours(args):
     loss_ev = []
 
     mode = "unfused" if args.unfused else ("chain" if args.chain else "fused")
+    step_loss = torch.empty(3, dtype=torch.float32, device=dev)
     fused_out = dict(out_rows=torch.empty((ROWS_PER_IMG_FUSED * batch, 7), dtype=torch.float64, device=dev),
                      out_offsets=torch.empty(batch + 1, dtype=torch.int64, device=dev),
                      n_overflow=torch.zeros(1, dtype=torch.int32, device=dev))
@@ -284,16 +285,21 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if mode == "fused":   # two launches: loss + counting pass, then decode + NMS with one CTA per image
-            def mark():
+            pending = []
+
+            def after_loss():   # between the two launches: the loss scalars are final
                 if record:
                     e1.record()
                     loss_ev.append((e0, e1))
+                if world > 1:   # the only collective (3 scalars) runs beside the decode + NMS kernel
+                    pending.append(dist.all_reduce(loss_box[0], async_op=True))
+            loss_box = [None]
             loss, _, _, res = engine.loss_decode_nms_fused(params, y_t, y_p, CONF_THR, NMS_THR, NMS_MODE,
                                                            rows_per_img_cap=ROWS_PER_IMG_FUSED,
                                                            global_batch=global_batch, dpreds=dpreds, out=fused_out,
-                                                           split_hook=mark)
-            if world > 1:
-                dist.all_reduce(loss)            # the only collective: 3 scalars
+                                                           split_hook=after_loss, loss_out=step_loss, loss_box=loss_box)
+            for w in pending:
+                w.wait()
             return loss, None, res
         if args.unfused:
             loss, _, _ = fused_losses(fns, y_t, y_p, global_batch=global_batch, dpreds=dpreds)

@@ -225,6 +225,8 @@ def run_map_config5(out, rank, world, dev, group, n_img_total, pool=256, check=1
     t0 = time.perf_counter()
     pr = meas.PRfunc(None, process_group=group, partition_classes=world > 1, chunk_source=source_of(a, b), **kw)
     t1 = time.perf_counter()
+    split = {}
+    meas.PRfunc(None, process_group=group, partition_classes=world > 1, chunk_source=source_of(a, b), timings=split, **kw)
     tab = pr.get_map()
     barrier(world)
     dt = max_over_ranks(time.perf_counter() - t0, world, dev)
@@ -236,6 +238,7 @@ def run_map_config5(out, rank, world, dev, group, n_img_total, pool=256, check=1
             "n_gpus": world, "images": n_img_total, "images_per_rank": b - a, "pool_images": pool,
             "seconds_total": dt, "seconds_until_curves": dt_curves, "images_per_s": n_img_total / dt,
             "records_in_largest_rank": n_rec, "mAP_voc2012": float(tab["ap"].iloc[-1]),
+            "phase_split_rank0_s (second run, device synchronised between phases)": split,
             "collective": "all-gather of per-class GT counts; records all-to-all to the class owner (class % world)"}
         if world > 1:
             t0 = time.perf_counter()

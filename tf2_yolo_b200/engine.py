@@ -366,7 +366,7 @@ def decode_nms_batch_exact(preds, class_num=1, threshold=0.5, version=1, nms_thr
 
 def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold=0.45, iou_mode=1,
                           rows_per_img_cap=1024, global_batch=None, dpreds=None, want_terms=False, out=None,
-                          out_capacity=None, split_hook=None):
+                          out_capacity=None, split_hook=None, loss_out=None, loss_box=None):
     """The train-and-evaluate step in two launches (yb_loss_decode_nms_fused): loss forward +
     gradient with the decode counting pass riding on its read of y_pred, then decode + NMS with one
     CTA per image.  Returns (loss [n], dpreds, terms, dict(out_rows, out_offsets, n_overflow))."""
@@ -395,7 +395,9 @@ def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold
         out_capacity = rows_per_img_cap * max(n_img, 1)
     with torch.cuda.device(dev):
         out_rows, out_offsets, n_overflow = _fused_outputs(dev, n_img, out_capacity, out)
-        loss = torch.empty(n, dtype=torch.float32, device=dev)
+        loss = loss_out if loss_out is not None else torch.empty(n, dtype=torch.float32, device=dev)
+        if loss_box is not None:
+            loss_box[0] = loss      # lets a split_hook see the tensor the loss kernel has just written
         terms = torch.empty((n, N.YB_LOSS_TERMS), dtype=_F64, device=dev) if want_terms else None
         lws_bytes = N.lib.yb_loss_workspace_bytes(n)
         lws = workspaces.get("loss", lws_bytes, dev)

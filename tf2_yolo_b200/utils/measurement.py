@@ -179,8 +179,20 @@ def _local_gt_counts(chunks, C, version, dev):
     return local
 
 
+def _tick(timings, key, t0):
+    """Phase timer (only when the caller asked for timings: it synchronises the device)."""
+    if timings is None:
+        return t0
+    import time
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    timings[key] = timings.get(key, 0.0) + (now - t0)
+    return now
+
+
 def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold, iou_threshold,
-                max_per_img, version, process_group=None, nms_sigma=0.5, chunk_source=None, partition=False):
+                max_per_img, version, process_group=None, nms_sigma=0.5, chunk_source=None, partition=False,
+                timings=None):
     """Phase 1 on this rank's images, then the exchange of SURVEY.md 8(e): per-class ground-truth
     counts are all-gathered (gt ids need the counts of earlier ranks: rank order = image order) and
     the records travel to the rank that OWNS their class (class % world: all-to-all, not an
@@ -195,6 +207,8 @@ def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_thres
             raise ValueError("at least one prediction array is needed")
         chunk_source = lambda: _chunks_of(y_trues, y_preds, dev)   # noqa: E731
     C = class_num
+    import time
+    t0 = time.perf_counter() if timings is not None else 0.0
     world, rank = dist_util.world(process_group) if process_group is not None else (1, 0)
     gt_base = torch.zeros(C, dtype=torch.int64, device=dev)
     gts_total = None
@@ -202,6 +216,7 @@ def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_thres
         local = _local_gt_counts(chunk_source(), C, version, dev)
         before, gts_total = dist_util.rank_offsets(local, process_group)
         gt_base = gt_base + before
+        t0 = _tick(timings, "gt_count_pass_and_allgather_s", t0)
     for attempt in range(2):
         ph = _Phase1(C, conf_threshold, nms_mode, nms_threshold, iou_threshold, max_per_img, version, nms_sigma, dev,
                      gt_base)
@@ -217,6 +232,7 @@ def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_thres
         except _CapacityExceeded:
             if attempt == 1:
                 raise
+    t0 = _tick(timings, "phase1_decode_nms_match_s", t0)
     out = _Accumulated()
     out.score = ph.score
     out.owned = None
@@ -238,6 +254,7 @@ def _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_thres
             class_counts = dist_util.allreduce_sum(class_counts, process_group)
     out.conf, out.gid, out.flag, out.cls = conf, gid, flag, cls
     out.class_counts = class_counts.cpu().numpy()
+    _tick(timings, "exchange_s", t0)
     return out
 
 
@@ -301,13 +318,15 @@ class PRfunc(object):
                  version=3,
                  process_group=None,
                  partition_classes=False,
-                 chunk_source=None):
+                 chunk_source=None,
+                 timings=None):
         """Keywords as the reference (utils/measurement.py:198-208).  Extensions for sharded / very
         large evaluations: ``process_group`` (the arrays are this rank's images, rank order = image
         order), ``partition_classes`` (phase 2 per class owner, class % world: ``precisions[c]`` /
         ``recalls[c]`` exist on the owner only, ``get_map`` is the same on every rank),
         ``chunk_source`` (callable -> iterator of device chunks ``(y_true, [preds])`` instead of
-        whole arrays; pass ``None`` for ``y_trues``)."""
+        whole arrays; pass ``None`` for ``y_trues``), ``timings`` (a dict that receives the seconds per
+        phase; asking for it synchronises the device between phases)."""
         class_num = len(class_names)
         self.class_num = class_num
         self.class_names = class_names
@@ -315,13 +334,17 @@ class PRfunc(object):
 
         acc = _accumulate(y_trues, y_preds, class_num, conf_threshold, nms_mode, nms_threshold,
                           iou_threshold, max_per_img, version, process_group, nms_sigma,
-                          chunk_source=chunk_source, partition=partition_classes and process_group is not None)
+                          chunk_source=chunk_source, partition=partition_classes and process_group is not None,
+                          timings=timings)
+        import time
+        t0 = time.perf_counter() if timings is not None else 0.0
         self.owned = acc.owned          # None: every class lives here
         gts = [int(g) for g in acc.gts]
         dev = acc.conf.device
         table = np.concatenate([[0], np.cumsum(acc.gts)]).astype(np.int64)
         order, tp_cum, tpp_cum = engine.pr_curve(acc.conf, acc.cls, acc.gid, acc.flag,
                                                  torch.from_numpy(table).to(dev), int(table[-1]))
+        t0 = _tick(timings, "phase2_sort_scan_s", t0)
         tp_cum = tp_cum.cpu().numpy()
         tpp_cum = tpp_cum.cpu().numpy()
         starts = np.concatenate([[0], np.cumsum(acc.class_counts)]).astype(np.int64)
@@ -353,6 +376,7 @@ class PRfunc(object):
 
         self.precisions = precisions
         self.recalls = recalls
+        _tick(timings, "host_curves_s", t0)
 
     def __call__(self, recall, class_idx=0):
         if class_idx >= self.class_num:

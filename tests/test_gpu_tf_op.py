@@ -91,3 +91,21 @@ def test_compute_rejects_mismatched_tensors(tf_stub):  # noqa: F811
     outs = (C.c_void_p * 2)(t.data_ptr(), p.data_ptr())
     rc = lib.tfstub_run(b"YoloGridLoss", attr_spec(attrs), 2, ins, elems, 2, outs, None, 0, None)
     assert rc == 4 and b"reshape" in lib.tfstub_last_error()
+
+
+def test_from_logits_attr_reaches_the_kernel(tf_stub):  # noqa: F811
+    """The op with from_logits=True == the ctypes from-logits loss on raw head outputs."""
+    from tf2_yolo_b200 import synth
+    from tf2_yolo_b200.grid_loss import wrap_yolo_loss_from_logits
+    lib = build_tfstub()
+    head = importlib.import_module("tf2_yolo_b200.tf_ops.head")
+    cfg = synth.make_config("v4-608", batch=2, seed=9)
+    S, B, Cn = 19, 3, 80
+    anc = cfg["anchors"][:3]
+    raw = torch.randn((2, S, S, B * (5 + Cn)), device="cuda") * 0.5
+    yt = torch.from_numpy(cfg["y_trues"][0]).cuda()
+    attrs = head.wrap_yolo_loss_from_logits(4, (S, S), B, Cn, anc, loss_weight=[1, 5, 1]).op_attrs
+    loss, draw = torch.zeros((), device="cuda"), torch.zeros_like(raw)
+    run_op(lib, "YoloGridLoss", attrs, [yt, raw], [loss, draw])
+    l2, g2 = wrap_yolo_loss_from_logits(4, (S, S), B, Cn, anchors=anc, loss_weight=[1, 5, 1]).value_and_grad(yt, raw)
+    assert torch.equal(loss.reshape(-1), l2.reshape(-1)) and torch.equal(draw, g2)

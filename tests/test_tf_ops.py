@@ -265,3 +265,38 @@ def test_kernel_construction_rejects_what_the_reference_cannot_mean(tf_stub):
     missing = dict(good)
     del missing["class_num"]
     assert lib.tfstub_construct(b"YoloGridLoss", attr_spec(missing)) == 1
+
+
+def test_raw_logit_head_keeps_the_reference_layer_names(tf_stub, monkeypatch):
+    """yolo_head_logits builds the reference head's convolutions under the reference's names
+    (yolov4/models/__init__.py:42-66) with no activation and no Anchor layer, in the per-box order
+    [xy, wh, conf, prob] the from_logits kernel reads; its loss reaches the op with from_logits."""
+    made = []
+
+    def conv(filters, size, activation=None, name=None):
+        made.append((name, filters, size, activation))
+        return lambda t: f"{name}({t})"
+    layers = types.ModuleType("tensorflow.keras.layers")
+    layers.Concatenate = lambda name=None: (lambda parts: (name, list(parts)))
+    models = types.ModuleType("tensorflow.keras.models")
+    models.Model = lambda inp, outs: types.SimpleNamespace(input=inp, output=outs)
+    keras = types.ModuleType("tensorflow.keras")
+    for name, mod in (("tensorflow.keras", keras), ("tensorflow.keras.layers", layers), ("tensorflow.keras.models", models)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    head = importlib.import_module("tf2_yolo_b200.tf_ops.head")
+    body = types.SimpleNamespace(input="img", output=["f19", "f38", "f76"])
+    model = head.yolo_head_logits(body, class_num=80, anchors=ANCHORS9, conv_layer=conv)
+    assert model.input == "img" and [o[0] for o in model.output] == ["out1_concat", "out2_concat", "out3_concat"]
+    assert len(made) == 3 * 3 * 4 and all(m[3] is None for m in made)          # 36 convolutions, none activated
+    assert [m[0] for m in made[:4]] == ["out1_box1_xy_conv", "out1_box1_wh_conv", "out1_box1_conf_conv",
+                                         "out1_box1_prob_conv"]
+    assert [m[1] for m in made[:4]] == [2, 2, 1, 80]
+    assert model.output[2][1][4].startswith("out3_box2_xy_conv(f76")               # per-box order inside a scale
+    with pytest.raises(ValueError):
+        head.yolo_head_logits(body, anchors=ANCHORS9[:8], conv_layer=conv)
+    f = head.wrap_yolo_loss_from_logits(4, (19, 19), 3, 80, ANCHORS9[:3], loss_weight=[1, 5, 1])
+    assert f.op_attrs["from_logits"] is True and f.op_attrs["version"] == 4
+    lib, _ = registered_ops()
+    assert lib.tfstub_construct(b"YoloGridLoss", attr_spec(f.op_attrs)) == 0, lib.tfstub_last_error()
+    with pytest.raises(ValueError):
+        head.wrap_yolo_loss_from_logits(2, (13, 13), 5, 20, ANCHORS9[:5])

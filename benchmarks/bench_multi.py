@@ -127,7 +127,29 @@ def run_kmeans(out, rank, world, dev, group, n=50_000_000, k=9):
     except Exception as e:  # noqa: BLE001
         ms_graph = f"graph capture failed: {type(e).__name__}: {e}"
         torch.cuda.synchronize()
-    st, done, _, _, _ = loop.read_state()
+    # the all-reduce inside the assignment launch, over NVLink peer memory (one launch per iteration)
+    ms_peer, t_full_peer, peer_same = None, None, None
+    if world > 1:
+        loop_p = engine.KMeansLloyd(shard, torch.from_numpy(c0).to(dev), YB_DIST_IOU, 0.0, 1 << 40, sharded=True,
+                                    peer_group=group)
+        for _ in range(5):
+            loop_p.step()
+        barrier(world)
+        e0.record()
+        for _ in range(reps):
+            loop_p.step()
+        e1.record()
+        barrier(world)
+        ms_peer = max_over_ranks(e0.elapsed_time(e1) / reps, world, dev)
+        peer_same = int(loop_p.read_state()[0])      # 0 = running (no exchange timed out)
+        barrier(world)
+        loop_p.close()
+        np.random.seed(4)
+        barrier(world)
+        t0 = time.perf_counter()
+        c_peer = km.kmeans(shard, k, km.iou_dist, 1e-5, verbose=False, process_group=group, exchange="peer")
+        torch.cuda.synchronize()
+        t_full_peer = time.perf_counter() - t0
     # full run: the reference's loop with its RNG stream
     np.random.seed(4)
     barrier(world)
@@ -153,6 +175,9 @@ def run_kmeans(out, rank, world, dev, group, n=50_000_000, k=9):
         out["kmeans_50M"] = {
             "n_gpus": world, "boxes": n, "k": k, "ms_per_iteration": ms, "ms_per_iteration_cuda_graph": ms_graph,
             "boxes_per_s": n / (ms * 1e-3), "GBps_aggregate": 16 * n / ms / 1e6,
+            "ms_per_iteration_peer_exchange_in_kernel": ms_peer, "peer_exchange_status": peer_same,
+            "full_run_s_sharded_peer_exchange": t_full_peer,
+            "centres_peer_equal_nccl": bool(np.array_equal(c_peer, c_sharded)) if world > 1 else None,
             "collective": f"all-reduce of {k * 3} doubles per iteration, same stream, no host sync",
             "full_run_s_sharded": t_full, "full_run_s_single_gpu": t_single, "iterations": n_iter,
             "single_gpu_ms_per_iteration_whole_run": 1e3 * t_single / max(n_iter, 1),

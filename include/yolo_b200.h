@@ -28,6 +28,7 @@ typedef struct CUstream_st* yb_stream_t; /* == cudaStream_t */
 #define YB_MAX_SCALES 4  /* FPN outputs per fused loss launch */
 #define YB_LOSS_TERMS 8  /* doubles per scale in terms_out */
 #define YB_LOSS_METRICS 10 /* doubles per scale in metrics_out */
+#define YB_MAX_PEERS 16   /* ranks of one node in a peer-memory exchange */
 #define YB_FUSED_MAX_ROWS 2048 /* decode rows per image the one-launch decode+NMS holds in shared memory */
 #define YB_ENCODE_MAX_BOXES 1024 /* boxes per image yb_encode_labels stages in shared memory */
 
@@ -284,7 +285,7 @@ int yb_kmeans_dist(const double* a, int64_t na, const double* b, int64_t nb, int
  * yb_kmeans_lloyd_update applies the update on every rank (identical inputs, identical centres).
  * `state` (device, yb_kmeans_state_bytes, zeroed by yb_kmeans_lloyd_init together with the
  * workspace's counter) holds 8-byte words: [0] status 0 running | 1 converged | 2 iteration cap |
- * 3 empty cluster, [1] completed updates, [4 + (e-1) % YB_KMEANS_HIST] the loss of update e
+ * 3 empty cluster | 4 peer exchange timed out, [1] completed updates, [4 + (e-1) % YB_KMEANS_HIST] the loss of update e
  * (double), then the k*(d+1) global sums / counts of the iteration that met an empty cluster.
  * A non-zero status FREEZES the loop: further steps return at once, so the host may queue
  * iterations in batches and look at `state` once per batch; the result does not depend on the
@@ -304,6 +305,28 @@ int yb_kmeans_lloyd_step(const double* data, int64_t n_points, int n_dim, double
 
 int yb_kmeans_lloyd_update(const double* packed, double* centers, int k, int n_dim, int dist_kind,
                            double stop_dist, int64_t max_iternum, int64_t* state, yb_stream_t stream);
+
+/* Sharded Lloyd iteration with the all-reduce INSIDE the launch: the last CTA stores the rank's
+ * k*(d+1) partial sums into every rank's mailbox (peer stores over NVLink / NVSwitch), publishes
+ * them with a system-scope release, waits for all ranks' contributions in its own mailbox, adds
+ * them in rank order (identical bits on every rank) and applies the update - one launch per
+ * iteration, no NCCL call, no extra kernel.  mailboxes_host[r] = device pointer to rank r's mailbox
+ * (yb_peer_mailbox_bytes(world) bytes, zeroed; own mailbox at [rank], the others opened from their
+ * IPC handles).  All ranks must issue the same sequence of steps; a rank that never arrives ends
+ * the peers' wait after 2 s with state[0] = 4 (exchange timed out) instead of hanging their GPUs.
+ * state[2] counts the exchanges.
+ * yb_peer_alloc is the only place this library owns device memory (IPC export needs a cudaMalloc
+ * allocation): yb_peer_free releases it; yb_peer_open / yb_peer_close map a peer's allocation. */
+size_t yb_peer_mailbox_bytes(int world);
+int yb_peer_alloc(size_t bytes, void** dev_ptr_host, void* ipc_handle64_host);
+int yb_peer_open(const void* ipc_handle64_host, void** dev_ptr_host);
+int yb_peer_close(void* dev_ptr);
+int yb_peer_free(void* dev_ptr);
+
+int yb_kmeans_lloyd_step_peers(const double* data, int64_t n_points, int n_dim, double* centers, int k,
+                               int dist_kind, double stop_dist, int64_t max_iternum, int64_t* state,
+                               int32_t* assign, void* workspace, size_t workspace_bytes,
+                               void* const* mailboxes_host, int rank, int world, yb_stream_t stream);
 
 /* min / max over all elements of data (kmeans.py:68-69). out2 = {min,max}. */
 int yb_minmax_f64(const double* data, int64_t n, double* out2, void* workspace,

@@ -235,3 +235,22 @@ def test_map_match_non_finite_boxes():
                 want, arg = np.max(iou), int(np.argmax(iou))
                 assert bg[k] == arg, (i, j)
                 assert (np.isnan(want) and np.isnan(bi[k])) or bi[k] == want, (i, j)
+
+
+def test_lloyd_step_with_the_in_kernel_exchange_single_rank():
+    """yb_kmeans_lloyd_step_peers with a world of one (the rank's own mailbox): the exchange code of
+    the last CTA runs - stores, release, acquire, rank-ordered sum - and the loop equals the plain
+    device loop bit for bit, iteration after iteration (both parities of the mailbox)."""
+    rng = np.random.default_rng(12)
+    data = torch.from_numpy(synth.make_kmeans_boxes(rng, 200_000, k=7)).cuda()
+    c0 = np.sort(rng.uniform(0.02, 0.8, (7, 2)), axis=0)
+    a = engine.KMeansLloyd(data, torch.from_numpy(c0).cuda(), YB_DIST_IOU, 1e-6, 1000)
+    b = engine.KMeansLloyd(data, torch.from_numpy(c0).cuda(), YB_DIST_IOU, 1e-6, 1000, sharded=True, peer_group="self")
+    for it in range(9):
+        a.step()
+        b.step()
+        sa, sb = a.read_state(), b.read_state()
+        assert sa[0] == sb[0] and sa[1] == sb[1] == it + 1
+        assert torch.equal(a.centers, b.centers), it
+        assert np.array_equal(sa[2][:it + 1], sb[2][:it + 1])
+    b.close()

@@ -17,6 +17,7 @@ YB_LOSS_METRICS = 10
 YB_ENCODE_MAX_BOXES = 1024
 YB_FUSED_MAX_ROWS = 2048
 YB_KMEANS_HIST = 64
+YB_MAX_PEERS = 16
 YB_DIST_IOU, YB_DIST_EUCLID = 0, 1
 
 
@@ -108,6 +109,13 @@ SIGNATURES = {
     "yb_kmeans_lloyd_init": (C.c_int, [_vp, _i32, _i32, _vp, _sz, _vp]),
     "yb_kmeans_lloyd_step": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _dbl, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_kmeans_lloyd_update": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _dbl, _i64, _vp, _vp]),
+    "yb_peer_mailbox_bytes": (_sz, [_i32]),
+    "yb_peer_alloc": (C.c_int, [_sz, C.POINTER(_vp), _vp]),
+    "yb_peer_open": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "yb_peer_close": (C.c_int, [_vp]),
+    "yb_peer_free": (C.c_int, [_vp]),
+    "yb_kmeans_lloyd_step_peers": (C.c_int, [_vp, _i64, _i32, _vp, _i32, _i32, _dbl, _i64, _vp, _vp, _vp, _sz,
+                                             C.POINTER(_vp), _i32, _i32, _vp]),
     "yb_minmax_f64": (C.c_int, [_vp, _i64, _vp, _vp, _sz, _vp]),
     "yb_encode_labels": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _dbl, _i32, _i32, _i32, _i32, C.POINTER(_vp), _i32,
                                    _vp, _vp]),

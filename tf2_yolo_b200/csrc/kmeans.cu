@@ -13,6 +13,7 @@
 // all but a vanishing fraction of the boxes (see the kernel).
 #include <climits>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -40,7 +41,82 @@ struct KmLaunch {
     double* centers_rw; // non-null: the last CTA applies the Lloyd update itself (single rank)
     double stop_dist;
     long long max_iter;
+    // peer exchange (yb_kmeans_lloyd_step_peers): the all-reduce of the k*(d+1) partial sums over
+    // NVLink peer memory, inside the same launch
+    unsigned char* mailbox[YB_MAX_PEERS];   // mailbox of every rank (own at [rank]); null = no exchange
+    int rank, world;
 };
+
+// Mailbox of one rank: box[parity][source rank] = kPeerSlotDoubles payload doubles + a flag word.
+constexpr int kPeerSlotDoubles = 16 * 5;                       // k <= 16, d <= 4: k*(d+1) <= 80
+constexpr size_t kPeerSlotBytes = (kPeerSlotDoubles + 2) * 8;  // payload | flag | pad
+__host__ __device__ inline size_t peer_slot_offset(int parity, int src, int world) {
+    return ((size_t)parity * world + src) * kPeerSlotBytes;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All-reduce of fin[0..nv) over the ranks through their mailboxes (whole CTA; the last CTA of the
+// launch): every rank stores its partial sums into slot [parity][rank] of EVERY mailbox (peer
+// stores over NVLink), publishes them with a system-scope release of the exchange number, waits for
+// the same number in all slots of its own mailbox and adds the slots in rank order - the same
+// order on every rank, so all ranks hold the same bits.  Two parities: a rank can be at most one
+// exchange ahead of a peer that is still reading.  A peer that never arrives (its host died) ends
+// the wait after 2 s with status 4 instead of hanging the GPU.
+__device__ inline bool km_peer_allreduce(const KmLaunch& L, double* fin, int nv) {
+    const int tid = threadIdx.x;
+    const unsigned long long seq = (unsigned long long)L.state[2] + 1ull;
+    const int parity = (int)(seq & 1ull);
+    __shared__ int s_ok;
+    if (tid == 0) s_ok = 1;
+    for (int i = tid; i < nv * L.world; i += blockDim.x) {
+        const int peer = i / nv, j = i - peer * nv;
+        double* slot = reinterpret_cast<double*>(L.mailbox[peer] + peer_slot_offset(parity, L.rank, L.world));
+        slot[j] = fin[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < L.world) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(
+            L.mailbox[tid] + peer_slot_offset(parity, L.rank, L.world) + kPeerSlotDoubles * 8);
+        st_release_sys(flag, seq);
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
+            L.mailbox[L.rank] + peer_slot_offset(parity, tid, L.world) + kPeerSlotDoubles * 8);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(mine) != seq) {
+            if (global_timer_ns() - t0 > 2000000000ull) {
+                s_ok = 0;
+                break;
+            }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
+    if (!s_ok) {
+        if (tid == 0) L.state[0] = 4;   // exchange timed out
+        return false;
+    }
+    if (tid < nv) {
+        double sum = 0.0;
+        for (int src = 0; src < L.world; ++src)
+            sum += __ldcg(reinterpret_cast<const double*>(L.mailbox[L.rank] + peer_slot_offset(parity, src, L.world)) + tid);
+        fin[tid] = sum;
+    }
+    __syncthreads();
+    if (tid == 0) L.state[2] = (long long)seq;
+    return true;
+}
 
 // ---- the Lloyd update, utils/kmeans.py:84-97, as device code -------------------------------------
 // state words (8 bytes each): [0] status 0 running | 1 loss < stop_dist | 2 iteration cap | 3 empty
@@ -447,11 +523,15 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        *L.counter = 0u;
-        if (L.centers_rw != nullptr)   // every CTA has long copied the centres: update them in place
-            km_lloyd_update(k, D, L.kind, s_fin, L.centers_rw, L.state, L.stop_dist, L.max_iter);
+    if (tid == 0) *L.counter = 0u;
+    bool ok = true;
+    if (L.mailbox[0] != nullptr) {
+        // s_fin is laid out [c*(D+1)+j] over K slots; the exchange covers the first k*(D+1) ... K may
+        // exceed k, so send all NV entries (unused ones are zero)
+        ok = km_peer_allreduce(L, s_fin, NV);
     }
+    if (tid == 0 && ok && L.centers_rw != nullptr)   // every CTA has long copied the centres: update them in place
+        km_lloyd_update(k, D, L.kind, s_fin, L.centers_rw, L.state, L.stop_dist, L.max_iter);
 }
 
 // sharded Lloyd loop: the update alone, on the all-reduced [sums | counts] (one thread)
@@ -658,6 +738,9 @@ extern "C" int yb_kmeans_assign(const double* data, int64_t n_points, int n_dim,
     L.centers_rw = nullptr;
     L.stop_dist = 0.0;
     L.max_iter = 0;
+    for (int i = 0; i < YB_MAX_PEERS; ++i) L.mailbox[i] = nullptr;
+    L.rank = 0;
+    L.world = 1;
     YB_CUDA_TRY(cudaMemsetAsync(L.counter, 0, sizeof(unsigned int), stream));
     switch (n_dim) {
         case 1: return launch_km_d<1>(L, stream);
@@ -688,10 +771,10 @@ extern "C" size_t yb_kmeans_state_bytes(int k, int n_dim) {
     return sizeof(long long) * (size_t)(4 + YB_KMEANS_HIST + k * (n_dim + 1));
 }
 
-extern "C" int yb_kmeans_lloyd_step(const double* data, int64_t n_points, int n_dim, double* centers, int k,
-                                    int dist_kind, double stop_dist, int64_t max_iternum, int64_t* state,
-                                    double* packed, int32_t* assign, void* workspace, size_t workspace_bytes,
-                                    yb_stream_t stream_) {
+static int lloyd_step_impl(const double* data, int64_t n_points, int n_dim, double* centers, int k, int dist_kind,
+                           double stop_dist, int64_t max_iternum, int64_t* state, double* packed, int32_t* assign,
+                           void* workspace, size_t workspace_bytes, void* const* mailboxes, int rank, int world,
+                           yb_stream_t stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (centers == nullptr || state == nullptr || workspace == nullptr) return YB_E_NULL;
     if (n_points > 0 && data == nullptr) return YB_E_NULL;
@@ -722,12 +805,74 @@ extern "C" int yb_kmeans_lloyd_step(const double* data, int64_t n_points, int n_
     L.centers_rw = (packed == nullptr) ? centers : nullptr;
     L.stop_dist = stop_dist;
     L.max_iter = max_iternum;
+    for (int i = 0; i < YB_MAX_PEERS; ++i) L.mailbox[i] = nullptr;
+    L.rank = rank;
+    L.world = world;
+    if (mailboxes != nullptr) {
+        if (world < 1 || world > YB_MAX_PEERS || rank < 0 || rank >= world) return YB_E_PARAM;
+        for (int i = 0; i < world; ++i) {
+            if (mailboxes[i] == nullptr) return YB_E_NULL;
+            L.mailbox[i] = reinterpret_cast<unsigned char*>(mailboxes[i]);
+        }
+    }
     switch (n_dim) {
         case 1: return launch_km_d<1>(L, stream);
         case 2: return launch_km_boxes(L, stream);
         case 3: return launch_km_d<3>(L, stream);
         default: return launch_km_d<4>(L, stream);
     }
+}
+
+extern "C" int yb_kmeans_lloyd_step(const double* data, int64_t n_points, int n_dim, double* centers, int k,
+                                    int dist_kind, double stop_dist, int64_t max_iternum, int64_t* state,
+                                    double* packed, int32_t* assign, void* workspace, size_t workspace_bytes,
+                                    yb_stream_t stream) {
+    return lloyd_step_impl(data, n_points, n_dim, centers, k, dist_kind, stop_dist, max_iternum, state, packed, assign,
+                           workspace, workspace_bytes, nullptr, 0, 1, stream);
+}
+
+extern "C" int yb_kmeans_lloyd_step_peers(const double* data, int64_t n_points, int n_dim, double* centers, int k,
+                                          int dist_kind, double stop_dist, int64_t max_iternum, int64_t* state,
+                                          int32_t* assign, void* workspace, size_t workspace_bytes,
+                                          void* const* mailboxes_host, int rank, int world, yb_stream_t stream) {
+    if (mailboxes_host == nullptr) return YB_E_NULL;
+    return lloyd_step_impl(data, n_points, n_dim, centers, k, dist_kind, stop_dist, max_iternum, state, nullptr, assign,
+                           workspace, workspace_bytes, mailboxes_host, rank, world, stream);
+}
+
+extern "C" size_t yb_peer_mailbox_bytes(int world) {
+    if (world < 1 || world > YB_MAX_PEERS) return 0;
+    return align_up(2 * (size_t)world * kPeerSlotBytes, 256);
+}
+
+// The one place this library owns device memory: a mailbox must come from cudaMalloc to be exported
+// to the other ranks' processes (cudaIpcGetMemHandle); the caller frees it with yb_peer_free.
+extern "C" int yb_peer_alloc(size_t bytes, void** dev_ptr, void* ipc_handle64) {
+    if (dev_ptr == nullptr || ipc_handle64 == nullptr || bytes == 0) return YB_E_NULL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    YB_CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+    YB_CUDA_TRY(cudaMemset(*dev_ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    YB_CUDA_TRY(cudaIpcGetMemHandle(&h, *dev_ptr));
+    memcpy(ipc_handle64, &h, sizeof(h));
+    return YB_OK;
+}
+extern "C" int yb_peer_open(const void* ipc_handle64, void** dev_ptr) {
+    if (dev_ptr == nullptr || ipc_handle64 == nullptr) return YB_E_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, sizeof(h));
+    YB_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return YB_OK;
+}
+extern "C" int yb_peer_close(void* dev_ptr) {
+    if (dev_ptr == nullptr) return YB_E_NULL;
+    YB_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+    return YB_OK;
+}
+extern "C" int yb_peer_free(void* dev_ptr) {
+    if (dev_ptr == nullptr) return YB_E_NULL;
+    YB_CUDA_TRY(cudaFree(dev_ptr));
+    return YB_OK;
 }
 
 extern "C" int yb_kmeans_lloyd_init(int64_t* state, int k, int n_dim, void* workspace, size_t workspace_bytes,

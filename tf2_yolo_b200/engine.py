@@ -491,7 +491,7 @@ class KMeansLloyd:
     """Device-resident Lloyd loop (yb_kmeans_lloyd_init / _step / _update): the boxes, the centres and
     the loop state stay on the GPU; ``step()`` queues one iteration without touching the host."""
 
-    def __init__(self, data, centers, dist_kind, stop_dist, max_iternum, sharded=False):
+    def __init__(self, data, centers, dist_kind, stop_dist, max_iternum, sharded=False, peer_group=None):
         require_cuda(data, centers)
         if data.dtype != _F64 or centers.dtype != _F64:
             raise N.YoloB200Error("kmeans needs float64")
@@ -507,12 +507,62 @@ class KMeansLloyd:
             self.ws_bytes = N.lib.yb_kmeans_workspace_bytes(data.shape[0], self.k, self.d)
             self.ws = torch.empty(self.ws_bytes + 256, dtype=torch.uint8, device=dev)
             self.ws_ptr = self.ws.data_ptr() + ((-self.ws.data_ptr()) % 256)
-            self.packed = torch.zeros(self.k * (self.d + 1), dtype=_F64, device=dev) if sharded else None
+            self.packed = torch.zeros(self.k * (self.d + 1), dtype=_F64, device=dev) if (sharded and peer_group is None) else None
             N.check(N.lib.yb_kmeans_lloyd_init(_ptr(self.state), self.k, self.d, C.c_void_p(self.ws_ptr), self.ws_bytes,
                                                _stream()), "yb_kmeans_lloyd_init")
+            self.peers = None
+            if peer_group is not None:
+                self._open_peers(peer_group)
+
+    def _open_peers(self, group):
+        """Mailboxes for the in-kernel all-reduce: allocate + export ours, open every peer's
+        (handles travel through the process group once)."""
+        import torch.distributed as dist
+        alone = isinstance(group, str) and group == "self"     # a single rank exchanging with itself (tests)
+        self.world, self.rank = (1, 0) if alone else (dist.get_world_size(group), dist.get_rank(group))
+        nbytes = N.lib.yb_peer_mailbox_bytes(self.world)
+        if nbytes == 0:
+            raise ValueError(f"peer exchange supports up to {N.YB_MAX_PEERS} ranks")
+        own, handle = C.c_void_p(), (C.c_char * 64)()
+        N.check(N.lib.yb_peer_alloc(nbytes, C.byref(own), handle), "yb_peer_alloc")
+        handles = [None] * self.world
+        if alone:
+            handles[0] = bytes(handle.raw)
+        else:
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        ptrs = (C.c_void_p * self.world)()
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                ptrs[r] = own.value
+            else:
+                p = C.c_void_p()
+                N.check(N.lib.yb_peer_open((C.c_char * 64).from_buffer_copy(h), C.byref(p)), "yb_peer_open")
+                ptrs[r] = p.value
+                self._opened.append(p.value)
+        self._own_mailbox = own.value
+        self.peers = ptrs
+        if not alone:
+            dist.barrier(group=group)  # every mailbox is mapped everywhere before the first exchange
+
+    def close(self):
+        """Release the peer mappings and the mailbox (after a barrier: nobody may still write to it)."""
+        if self.peers is not None:
+            torch.cuda.synchronize()
+            for p in self._opened:
+                N.lib.yb_peer_close(C.c_void_p(p))
+            N.lib.yb_peer_free(C.c_void_p(self._own_mailbox))
+            self.peers = None
 
     def step(self, assign=None):
-        """The assignment pass (+ the update when not sharded) of one iteration."""
+        """The assignment pass (+ the update when not sharded, + the peer all-reduce and the update
+        when sharded over peer memory) of one iteration."""
+        if self.peers is not None:
+            N.check(N.lib.yb_kmeans_lloyd_step_peers(_ptr(self.data), self.data.shape[0], self.d, _ptr(self.centers),
+                                                     self.k, self.kind, self.stop, self.max_iter, _ptr(self.state),
+                                                     _ptr(assign), C.c_void_p(self.ws_ptr), self.ws_bytes, self.peers,
+                                                     self.rank, self.world, _stream()), "yb_kmeans_lloyd_step_peers")
+            return
         N.check(N.lib.yb_kmeans_lloyd_step(_ptr(self.data), self.data.shape[0], self.d, _ptr(self.centers), self.k,
                                            self.kind, self.stop, self.max_iter, _ptr(self.state), _ptr(self.packed),
                                            _ptr(assign), C.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),

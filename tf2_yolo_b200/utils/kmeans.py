@@ -111,12 +111,15 @@ def _bcast(arr, process_group):
 
 
 def kmeans(data, n_cluster, dist_func, stop_dist, max_iternum=10000, verbose=True,
-           process_group=None, return_assignments=False, check_every=8):
+           process_group=None, return_assignments=False, check_every=8, exchange="nccl"):
     """k-means with the reference's semantics; ``data`` is (num_samples, num_dims) as an ndarray
     or a float64 CUDA tensor (this rank's shard when ``process_group`` is given).
     ``check_every`` iterations are queued between two looks at the loop state (any value gives the
     same centres).  ``return_assignments``: also the assignment of every box against the returned
-    (float64, pre-rounding) centres."""
+    (float64, pre-rounding) centres.  ``exchange``: how the k*(d+1) partial sums of a sharded
+    iteration are all-reduced - "nccl" (an all-reduce on the same stream between the assignment
+    launch and a small update launch) or "peer" (inside the assignment launch, over NVLink peer
+    memory: one launch per iteration; ranks of one node, NCCL group for the handle exchange)."""
     kind = _kind_of(dist_func)
     own_dist = iou_dist if kind == YB_DIST_IOU else euclidean_dist
     if torch.is_tensor(data):
@@ -140,13 +143,16 @@ def kmeans(data, n_cluster, dist_func, stop_dist, max_iternum=10000, verbose=Tru
 
     with torch.cuda.device(dev):
         dev_center = torch.from_numpy(np.ascontiguousarray(center.reshape(n_cluster, n_dim))).to(dev)
-        loop = engine.KMeansLloyd(dev_data, dev_center, kind, stop_dist, max_iternum, sharded=sharded)
+        if exchange not in ("nccl", "peer"):
+            raise ValueError(f"Invalid exchange: {exchange}")
+        peer = process_group if (sharded and exchange == "peer") else None
+        loop = engine.KMeansLloyd(dev_data, dev_center, kind, stop_dist, max_iternum, sharded=sharded, peer_group=peer)
         seen = 0          # updates whose loss has been reported
         check_every = max(1, min(int(check_every), engine.N.YB_KMEANS_HIST))
         while True:
             for _ in range(check_every):
                 loop.step()
-                if sharded:
+                if sharded and peer is None:
                     dist_util.allreduce_sum(loop.packed, process_group)   # same stream, no host sync
                     loop.update()
             status, done, hist, sums, counts = loop.read_state()
@@ -176,12 +182,18 @@ def kmeans(data, n_cluster, dist_func, stop_dist, max_iternum=10000, verbose=Tru
                 dev_center.copy_(torch.from_numpy(np.ascontiguousarray(new_center.reshape(n_cluster, n_dim))))
                 status = 1 if loss < stop_dist else (2 if done + 1 > max_iternum else 0)
                 loop.resume(status, done)
+            if status == 4:
+                raise YoloB200Error("k-means peer exchange timed out: a rank did not issue its iteration")
             if status != 0:
                 break
         center = dev_center.cpu().numpy()
         assign = None
         if return_assignments:
             assign, _, _ = engine.kmeans_assign(dev_data, dev_center, kind, want_assign=True)
+        if peer is not None:
+            import torch.distributed as dist
+            dist.barrier(group=process_group)
+            loop.close()
     center = center.reshape((n_cluster, n_dim)).astype("float32")
     if return_assignments:
         return center, assign

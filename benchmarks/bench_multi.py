@@ -244,7 +244,10 @@ def run_map_config5(out, rank, world, dev, group, n_img_total, pool=256, check=1
                 yield d_true[idx], [p[idx] for p in d_preds]
         return source
     kw = dict(class_names=names, conf_threshold=0.05, nms_mode=1, nms_threshold=0.5, max_per_img=100, version=4)
-    meas.PRfunc(None, chunk_source=source_of(0, min(64, n_img_total)), **kw)      # warm (allocator, kernels)
+    # warm-up on a slice of this rank's images, through the same collectives (NCCL sets up its
+    # all-to-all connections on first use: seconds at 8 ranks), then the timed run
+    meas.PRfunc(None, process_group=group, partition_classes=world > 1,
+                chunk_source=source_of(a, min(b, a + 2 * chunk)), **kw).get_map()
     torch.cuda.synchronize()
     barrier(world)
     t0 = time.perf_counter()

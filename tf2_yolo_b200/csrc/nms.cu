@@ -296,6 +296,8 @@ struct BigShared {
     int nkept;
     int nlist;
     long long scan[32];
+    unsigned short bpos[kSweep];            // visit positions of the current block (alive-list sweep)
+    int wc[2][2][kBigThreads / 32];         // per-pass, per-item-row, per-warp survivor counts (ordered compaction)
 };
 
 // One segment.  The planes hold the boxes in VISIT order: X = (x0, x1), Y = (y0, y1), C = (x, y)
@@ -407,9 +409,163 @@ __device__ __forceinline__ void nms_segment(const double* __restrict__ rows, dou
     //    that are still alive behind the last finished block, compacted after every block, so the
     //    threads share the remaining boxes evenly and no lane carries a dead box; without it the
     //    threads stride over all positions behind the block.
+    if (SMEM && MODE != 3) {
+        // Blocks of the next kSweep boxes that are STILL ALIVE, in visit order (the list of alive
+        // positions is compacted in order after every block): a dense scene kills most boxes early,
+        // so the number of blocks - each a mask build, a serial resolve and a handful of barriers -
+        // follows the boxes that survive until they are visited, not the segment size.
+        const unsigned short* cur = nullptr;       // nullptr: the identity list 0 .. n-1
+        unsigned short* bufs[2] = {alist, alist + kBigCap};
+        int which = 0, n_list = n;
+        const int lane = tid & 31, wrp = tid >> 5;
+        while (n_list > 0) {
+            const int m = min(kSweep, n_list);
+            if (tid < kSweep) {
+                S.mask[tid] = 0ull;
+                if (tid < m) S.bpos[tid] = cur ? cur[tid] : (unsigned short)tid;
+            }
+            __syncthreads();
+            {   // 64x64 upper-triangular mask over the block's boxes, kMaskParts threads per row
+                constexpr int kCols = 64 / kMaskParts;
+                const int i = tid / kMaskParts, part = tid % kMaskParts;
+                if (i < m) {
+                    const int vi = S.bpos[i];
+                    const BoxC bi = load_box(vi);
+                    unsigned long long bits = 0ull;
+                    const int j0 = max(part * kCols, i + 1), j1 = min(part * kCols + kCols, m);
+                    for (int j = j0; j < j1; ++j) {
+                        const int vj = S.bpos[j];
+                        const BoxC bj = load_box(vj);
+                        int r = suppresses_fast<M>(bi, bj, thr, pos_thr);
+                        if (r < 0) r = suppresses_exact<M>(rows, mem[ord[vi]], mem[ord[vj]], thr) ? 1 : 0;
+                        if (r) bits |= 1ull << j;
+                    }
+                    if (bits) atomicOr(&S.mask[i], bits);
+                }
+            }
+            __syncthreads();
+            const bool last_block = n_list == m;
+            if (tid < 32) {
+                // resolve the block in warp 0: lane l owns rows l and l+32; the serial chain over the
+                // 64 rows runs on register shuffles, replicated in every lane
+                const unsigned long long m0 = S.mask[tid], m1 = S.mask[tid + 32];
+                unsigned long long dead = (m >= 64) ? 0ull : (~0ull << m);   // rows >= m do not exist
+#pragma unroll
+                for (int i = 0; i < kSweep; ++i) {
+                    const unsigned long long mi = __shfl_sync(0xffffffffu, (i < 32) ? m0 : m1, i & 31);
+                    if (!((dead >> i) & 1ull)) dead |= mi;
+                }
+                const unsigned long long kept_bits = ~dead;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int bp = tid + 32 * h;
+                    if (bp < m) {
+                        const bool kf = (kept_bits >> bp) & 1ull;
+                        const int v = S.bpos[bp];
+                        rem[v] = kf ? 0 : 1;
+                        if (kf && !last_block) {   // kept boxes of this block, compact
+                            const int q = __popcll(kept_bits & ((1ull << bp) - 1ull));
+                            S.kX[q] = X[v];
+                            S.kY[q] = Y[v];
+                            if (M == 2) S.kC[q] = C[v];
+                            S.kA[q] = A[v];
+                            S.krow[q] = mem[ord[v]];
+                        }
+                    }
+                }
+                if (tid == 0) S.nkept = __popcll(kept_bits);
+            }
+            __syncthreads();
+            if (last_block) break;   // nothing behind the block (uniform)
+            const int nk = S.nkept;
+            const int n_items = n_list - m;
+            unsigned short* next = bufs[which];
+            int out_base = 0;        // survivors written so far: the same value in every thread
+            // every listed box behind the block against the block's kept boxes, kJpt boxes per
+            // thread in flight (independent fp64 chains; the kept box is one broadcast load for all)
+            for (int base = 0, pass = 0; base < n_items; base += kBigThreads * kJpt, ++pass) {
+                double2 jx[kJpt], jy[kJpt];   // corners only: area / centre are fetched for overlapping pairs
+                int jj[kJpt];
+                bool alive[kJpt];
+                bool any = false;
+#pragma unroll
+                for (int u = 0; u < kJpt; ++u) {
+                    const int slot = base + u * kBigThreads + tid;
+                    alive[u] = slot < n_items;
+                    jj[u] = 0;
+                    if (alive[u]) {
+                        jj[u] = cur ? (int)cur[m + slot] : m + slot;
+                        jx[u] = X[jj[u]];
+                        jy[u] = Y[jj[u]];
+                    }
+                    any |= alive[u];
+                }
+                if (any) {
+                    for (int q = 0; q < nk; ++q) {
+                        const double2 ix = S.kX[q], iy = S.kY[q];
+                        any = false;
+#pragma unroll
+                        for (int u = 0; u < kJpt; ++u) {
+                            if (alive[u]) {
+                                const double iw = sel_min(ix.y, jx[u].y) - sel_max(ix.x, jx[u].x);
+                                const double ih = sel_min(iy.y, jy[u].y) - sel_max(iy.x, jy[u].x);
+                                int r = -1;
+                                if (pos_thr) {
+                                    r = 0;
+                                    if (iw > 0.0 && ih > 0.0) {
+                                        double ew = 0.0, eh = 0.0, dx = 0.0, dy = 0.0;
+                                        if (M == 2) {
+                                            ew = sel_max(ix.y, jx[u].y) - sel_min(ix.x, jx[u].x);
+                                            eh = sel_max(iy.y, jy[u].y) - sel_min(iy.x, jy[u].x);
+                                            const double2 ic = S.kC[q], jc = C[jj[u]];
+                                            dx = ic.x - jc.x;
+                                            dy = ic.y - jc.y;
+                                        }
+                                        r = decide_overlapping<M>(iw, ih, S.kA[q], A[jj[u]], ew, eh, dx, dy, thr);
+                                    }
+                                }
+                                if (r < 0) r = suppresses_exact<M>(rows, S.krow[q], mem[ord[jj[u]]], thr) ? 1 : 0;
+                                if (r) {
+                                    alive[u] = false;
+                                    rem[jj[u]] = 1;
+                                }
+                            }
+                            any |= alive[u];
+                        }
+                        if (!any) break;
+                    }
+                }
+                // survivors of this pass go to the next list IN ORDER: per-warp counts, then every
+                // thread walks the (item row, warp) table up to its own entry
+                unsigned bal[kJpt];
+#pragma unroll
+                for (int u = 0; u < kJpt; ++u) {
+                    bal[u] = __ballot_sync(0xffffffffu, alive[u]);
+                    if (lane == 0) S.wc[pass & 1][u][wrp] = __popc(bal[u]);
+                }
+                __syncthreads();
+                int run = out_base, my_off[kJpt];
+#pragma unroll
+                for (int u = 0; u < kJpt; ++u) {
+                    for (int w = 0; w < kBigThreads / 32; ++w) {
+                        if (w == wrp) my_off[u] = run;
+                        run += S.wc[pass & 1][u][w];
+                    }
+                }
+                out_base = run;
+#pragma unroll
+                for (int u = 0; u < kJpt; ++u)
+                    if (alive[u]) next[my_off[u] + __popc(bal[u] & ((1u << lane) - 1u))] = (unsigned short)jj[u];
+            }
+            __syncthreads();   // the next list is complete
+            cur = next;
+            n_list = out_base;
+            which ^= 1;
+        }
+    }
     unsigned short* cur_list = nullptr;   // nullptr: implicit list = every position behind the block
     int n_list = 0;
-    for (int blk = 0; MODE != 3 && blk < n; blk += kSweep) {
+    for (int blk = 0; !SMEM && MODE != 3 && blk < n; blk += kSweep) {
         const int m = min(kSweep, n - blk);
         if (tid < kSweep) S.mask[tid] = 0ull;
         __syncthreads();

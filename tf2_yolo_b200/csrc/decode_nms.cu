@@ -92,12 +92,15 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     unsigned int* s_ccount = reinterpret_cast<unsigned int*>(fsm + lay.ccount);
     unsigned int* s_cstart = reinterpret_cast<unsigned int*>(fsm + lay.cstart);
     unsigned int* s_ckept = reinterpret_cast<unsigned int*>(fsm + lay.ckept);
-    __shared__ unsigned int s_img, s_kept;
+    __shared__ unsigned int s_img, s_kept, s_next_class;
     __shared__ long long s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    if (tid == 0) s_img = atomicAdd(F.ticket, 1u);   // images in ticket order: predecessors are running
+    if (tid == 0) {
+        s_img = atomicAdd(F.ticket, 1u);   // images in ticket order: predecessors are running
+        s_next_class = 0u;
+    }
     for (int c = tid; c < C; c += kFusedThreads) {
         s_ccount[c] = 0u;
         s_ckept[c] = 0u;
@@ -163,8 +166,13 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     __syncthreads();
     const bool pos_thr = F.nms_thr > 0.0;
     const double nms_thr = F.nms_thr;
-    // ---- 4. one warp per class: greedy sweep in visit order ----------------------------------------
-    for (int c = warp; c < C; c += kFusedWarps) {
+    // ---- 4. one warp per class: greedy sweep in visit order.  Classes are handed out by a counter
+    //         (a static round-robin leaves warps idle while one works through two large classes) ----
+    for (;;) {
+        int c = 0;
+        if (lane == 0) c = (int)atomicAdd(&s_next_class, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= C) break;
         const int n = (int)s_ccount[c];
         if (n == 0) continue;
         const int start = (int)s_cstart[c];

@@ -471,6 +471,8 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                     }
                 }
                 const float resp = (lb == amax) ? 1.f : 0.f;
+                int dec_n = 0;                                            // hits of this lane's box
+                unsigned my_img = 0, my_cellpos = 0, my_cis = 0, my_base = 0;
                 if (kDecode) {
                     // head decode, counting pass (utils/tools.py:411-412), on the tile that is already in
                     // shared memory: hits of c*p_k >= thr per cell, stored in decode OUTPUT order, cells
@@ -487,7 +489,7 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         tot += nq;
                         before += (q < lb) ? nq : 0;
                     }
-                    unsigned my_img = 0, my_cellpos = 0, my_cis = 0;
+                    dec_n = n;
                     if (valid) {
                         const long long g = cell0 + cell;
                         const long long img = g / L.dec_cells[s];
@@ -499,44 +501,10 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         my_cellpos = (unsigned)(o - img * L.dec_per_img);
                         my_cis = ((unsigned)s << 28) | (unsigned)(g - img * L.dec_cells[s]);
                     }
-                    if (L.dec_buckets.n != nullptr) {
-                        // rows of the boxes with hits into their image's bucket: the WARP serves one hot
-                        // box at a time (32 class scores per step, ballot, lane-parallel row writes) -
-                        // a lane walking its own C scores again would stall the other 31 for C steps
-                        unsigned hot = __ballot_sync(0xffffffffu, valid && n > 0);
-                        // every hot lane reserves its rows first: the atomics' round trips overlap
-                        unsigned my_base = 0;
-                        if (valid && n > 0) my_base = atomicAdd(&L.dec_buckets.n[my_img], (unsigned)n);
-                        while (hot) {
-                            const int src = __ffs(hot) - 1;
-                            hot &= hot - 1;
-                            const int hcell = __shfl_sync(0xffffffffu, cell, src), hlb = __shfl_sync(0xffffffffu, lb, src);
-                            const float hc = __shfl_sync(0xffffffffu, c, src);
-                            const float hx = __shfl_sync(0xffffffffu, px, src), hy = __shfl_sync(0xffffffffu, py, src);
-                            const float hw = __shfl_sync(0xffffffffu, pw, src), hh = __shfl_sync(0xffffffffu, ph, src);
-                            const unsigned himg = __shfl_sync(0xffffffffu, my_img, src);
-                            const unsigned hpos = __shfl_sync(0xffffffffu, my_cellpos, src);
-                            const unsigned hcis = __shfl_sync(0xffffffffu, my_cis, src);
-                            unsigned u = __shfl_sync(0xffffffffu, my_base, src);
-                            const float* hprob = (V == 1) ? sp + hcell * S.pcf + 5 * B : sp + hcell * S.pcf + hlb * bstride + 5;
-                            FusedRow* dst = L.dec_buckets.row + (size_t)himg * L.dec_buckets.cap;
-                            for (int k0 = 0; k0 < C; k0 += 32) {
-                                const int k = k0 + lane;
-                                const float p = (k < C) ? hprob[k] : 0.f;
-                                const bool hit = (k < C) && (__fmul_rn(hc, p) >= L.dec_thr);
-                                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                                const unsigned at = u + __popc(m & ((1u << lane) - 1u));
-                                if (hit && at < (unsigned)L.dec_buckets.cap) {
-                                    FusedRow fr;
-                                    fr.key = fused_key(hpos, hlb, k);
-                                    fr.x = hx; fr.y = hy; fr.w = hw; fr.h = hh; fr.c = hc; fr.p = p;
-                                    fr.cell = hcis;
-                                    dst[at] = fr;
-                                }
-                                u += __popc(m);
-                            }
-                        }
-                    }
+                    // a hot lane reserves its rows in the image's bucket NOW and uses them after the loss
+                    // arithmetic below: the atomic's round trip to L2 hides behind it
+                    if (L.dec_buckets.n != nullptr && valid && n > 0)
+                        my_base = atomicAdd(&L.dec_buckets.n[my_img], (unsigned)n);
                 }
                 if (kMetrics) {
                     // In-training metrics of yolov*/metrics/yolo_metrics.py folded into this pass (they
@@ -686,6 +654,44 @@ loss_fwd_bwd_kernel(const __grid_constant__ LossLaunch L) {
                         g0 *= px * (1.f - px); g1 *= py * (1.f - py); g4 *= c * (1.f - c);
                         g2 *= pw; g3 *= ph;
                     }
+                }
+                if (kDecode && L.dec_buckets.n != nullptr) {
+                    // rows of the boxes with hits into their image's bucket (before the gradients overwrite
+                    // the tile): the WARP serves one hot box at a time (32 class scores per step, ballot,
+                    // lane-parallel row writes) - a lane walking its own C scores again would stall the
+                    // other 31 for C steps
+                    unsigned hot = __ballot_sync(0xffffffffu, valid && dec_n > 0);
+                    while (hot) {
+                        const int src = __ffs(hot) - 1;
+                        hot &= hot - 1;
+                        const int hcell = __shfl_sync(0xffffffffu, cell, src), hlb = __shfl_sync(0xffffffffu, lb, src);
+                        const float hc = __shfl_sync(0xffffffffu, c, src);
+                        const float hx = __shfl_sync(0xffffffffu, px, src), hy = __shfl_sync(0xffffffffu, py, src);
+                        const float hw = __shfl_sync(0xffffffffu, pw, src), hh = __shfl_sync(0xffffffffu, ph, src);
+                        const unsigned himg = __shfl_sync(0xffffffffu, my_img, src);
+                        const unsigned hpos = __shfl_sync(0xffffffffu, my_cellpos, src);
+                        const unsigned hcis = __shfl_sync(0xffffffffu, my_cis, src);
+                        unsigned u = __shfl_sync(0xffffffffu, my_base, src);
+                        const float* hprob = (V == 1) ? sp + hcell * S.pcf + 5 * B : sp + hcell * S.pcf + hlb * bstride + 5;
+                        FusedRow* dst = L.dec_buckets.row + (size_t)himg * L.dec_buckets.cap;
+                        for (int k0 = 0; k0 < C; k0 += 32) {
+                            const int k = k0 + lane;
+                            const float p = (k < C) ? hprob[k] : 0.f;
+                            const bool hit = (k < C) && (__fmul_rn(hc, p) >= L.dec_thr);
+                            const unsigned m = __ballot_sync(0xffffffffu, hit);
+                            const unsigned at = u + __popc(m & ((1u << lane) - 1u));
+                            if (hit && at < (unsigned)L.dec_buckets.cap) {
+                                FusedRow fr;
+                                fr.key = fused_key(hpos, hlb, k);
+                                fr.x = hx; fr.y = hy; fr.w = hw; fr.h = hh; fr.c = hc; fr.p = p;
+                                fr.cell = hcis;
+                                dst[at] = fr;
+                            }
+                            u += __popc(m);
+                        }
+                    }
+                }
+                if (valid) {
                     if (write) {
                         pc[0] = g0; pc[1] = g1; pc[2] = g2; pc[3] = g3; pc[4] = g4;
                         // class scores of a non-responsible box get exactly zero gradient;

@@ -275,7 +275,15 @@ def run_ours(args):
     loss_ev = []
 
     mode = "unfused" if args.unfused else ("chain" if args.chain else "fused")
-    step_loss = torch.empty(3, dtype=torch.float32, device=dev)
+    step_loss = [torch.empty(3, dtype=torch.float32, device=dev) for _ in range(2)]   # double-buffered
+    in_flight = [None, None]     # the asynchronous loss all-reduce of each buffer
+    step_no = [0]
+
+    def join_collectives():      # every rank's loss scalars are global after this
+        for i in range(2):
+            if in_flight[i] is not None:
+                in_flight[i].wait()
+                in_flight[i] = None
     fused_out = dict(out_rows=torch.empty((ROWS_PER_IMG_FUSED * batch, 7), dtype=torch.float64, device=dev),
                      out_offsets=torch.empty(batch + 1, dtype=torch.int64, device=dev),
                      n_overflow=torch.zeros(1, dtype=torch.int32, device=dev))
@@ -285,21 +293,23 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if mode == "fused":   # two launches: loss + counting pass, then decode + NMS with one CTA per image
-            pending = []
+            slot = step_no[0] & 1
+            step_no[0] += 1
+            if in_flight[slot] is not None:      # the all-reduce that last used this loss buffer (two steps ago)
+                in_flight[slot].wait()
+                in_flight[slot] = None
 
             def after_loss():   # between the two launches: the loss scalars are final
                 if record:
                     e1.record()
                     loss_ev.append((e0, e1))
-                if world > 1:   # the only collective (3 scalars) runs beside the decode + NMS kernel
-                    pending.append(dist.all_reduce(loss_box[0], async_op=True))
-            loss_box = [None]
+                if world > 1:   # the only collective (3 scalars): runs beside the decode + NMS kernel and
+                    # the next step's loss kernel; it is joined when its buffer comes round again
+                    in_flight[slot] = dist.all_reduce(step_loss[slot], async_op=True)
             loss, _, _, res = engine.loss_decode_nms_fused(params, y_t, y_p, CONF_THR, NMS_THR, NMS_MODE,
                                                            rows_per_img_cap=ROWS_PER_IMG_FUSED,
                                                            global_batch=global_batch, dpreds=dpreds, out=fused_out,
-                                                           split_hook=after_loss, loss_out=step_loss, loss_box=loss_box)
-            for w in pending:
-                w.wait()
+                                                           split_hook=after_loss, loss_out=step_loss[slot])
             return loss, None, res
         if args.unfused:
             loss, _, _ = fused_losses(fns, y_t, y_p, global_batch=global_batch, dpreds=dpreds)
@@ -322,6 +332,7 @@ def run_ours(args):
         return loss, offs, res
 
     def barrier():
+        join_collectives()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -370,6 +381,7 @@ def run_ours(args):
         ev0.record()
         for _ in range(args.steps):
             out = step(dev_t, dev_p, record=True)
+        join_collectives()          # the round ends when every step's collective has completed
         ev1.record()
         barrier()
         round_ms.append(agree(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None))

@@ -289,15 +289,15 @@ def run_ours(args):
                      n_overflow=torch.zeros(1, dtype=torch.int32, device=dev))
 
     def step(y_t, y_p, record=False):
+        slot = step_no[0] & 1
+        step_no[0] += 1
+        if mode == "fused" and in_flight[slot] is not None:   # the all-reduce that last used this loss buffer
+            in_flight[slot].wait()                            # (two steps ago)
+            in_flight[slot] = None
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if mode == "fused":   # two launches: loss + counting pass, then decode + NMS with one CTA per image
-            slot = step_no[0] & 1
-            step_no[0] += 1
-            if in_flight[slot] is not None:      # the all-reduce that last used this loss buffer (two steps ago)
-                in_flight[slot].wait()
-                in_flight[slot] = None
 
             def after_loss():   # between the two launches: the loss scalars are final
                 if record:

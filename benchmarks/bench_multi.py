@@ -253,12 +253,13 @@ def run_map_config5(out, rank, world, dev, group, n_img_total, pool=256, check=1
     t0 = time.perf_counter()
     pr = meas.PRfunc(None, process_group=group, partition_classes=world > 1, chunk_source=source_of(a, b), **kw)
     t1 = time.perf_counter()
-    split = {}
-    meas.PRfunc(None, process_group=group, partition_classes=world > 1, chunk_source=source_of(a, b), timings=split, **kw)
     tab = pr.get_map()
     barrier(world)
     dt = max_over_ranks(time.perf_counter() - t0, world, dev)
     dt_curves = max_over_ranks(t1 - t0, world, dev)
+    split = {}      # the same once more with the device synchronised between the phases
+    meas.PRfunc(None, process_group=group, partition_classes=world > 1, chunk_source=source_of(a, b), timings=split, **kw)
+    barrier(world)
     n_rec = sum(len(p) - 1 for p in pr.precisions if p is not None)
     n_rec = int(max_over_ranks(float(n_rec), world, dev))
     if rank == 0:

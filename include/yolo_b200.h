@@ -393,6 +393,14 @@ int yb_pr_curve(const double* conf, const int32_t* cls, const int64_t* gt_id, co
                 int64_t* tp_cum, int64_t* tpp_cum, void* workspace, size_t workspace_bytes,
                 yb_stream_t stream);
 
+/* Precision / recall of every prefix of every class (utils/measurement.py:302-319) from the running
+ * counts of yb_pr_curve: class_start (class_num+1 int64, device) = extents of the classes in the
+ * sorted array, gts (class_num int64, device) = ground truths per class (> 0 wherever a class has
+ * records).  precision_mode 0: tpp/dets, 1: tp/(tp+fp), 2: tp/dets; recall = tp/gts. */
+int yb_pr_points(const int64_t* tp_cum, const int64_t* tpp_cum, const int64_t* class_start,
+                 const int64_t* gts, int class_num, int64_t n_det, int precision_mode,
+                 double* precision, double* recall, yb_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * Label-side helpers.
  * yb_down2x_labels: utils/tools.py:342-367 (down2xlabel): (n_img, gh, gw, channels) labels,

@@ -136,3 +136,23 @@ def test_synth_shapes_and_invariants():
     assert all(np.array_equal(a, b) for a, b in zip(cfg["y_preds"], again["y_preds"]))
     assert ydist.shard_range(10, 3, 4) == (8, 10) and ydist.shard_range(7, 0, 8) == (0, 1)
     assert sum(b - a for a, b in (ydist.shard_range(1001, r, 8) for r in range(8))) == 1001
+
+
+def test_prfunc_call_fast_path_equals_the_reference_expression():
+    """PRfunc.__call__: binary search + suffix maxima == `(recalls > r).sum()` / `precisions[-k:].max()`
+    (utils/measurement.py:333-337) on sorted recalls; unsorted or NaN inputs take the literal form."""
+    rng = np.random.default_rng(4)
+    pr = meas.PRfunc.__new__(meas.PRfunc)
+    pr.class_num = 3
+    tp = np.cumsum(rng.integers(0, 2, 500))
+    rec = np.append(tp / 200.0, tp[-1] / 200.0)                  # non-decreasing + the sentinel
+    prec = np.append(tp / np.arange(1, 501), 0)
+    pr.recalls = [rec, rng.permutation(rec), np.array([0.5])]
+    pr.precisions = [prec, prec, np.array([0.0])]
+    for c in range(3):
+        for r in [0, 0.14, 0.29, 0.43, 0.57, 0.71, 1, -1.0, 2.0, float(rec[10]), float(rec[-1]), 0.5]:
+            k = (pr.recalls[c] > r).sum()
+            want = 0 if k == 0 else pr.precisions[c][-k:].max()
+            got = pr(r, c)
+            assert got == want and type(got) is type(want), (c, r)
+    assert pr._suffix_max[1] is None and pr._suffix_max[0] is not None

@@ -127,6 +127,7 @@ SIGNATURES = {
     "yb_map_accumulate": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _dbl, _i64, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _sz, _vp]),
     "yb_map_append": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "yb_pr_points": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "yb_pr_curve_workspace_bytes": (_sz, [_i64, _i64]),
     "yb_pr_curve": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
 }

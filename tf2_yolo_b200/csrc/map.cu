@@ -403,6 +403,34 @@ __global__ void map_append_kernel(const double* __restrict__ conf, const long lo
     }
 }
 
+// precision / recall of every prefix of every class (utils/measurement.py:302-319), from the running
+// counts of yb_pr_curve: record i of the sorted array belongs to the class whose extent
+// [class_start[c], class_start[c+1]) contains it; num_dets = i - start + 1, num_tp / num_tpp =
+// counts since the class start; precision by mode (0: tpp/dets, 1: tp/(tp+fp), 2: tp/dets),
+// recall = tp / gts - int64 / int64 true divisions, as NumPy does them (exact conversions below 2^53).
+__global__ void pr_points_kernel(const long long* __restrict__ tp_cum, const long long* __restrict__ tpp_cum,
+                                 const long long* __restrict__ class_start, const long long* __restrict__ gts,
+                                 int C, long long n, int mode, double* __restrict__ precision,
+                                 double* __restrict__ recall) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = C;   // class_start[lo] <= i < class_start[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (class_start[mid] <= i) lo = mid; else hi = mid;
+        }
+        const long long a = class_start[lo];
+        const long long tp = tp_cum[i + 1] - tp_cum[a], tpp = tpp_cum[i + 1] - tpp_cum[a];
+        const long long dets = i - a + 1, fp = dets - tpp;
+        double p;
+        if (mode == 0) p = (double)tpp / (double)dets;
+        else if (mode == 1) p = (double)tp / (double)(tp + fp);
+        else p = (double)tp / (double)dets;
+        precision[i] = p;
+        recall[i] = (double)tp / (double)gts[lo];
+    }
+}
+
 static long long next_pow2(long long n) {
     long long p = kSortTile;
     while (p < n) p <<= 1;
@@ -476,6 +504,26 @@ extern "C" int yb_map_append(const double* conf, const int64_t* gt_id, const uin
         conf, reinterpret_cast<const long long*>(gt_id), flag, cls, reinterpret_cast<const long long*>(n_src), conf_dst,
         reinterpret_cast<long long*>(gt_id_dst), flag_dst, cls_dst, dst_capacity, reinterpret_cast<long long*>(total),
         counter);
+    YB_CUDA_TRY(cudaGetLastError());
+    return YB_OK;
+}
+
+extern "C" int yb_pr_points(const int64_t* tp_cum, const int64_t* tpp_cum, const int64_t* class_start,
+                            const int64_t* gts, int class_num, int64_t n_det, int precision_mode,
+                            double* precision, double* recall, yb_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n_det < 0 || class_num < 1) return YB_E_SHAPE;
+    if (precision_mode < 0 || precision_mode > 2) return YB_E_PARAM;
+    if (n_det == 0) return YB_OK;
+    if (tp_cum == nullptr || tpp_cum == nullptr || class_start == nullptr || gts == nullptr || precision == nullptr ||
+        recall == nullptr)
+        return YB_E_NULL;
+    const int threads = 256;
+    const int blocks = (int)min((long long)kNumSMs * 8, ((long long)n_det + threads - 1) / threads);
+    pr_points_kernel<<<blocks, threads, 0, stream>>>(
+        reinterpret_cast<const long long*>(tp_cum), reinterpret_cast<const long long*>(tpp_cum),
+        reinterpret_cast<const long long*>(class_start), reinterpret_cast<const long long*>(gts), class_num, n_det,
+        precision_mode, precision, recall);
     YB_CUDA_TRY(cudaGetLastError());
     return YB_OK;
 }

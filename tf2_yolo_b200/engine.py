@@ -670,6 +670,19 @@ def pr_curve(conf, cls, gt_id, flag, gt_table_base, n_gt_total):
     return order[:D], tp, tpp
 
 
+def pr_points(tp_cum, tpp_cum, class_start, gts, precision_mode):
+    """precision / recall of every sorted record (yb_pr_points): two f64[D] CUDA tensors."""
+    require_cuda(tp_cum, tpp_cum, class_start, gts)
+    D = tp_cum.shape[0] - 1
+    dev = tp_cum.device
+    with torch.cuda.device(dev):
+        precision = torch.empty(max(D, 1), dtype=_F64, device=dev)
+        recall = torch.empty(max(D, 1), dtype=_F64, device=dev)
+        N.check(N.lib.yb_pr_points(_ptr(tp_cum), _ptr(tpp_cum), _ptr(class_start), _ptr(gts), gts.shape[0], D,
+                                   int(precision_mode), _ptr(precision), _ptr(recall), _stream()), "yb_pr_points")
+    return precision[:D], recall[:D]
+
+
 # --------------------------------------------------------------------------
 # label-side helpers
 # --------------------------------------------------------------------------

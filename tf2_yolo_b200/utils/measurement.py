@@ -345,34 +345,27 @@ class PRfunc(object):
         order, tp_cum, tpp_cum = engine.pr_curve(acc.conf, acc.cls, acc.gid, acc.flag,
                                                  torch.from_numpy(table).to(dev), int(table[-1]))
         t0 = _tick(timings, "phase2_sort_scan_s", t0)
-        tp_cum = tp_cum.cpu().numpy()
-        tpp_cum = tpp_cum.cpu().numpy()
+        if precision_mode not in (0, 1, 2):
+            raise UnboundLocalError("precision")      # the reference's failure for an unknown mode
         starts = np.concatenate([[0], np.cumsum(acc.class_counts)]).astype(np.int64)
-
+        for class_i in range(class_num):
+            if (self.owned is None or class_i in self.owned) and gts[class_i] == 0:
+                raise ZeroDivisionError(f"class {class_i} has no ground truth (the reference fails here too)")
+        # precision / recall of every prefix on the device (int64 / int64 true divisions as in
+        # measurement.py:311-319), one copy back per array
+        prec_d, rec_d = engine.pr_points(tp_cum, tpp_cum, torch.from_numpy(starts).to(dev),
+                                         torch.from_numpy(np.asarray(acc.gts, dtype=np.int64)).to(dev), precision_mode)
+        prec_h, rec_h = prec_d.cpu().numpy(), rec_d.cpu().numpy()
         precisions, recalls = [], []
         for class_i in range(class_num):
             if self.owned is not None and class_i not in self.owned:
                 precisions.append(None)
                 recalls.append(None)
                 continue
-            num_gts = gts[class_i]
-            if num_gts == 0:
-                raise ZeroDivisionError(f"class {class_i} has no ground truth (the reference fails here too)")
             a, b = int(starts[class_i]), int(starts[class_i + 1])
-            num_tp = tp_cum[a + 1:b + 1] - tp_cum[a]
-            num_tpp = tpp_cum[a + 1:b + 1] - tpp_cum[a]
-            num_dets = np.arange(1, b - a + 1, dtype=np.int64)
-            num_fp = num_dets - num_tpp
-            if precision_mode == 0:
-                precision = num_tpp/num_dets
-            elif precision_mode == 1:
-                precision = num_tp/(num_tp + num_fp)
-            elif precision_mode == 2:
-                precision = num_tp/num_dets
-            recall = num_tp/num_gts
-            last = recall[-1] if b > a else 0.0
-            precisions.append(np.append(precision, 0))
-            recalls.append(np.append(recall, last))
+            last = rec_h[b - 1] if b > a else 0.0
+            precisions.append(np.append(prec_h[a:b], 0))
+            recalls.append(np.append(rec_h[a:b], last))
 
         self.precisions = precisions
         self.recalls = recalls
@@ -385,12 +378,27 @@ class PRfunc(object):
         recalls = self.recalls[class_idx]
         if precisions is None:
             raise KeyError(f"class {class_idx} is owned by another rank (partition_classes=True)")
-        pc_idx = (recalls > recall).sum()
+        # the reference's `(recalls > recall).sum()` / `precisions[-pc_idx:].max()` (measurement.py:333-337):
+        # recall is a running count over a fixed total, i.e. non-decreasing, so the count is a binary
+        # search and the maximum a lookup in the suffix maxima - same numbers, without two passes over
+        # millions of points per query (get_map asks 7 or 11 times per class)
+        fast = self._fast_lookup(class_idx, precisions, recalls)
+        if fast is None:
+            pc_idx = (recalls > recall).sum()
+            return 0 if pc_idx == 0 else precisions[-pc_idx:].max()
+        pc_idx = len(recalls) - int(np.searchsorted(recalls, recall, side="right"))
         if pc_idx == 0:
-            precision = 0
-        else:
-            precision = precisions[-pc_idx:].max()
-        return precision
+            return 0
+        return fast[len(precisions) - pc_idx]
+
+    def _fast_lookup(self, class_idx, precisions, recalls):
+        """Suffix maxima of the class's precisions, or None when its recalls are not sorted."""
+        cache = self.__dict__.setdefault("_suffix_max", {})
+        if class_idx not in cache:
+            ok = (len(recalls) == len(precisions) and len(recalls) > 0 and not np.isnan(precisions).any()
+                  and bool(np.all(recalls[1:] >= recalls[:-1])))
+            cache[class_idx] = np.maximum.accumulate(precisions[::-1])[::-1] if ok else None
+        return cache[class_idx]
 
     def plot_pr_curve(self, class_idx=-1, smooth=False, figsize=None, return_fig=False):
         """Plot PR curve (presentation only; needs matplotlib)."""

@@ -131,3 +131,19 @@ def test_two_launch_step_equals_the_separate_calls():
     for _ in range(3):
         loss2, _, _, r2 = engine.loss_decode_nms_fused([f.params for f in fns], yts, yps, 0.5, 0.45, 2)
         assert torch.equal(loss2, loss0) and torch.equal(r2["out_rows"][:offs[-1]], r["out_rows"][:offs[-1]])
+
+
+def test_checked_form_falls_back_for_shapes_the_per_image_kernel_does_not_take():
+    """class_num > 256 and float64 grids go through the general chain (same result, no error)."""
+    rng = np.random.default_rng(5)
+    p = rng.uniform(0.3, 1.0, (2, 3, 3, 1 * (5 + 300))).astype(np.float32)      # 300 classes
+    t = torch.from_numpy(p).cuda()
+    ref_rows, ref_offs = chain([t], 300, 0.9, 3, 0.45, 1)
+    r, o = engine.decode_nms_batch_exact([t], 300, 0.9, 3, 0.45, 1)
+    assert np.array_equal(r.cpu().numpy(), ref_rows) and np.array_equal(o.cpu().numpy(), ref_offs)
+    with pytest.raises(ValueError):
+        engine.decode_nms_batch([t], 300, 0.9, 3)
+    t64 = torch.from_numpy(p[..., :5 + 4].astype(np.float64)).cuda()
+    r64, o64 = engine.decode_nms_batch_exact([t64], 4, 0.5, 3, 0.45, 1)
+    a, b = chain([t64], 4, 0.5, 3, 0.45, 1)
+    assert np.array_equal(r64.cpu().numpy(), a) and np.array_equal(o64.cpu().numpy(), b)

@@ -180,3 +180,26 @@ def test_config5_kmeans_50m_conservation_and_sampled_assignments():
     # deterministic: same bits on a second pass
     _, s2, c2 = engine.kmeans_assign(data, cen, YB_DIST_IOU)
     assert torch.equal(s2, sums) and torch.equal(c2, counts)
+
+
+def test_config3_two_launch_step_equals_the_chain_at_batch_128():
+    """BASELINE config 3 at its stated size: the two-launch step (loss + counting pass, decode + NMS
+    with one CTA per image) returns the loss, the gradients and the survivors of the separate calls."""
+    import torch
+    from tf2_yolo_b200 import engine, synth
+    from tf2_yolo_b200.grid_loss import fused_losses
+    from tf2_yolo_b200.yolov4.losses import wrap_yolo_loss
+    cfg = synth.make_config("v4-608", batch=128, seed=2)
+    B, C = 3, 80
+    fns = [wrap_yolo_loss((S, S), B, C, anchors=cfg["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1])
+           for si, S in enumerate(cfg["grids"])]
+    yts = [torch.from_numpy(a).cuda() for a in cfg["y_trues"]]
+    yps = [torch.from_numpy(a).cuda() for a in cfg["y_preds"]]
+    loss0, d0, _ = fused_losses(fns, yts, yps)
+    rows, offs = engine.decode_batch_exact(yps, C, 0.5, 4)
+    g = engine.nms_batch(rows, offs, C, 0.45, 2)
+    n = int(g["out_offsets"][-1].item())
+    loss, d, _, r = engine.loss_decode_nms_fused([f.params for f in fns], yts, yps, 0.5, 0.45, 2, rows_per_img_cap=1024)
+    assert int(r["n_overflow"].item()) == 0
+    assert torch.equal(loss, loss0) and all(torch.equal(a, b) for a, b in zip(d, d0))
+    assert torch.equal(r["out_offsets"], g["out_offsets"]) and torch.equal(r["out_rows"][:n], g["out_rows"][:n])

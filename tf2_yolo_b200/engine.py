@@ -354,11 +354,14 @@ def decode_nms_batch_exact(preds, class_num=1, threshold=0.5, version=1, nms_thr
                            rows_per_img_cap=1024):
     """decode_nms_batch with the overflow check (one host sync): falls back to the general chain
     (yb_decode + yb_nms, any size) when an image exceeds the cap.  Returns (rows (K,7), offsets)."""
-    r = decode_nms_batch(preds, class_num, threshold, version, nms_threshold, iou_mode, rows_per_img_cap)
-    if int(r["n_overflow"].item()) == 0:
-        total = int(r["out_offsets"][-1].item())
-        if total <= r["out_rows"].shape[0]:
-            return r["out_rows"][:total], r["out_offsets"]
+    p, n_img = make_decode_params(preds, class_num, threshold, version)
+    supported = (not p.is_f64) and N.lib.yb_decode_nms_workspace_bytes(C.byref(p), n_img, int(rows_per_img_cap)) > 0
+    if supported:   # float32 heads, class_num <= 256, grids below 2^19 cells per image
+        r = decode_nms_batch(preds, class_num, threshold, version, nms_threshold, iou_mode, rows_per_img_cap)
+        if int(r["n_overflow"].item()) == 0:
+            total = int(r["out_offsets"][-1].item())
+            if total <= r["out_rows"].shape[0]:
+                return r["out_rows"][:total], r["out_offsets"]
     rows, offs = decode_batch_exact(preds, class_num, threshold, version)
     g = nms_batch(rows, offs, class_num, nms_threshold, iou_mode)
     return g["out_rows"][:int(g["out_offsets"][-1].item())], g["out_offsets"]

@@ -240,6 +240,17 @@ int yb_loss_decode_nms_fused(const yb_loss_scale* scales_host, int n_scales, flo
                              void* loss_workspace, size_t loss_workspace_bytes, void* fused_workspace,
                              size_t fused_workspace_bytes, yb_stream_t stream);
 
+/* yb_loss_decode_nms_fused for workspaces that the caller ZEROED ONCE (all yb_loss_workspace_bytes /
+ * yb_decode_nms_workspace_bytes bytes) and has handed to nothing but this entry point since: both
+ * kernels leave their control blocks zeroed, so the call is two launches and no memset - the form
+ * a captured CUDA graph replays.  After a call that returned an error, zero them again. */
+int yb_loss_decode_nms_fused_clean(const yb_loss_scale* scales_host, int n_scales, float* loss_out,
+                                   double* terms_out, double decode_threshold, double nms_threshold,
+                                   int iou_mode, int rows_per_img_cap, double* out_rows,
+                                   int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                                   void* loss_workspace, size_t loss_workspace_bytes,
+                                   void* fused_workspace, size_t fused_workspace_bytes, yb_stream_t stream);
+
 int yb_decode_nms_finish(const void* const* preds_host, int64_t n_img, const yb_decode_params* p,
                          double nms_threshold, int iou_mode, int rows_per_img_cap, double* out_rows,
                          int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,

@@ -147,3 +147,43 @@ def test_checked_form_falls_back_for_shapes_the_per_image_kernel_does_not_take()
     r64, o64 = engine.decode_nms_batch_exact([t64], 4, 0.5, 3, 0.45, 1)
     a, b = chain([t64], 4, 0.5, 3, 0.45, 1)
     assert np.array_equal(r64.cpu().numpy(), a) and np.array_equal(o64.cpu().numpy(), b)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_static_step_replays_without_memsets(graph):
+    """TrainEvalStep (yb_loss_decode_nms_fused_clean): workspaces zeroed once, the kernels leave them
+    zeroed; every replay - also after the inputs were refilled in place and after an overflowing
+    step - gives the bits of the eager two-launch step."""
+    from tf2_yolo_b200.yolov4.losses import wrap_yolo_loss
+    B, C = 3, 80
+    cfgs = [synth.make_config("v4-608", batch=5, seed=s) for s in (5, 6)]
+    fns = [wrap_yolo_loss((S, S), B, C, anchors=cfgs[0]["anchors"][si * B:(si + 1) * B], loss_weight=[1, 5, 1])
+           for si, S in enumerate(cfgs[0]["grids"])]
+    params = [f.params for f in fns]
+    yts = [torch.from_numpy(a).cuda() for a in cfgs[0]["y_trues"]]
+    yps = [torch.from_numpy(a).cuda() for a in cfgs[0]["y_preds"]]
+    step = engine.TrainEvalStep(params, yts, yps, 0.5, 0.45, 2, rows_per_img_cap=1024, graph=graph)
+    assert (step.graph is not None) == graph
+    for rep in range(5):
+        cfg = cfgs[rep & 1]
+        for dst, src in zip(yts + yps, cfg["y_trues"] + cfg["y_preds"]):
+            dst.copy_(torch.from_numpy(src))
+        loss, d, _, r = step.run()
+        loss0, d0, _, r0 = engine.loss_decode_nms_fused(params, yts, yps, 0.5, 0.45, 2, rows_per_img_cap=1024)
+        n = int(r0["out_offsets"][-1].item())
+        assert n > 0 and int(r["n_overflow"].item()) == 0
+        assert torch.equal(loss, loss0) and all(torch.equal(a, b) for a, b in zip(d, d0))
+        assert torch.equal(r["out_offsets"], r0["out_offsets"]) and torch.equal(r["out_rows"][:n], r0["out_rows"][:n])
+        torch.cuda.synchronize()
+        # only the row buckets (never read before they are rewritten) may hold anything
+        assert int(step.lws.count_nonzero().item()) == 0
+        head = step._aligned(step.fws) - step.fws.data_ptr()
+        assert int(step.fws[head:head + 768].count_nonzero().item()) == 0
+    # a step whose images overflow the row capacity also leaves the control block clean
+    small = engine.TrainEvalStep(params, yts, yps, 0.5, 0.45, 2, rows_per_img_cap=32, graph=graph)
+    for _ in range(2):
+        _, _, _, r = small.run()
+        assert int(r["n_overflow"].item()) == 5 and int(r["out_offsets"][-1].item()) == 0
+    torch.cuda.synchronize()
+    head = small._aligned(small.fws) - small.fws.data_ptr()
+    assert int(small.fws[head:head + 768].count_nonzero().item()) == 0

@@ -97,6 +97,8 @@ SIGNATURES = {
                                        _vp, _vp, _sz, _vp]),
     "yb_loss_decode_nms_fused": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _dbl, _dbl, _i32, _i32, _vp, _i64,
                                            _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+    "yb_loss_decode_nms_fused_clean": (C.c_int, [C.POINTER(LossScale), _i32, _vp, _vp, _dbl, _dbl, _i32, _i32, _vp,
+                                                 _i64, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "yb_nms_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "yb_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "yb_soft_nms": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _dbl, _dbl, _dbl, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

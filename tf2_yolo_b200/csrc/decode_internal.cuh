@@ -84,7 +84,7 @@ int decode_finish(const DecodeLaunch& L, const DecodeWs& ws, bool is_f64, double
 // memset) and returns the per-image buckets the counting pass must fill; fused_finish launches
 // the per-image kernel.
 int fused_prepare(const void* const* preds, int64_t n_img, const yb_decode_params* p, int row_cap, void* workspace,
-                  size_t workspace_bytes, DecodeLaunch& D, HotBuckets& K, cudaStream_t stream);
+                  size_t workspace_bytes, DecodeLaunch& D, HotBuckets& K, cudaStream_t stream, bool clear = true);
 int fused_finish(const DecodeLaunch& D, int64_t n_img, int row_cap, void* workspace, double nms_threshold,
                  int iou_mode, double* out_rows, int64_t out_capacity, int64_t* out_offsets,
                  unsigned int* n_overflow, cudaStream_t stream);

@@ -41,7 +41,7 @@ struct FusedLaunch {
     long long* out_offsets;    // [n_img + 1]
     unsigned int* n_overflow;  // [1] or null
     unsigned long long* status;   // [n_img] look-back words, zero on entry
-    unsigned int* ticket;         // [1], zero on entry
+    unsigned int* ticket;         // [2]: ticket counter, finished-CTA counter; zero on entry, zero on exit
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -74,6 +74,18 @@ struct FusedSmem {
     }
 };
 
+#ifdef YB_FUSED_PROF
+__device__ unsigned long long g_fused_prof[4096 * 16];
+__device__ __forceinline__ unsigned long long prof_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    return t;
+}
+#define PROF(k) do { if (threadIdx.x == 0 && blockIdx.x < 4096) g_fused_prof[blockIdx.x * 16 + (k)] = prof_now(); } while (0)
+#else
+#define PROF(k) do { } while (0)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(kFusedThreads)
 decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
@@ -97,6 +109,7 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
+    PROF(0);
     if (tid == 0) {
         s_img = atomicAdd(F.ticket, 1u);   // images in ticket order: predecessors are running
         s_next_class = 0u;
@@ -107,6 +120,7 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     }
     __syncthreads();
     const long long img = s_img;
+    PROF(1);
 
     // ---- 1. the image's rows, as the counting pass filed them (any order): class histogram ----------
     const unsigned n_filed = F.K.n[img];
@@ -115,12 +129,23 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     const FusedRow* bucket = F.K.row + img * F.K.cap;
     for (int i = tid; i < n_rows; i += kFusedThreads) atomicAdd(&s_ccount[bucket[i].key & 255u], 1u);
     __syncthreads();
+    PROF(2);
     for (int c = tid; c <= C; c += kFusedThreads) {
         unsigned sum = 0;
         for (int j = 0; j < c; ++j) sum += s_ccount[j];
         s_cstart[c] = sum;
     }
     __syncthreads();
+    PROF(3);
+#ifdef YB_FUSED_PROF
+    if (tid == 0 && blockIdx.x < 4096) {
+        unsigned mx = 0;
+        for (int c = 0; c < C; ++c) mx = max(mx, s_ccount[c]);
+        g_fused_prof[blockIdx.x * 16 + 12] = n_rows;
+        g_fused_prof[blockIdx.x * 16 + 13] = mx;
+        g_fused_prof[blockIdx.x * 16 + 14] = img;
+    }
+#endif
     // ---- 2. class-major order.  Only the survivors leave the kernel, class-major and in the
     //         reference's row order inside a class (utils/tools.py:730-732), so the rows are sorted
     //         by (class, cell, box) directly: a row takes any free slot of its class segment, then
@@ -132,6 +157,7 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         s_key[slot] = key;
     }
     __syncthreads();
+    PROF(4);
     for (int i = tid; i < n_rows; i += kFusedThreads) {
         const FusedRow fr = bucket[i];
         const unsigned key = fr.key, cls = key & 255u;
@@ -152,6 +178,7 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         s_conf[rank] = __dmul_rn((double)fr.c, (double)fr.p);   // conf = c * p in float64 (utils/tools.py:716)
     }
     __syncthreads();
+    PROF(5);
     for (int c = tid; c < C; c += kFusedThreads) s_ckept[c] = 0u;
     // ---- 3. visit rank of every row inside its class (np.argsort(conf)[::-1], utils/tools.py:717) ---
     for (int r = tid; r < n_rows; r += kFusedThreads) {
@@ -164,6 +191,7 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         s_vrank[r] = (unsigned short)vis;
     }
     __syncthreads();
+    PROF(6);
     const bool pos_thr = F.nms_thr > 0.0;
     const double nms_thr = F.nms_thr;
     // ---- 4. one warp per class: greedy sweep in visit order.  Classes are handed out by a counter
@@ -205,7 +233,9 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         }
         if (lane == 0) s_ckept[c] = (unsigned)kept_before;
     }
+    PROF(7);      // thread 0's own classes done
     __syncthreads();
+    PROF(8);
     // ---- 5. survivors of the image: class-major positions; the image's offset by look-back ---------
     if (tid == 0) {
         unsigned sum = 0;
@@ -217,6 +247,7 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         s_kept = sum;
     }
     __syncthreads();
+    PROF(9);
     if (warp == 0) {
         const unsigned long long agg = (unsigned long long)s_kept | ((unsigned long long)(overflow ? 1 : 0) << kStOvfShift);
         unsigned long long excl = 0;
@@ -254,18 +285,38 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
             }
         }
     }
+    PROF(10);
     // source row of every output position, then a coalesced copy
     for (int r = tid; r < n_rows; r += kFusedThreads)
         if (s_rank[r] != 0xffffu) s_outsrc[s_ckept[s_cls[r]] + s_rank[r]] = (unsigned short)r;
     __syncthreads();
-    if (F.out_rows == nullptr) return;
-    const long long base = s_base;
-    const int n_out = (int)s_kept;
-    for (int f = tid; f < n_out * 7; f += kFusedThreads) {
-        const int q = f / 7, k = f - q * 7;
-        if (base + q < F.out_cap) F.out_rows[(base + q) * 7 + k] = s_rows[(size_t)s_outsrc[q] * 7 + k];
+    if (F.out_rows != nullptr) {
+        const long long base = s_base;
+        const int n_out = (int)s_kept;
+        for (int f = tid; f < n_out * 7; f += kFusedThreads) {
+            const int q = f / 7, k = f - q * 7;
+            if (base + q < F.out_cap) F.out_rows[(base + q) * 7 + k] = s_rows[(size_t)s_outsrc[q] * 7 + k];
+        }
+    }
+    PROF(11);
+    // leave the control block as it was found: this image's bucket counter now, the look-back words
+    // and the counters by whichever CTA finishes last (every look-back is over by then)
+    if (tid == 0) {
+        F.K.n[img] = 0u;
+        __threadfence();
+        if (atomicAdd(F.ticket + 1, 1u) == (unsigned)L.n_img - 1u) {
+            for (long long i = 0; i < L.n_img; ++i) F.status[i] = 0ull;
+            F.ticket[0] = 0u;
+            F.ticket[1] = 0u;
+        }
     }
 }
+
+#ifdef YB_FUSED_PROF
+extern "C" int yb_debug_fused_prof(unsigned long long* host, int n_words) {
+    return (int)cudaMemcpyFromSymbol(host, g_fused_prof, sizeof(unsigned long long) * (size_t)n_words);
+}
+#endif
 
 // ---- host side -----------------------------------------------------------------------------------
 struct FusedWs {
@@ -340,7 +391,7 @@ static int fused_launch(const DecodeLaunch& D, const FusedWs& W, int row_cap, do
 
 // Shared with loss.cu (yb_loss_decode_nms_fused): workspace carve-up + memset, then the launch.
 int fused_prepare(const void* const* preds, int64_t n_img, const yb_decode_params* p, int row_cap, void* workspace,
-                  size_t workspace_bytes, DecodeLaunch& D, HotBuckets& K, cudaStream_t stream) {
+                  size_t workspace_bytes, DecodeLaunch& D, HotBuckets& K, cudaStream_t stream, bool clear) {
     int rc = fused_check(p, n_img, row_cap);
     if (rc != YB_OK) return rc;
     rc = decode_fill(preds, n_img, p, D);
@@ -352,7 +403,7 @@ int fused_prepare(const void* const* preds, int64_t n_img, const yb_decode_param
         if (D.n_img * D.cells[s] > 0xffffffffll || D.B[s] > 32) return YB_E_SHAPE;
     FusedWs W;
     fused_layout(n_img, row_cap, &W, reinterpret_cast<char*>(workspace));
-    YB_CUDA_TRY(cudaMemsetAsync(W.zero, 0, W.zero_bytes, stream));
+    if (clear) YB_CUDA_TRY(cudaMemsetAsync(W.zero, 0, W.zero_bytes, stream));
     K = W.K;
     return YB_OK;
 }

@@ -933,7 +933,8 @@ struct FusedDecode {   // optional: count decode hits inside the loss pass
 
 static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out, double* terms_out,
                      double* metrics_out, double recall_iou_threshold, void* workspace,
-                     size_t workspace_bytes, yb_stream_t stream_, const FusedDecode* fd = nullptr) {
+                     size_t workspace_bytes, yb_stream_t stream_, const FusedDecode* fd = nullptr,
+                     bool workspace_is_clean = false) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (scales == nullptr || loss_out == nullptr || workspace == nullptr) return YB_E_NULL;
     if (n_scales < 1 || n_scales > YB_MAX_SCALES) return YB_E_SHAPE;
@@ -1025,8 +1026,10 @@ static int loss_impl(const yb_loss_scale* scales, int n_scales, float* loss_out,
     const size_t smem = (size_t)n_stages * stage_bytes + acc_bytes(ncw) + bar_bytes;
     const int threads = (ncw + 1) * 32;
     int grid = min(max(total_tiles, 1), kNumSMs * ctas_per_sm);
-    // sums + control words start at zero (the kernel also leaves them zeroed)
-    YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, loss_gacc_bytes(n_scales) + kCtrlWords * sizeof(unsigned int), stream));
+    // sums + control words start at zero; the kernel leaves them zeroed, so a caller that zeroed the
+    // workspace once and only ever hands it to this kernel may skip the per-call memset
+    if (!workspace_is_clean)
+        YB_CUDA_TRY(cudaMemsetAsync(workspace, 0, loss_gacc_bytes(n_scales) + kCtrlWords * sizeof(unsigned int), stream));
     switch (version) {
         case 1: return launch_loss<1>(L, grid, threads, smem, stream);
         case 2: return launch_loss<2>(L, grid, threads, smem, stream);
@@ -1103,12 +1106,11 @@ extern "C" int yb_loss_decode_fused(const yb_loss_scale* scales, int n_scales, f
 
 // The whole train-and-evaluate step in TWO launches: the loss kernel (forward + gradient + the
 // decode counting pass into per-image buckets) and the one-CTA-per-image decode + NMS kernel.
-extern "C" int yb_loss_decode_nms_fused(const yb_loss_scale* scales, int n_scales, float* loss_out,
-                                        double* terms_out, double decode_threshold, double nms_threshold,
-                                        int iou_mode, int rows_per_img_cap, double* out_rows,
-                                        int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
-                                        void* loss_workspace, size_t loss_workspace_bytes, void* fused_workspace,
-                                        size_t fused_workspace_bytes, yb_stream_t stream_) {
+static int step_impl(const yb_loss_scale* scales, int n_scales, float* loss_out, double* terms_out,
+                     double decode_threshold, double nms_threshold, int iou_mode, int rows_per_img_cap,
+                     double* out_rows, int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                     void* loss_workspace, size_t loss_workspace_bytes, void* fused_workspace,
+                     size_t fused_workspace_bytes, yb_stream_t stream_, bool clean) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (scales == nullptr) return YB_E_NULL;
     const bool count_only = out_offsets == nullptr;   // the per-image kernel comes later: yb_decode_nms_finish
@@ -1149,14 +1151,41 @@ extern "C" int yb_loss_decode_nms_fused(const yb_loss_scale* scales, int n_scale
     DecodeWs ws;
     memset(&ws, 0, sizeof(ws));
     int rc = fused_prepare(preds, n_img, &dp, rows_per_img_cap, fused_workspace, fused_workspace_bytes, DL, ws.buckets,
-                           stream);
+                           stream, !clean);
     if (rc != YB_OK) return rc;
     FusedDecode fd{&DL, &ws};   // counts / flat list stay null: only the per-image buckets are filled
     rc = loss_impl(scales, n_scales, loss_out, terms_out, nullptr, 0.5, loss_workspace, loss_workspace_bytes, stream_,
-                   &fd);
+                   &fd, clean);
     if (rc != YB_OK || count_only) return rc;
     return fused_finish(DL, n_img, rows_per_img_cap, fused_workspace, nms_threshold, iou_mode, out_rows, out_capacity,
                         out_offsets, n_overflow, stream);
+}
+
+extern "C" int yb_loss_decode_nms_fused(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                                        double* terms_out, double decode_threshold, double nms_threshold,
+                                        int iou_mode, int rows_per_img_cap, double* out_rows,
+                                        int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                                        void* loss_workspace, size_t loss_workspace_bytes, void* fused_workspace,
+                                        size_t fused_workspace_bytes, yb_stream_t stream) {
+    return step_impl(scales, n_scales, loss_out, terms_out, decode_threshold, nms_threshold, iou_mode, rows_per_img_cap,
+                     out_rows, out_capacity, out_offsets, n_overflow, loss_workspace, loss_workspace_bytes,
+                     fused_workspace, fused_workspace_bytes, stream, false);
+}
+
+// The same for workspaces the caller zeroed ONCE and has handed to nothing but this entry point
+// since: both kernels leave their control blocks zeroed, so the step is two launches and nothing else
+// (no memsets) - what a captured CUDA graph of a training loop replays.
+extern "C" int yb_loss_decode_nms_fused_clean(const yb_loss_scale* scales, int n_scales, float* loss_out,
+                                              double* terms_out, double decode_threshold, double nms_threshold,
+                                              int iou_mode, int rows_per_img_cap, double* out_rows,
+                                              int64_t out_capacity, int64_t* out_offsets, unsigned int* n_overflow,
+                                              void* loss_workspace, size_t loss_workspace_bytes,
+                                              void* fused_workspace, size_t fused_workspace_bytes,
+                                              yb_stream_t stream) {
+    if (out_offsets == nullptr) return YB_E_NULL;   // the split form would leave the buckets filled
+    return step_impl(scales, n_scales, loss_out, terms_out, decode_threshold, nms_threshold, iou_mode, rows_per_img_cap,
+                     out_rows, out_capacity, out_offsets, n_overflow, loss_workspace, loss_workspace_bytes,
+                     fused_workspace, fused_workspace_bytes, stream, true);
 }
 
 static int loss_single(int version, const float* y_true, const float* y_pred, int64_t n_cells,

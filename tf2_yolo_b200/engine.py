@@ -429,6 +429,104 @@ def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold
     return loss, outs, terms, dict(out_rows=out_rows, out_offsets=out_offsets, n_overflow=n_overflow)
 
 
+class TrainEvalStep:
+    """The two-launch train-and-evaluate step over STATIC buffers, replayed from a CUDA graph.
+
+    What a training loop with fixed shapes does with loss_decode_nms_fused: the tensors handed in
+    are the buffers every step reads (refill them in place), the workspaces belong to this object
+    and are zeroed once - both kernels leave them zeroed (yb_loss_decode_nms_fused_clean) - so a
+    step is exactly two kernel nodes, plus whatever `tail` enqueues (e.g. the all-reduce of the
+    loss scalars), captured once and replayed by run().  graph=False launches the same two kernels
+    eagerly."""
+
+    def __init__(self, params, y_trues, y_preds, threshold=0.5, nms_threshold=0.45, iou_mode=1,
+                 rows_per_img_cap=1024, global_batch=None, dpreds=None, want_terms=False, out=None,
+                 out_capacity=None, tail=None, graph=True):
+        n = len(params)
+        require_cuda(*y_trues, *y_preds)
+        self.dev = dev = y_preds[0].device
+        self.n = n
+        self.n_img = n_img = y_preds[0].shape[0]
+        self._keep = (list(y_trues), list(y_preds))
+        self.scales = (N.LossScale * n)()
+        self.dpreds = []
+        for i, (p, yt, yp) in enumerate(zip(params, y_trues, y_preds)):
+            if yt.dtype != torch.float32 or yp.dtype != torch.float32:
+                raise N.YoloB200Error("loss tensors must be float32")
+            cells_per_img = p.grid_h * p.grid_w
+            pcf = (5 * p.bbox_num + p.class_num) if p.version == 1 else p.bbox_num * (5 + p.class_num)
+            if yp.numel() != n_img * cells_per_img * pcf or yt.numel() != n_img * cells_per_img * (5 + p.class_num):
+                raise ValueError("every scale must hold the same images with matching grid / info sizes")
+            q = N.LossParams.from_buffer_copy(p)
+            q.inv_batch = 1.0 / float(global_batch if global_batch is not None else max(n_img, 1))
+            d = dpreds[i] if dpreds is not None else torch.empty_like(yp)
+            self.dpreds.append(d)
+            self.scales[i].y_true, self.scales[i].y_pred, self.scales[i].dpred = yt.data_ptr(), yp.data_ptr(), d.data_ptr()
+            self.scales[i].n_cells = n_img * cells_per_img
+            self.scales[i].p = q
+        dparams, _ = make_decode_params(y_preds, params[0].class_num, threshold, params[0].version)
+        self.args = (float(threshold), float(nms_threshold), int(iou_mode), int(rows_per_img_cap))
+        if out_capacity is None:
+            out_capacity = rows_per_img_cap * max(n_img, 1)
+        with torch.cuda.device(dev):
+            self.out_rows, self.out_offsets, self.n_overflow = _fused_outputs(dev, n_img, out_capacity, out)
+            self.loss = torch.empty(n, dtype=torch.float32, device=dev)
+            self.terms = torch.empty((n, N.YB_LOSS_TERMS), dtype=_F64, device=dev) if want_terms else None
+            self.lws_bytes = N.lib.yb_loss_workspace_bytes(n)
+            self.fws_bytes = N.lib.yb_decode_nms_workspace_bytes(C.byref(dparams), n_img, int(rows_per_img_cap))
+            if self.fws_bytes == 0:
+                raise ValueError("TrainEvalStep: class_num <= 256, 32 <= rows_per_img_cap <= "
+                                 f"{N.YB_FUSED_MAX_ROWS}")
+            # private, zeroed once: nothing but the clean entry point ever touches them
+            self.lws = torch.zeros(self.lws_bytes + 256, dtype=torch.uint8, device=dev)
+            self.fws = torch.zeros(self.fws_bytes + 256, dtype=torch.uint8, device=dev)
+        self.tail = tail
+        self.graph = None
+        if graph:
+            self._capture()
+
+    def _aligned(self, t):
+        return (t.data_ptr() + 255) // 256 * 256
+
+    def _launch(self):
+        thr, nms_thr, mode, cap = self.args
+        rc = N.lib.yb_loss_decode_nms_fused_clean(self.scales, self.n, _ptr(self.loss), _ptr(self.terms), thr,
+                                                  nms_thr, mode, cap, _ptr(self.out_rows), self.out_rows.shape[0],
+                                                  _ptr(self.out_offsets), _ptr(self.n_overflow),
+                                                  self._aligned(self.lws), self.lws_bytes,
+                                                  self._aligned(self.fws), self.fws_bytes, _stream())
+        if rc != 0:     # the kernels may not have run to their self-cleaning end
+            self.lws.zero_()
+            self.fws.zero_()
+        N.check(rc, "yb_loss_decode_nms_fused_clean")
+        if self.tail is not None:
+            self.tail(self)
+
+    def _capture(self):
+        with torch.cuda.device(self.dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):      # warm-up outside the capture (lazy module load, smem opt-in)
+                self._launch()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._launch()
+            self.graph = g
+
+    def run(self):
+        """One step on the current stream.  Returns (loss [n], dpreds, terms, dict(out_rows, ...))
+        - the same static tensors every time."""
+        with torch.cuda.device(self.dev):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._launch()
+        return self.loss, self.dpreds, self.terms, dict(out_rows=self.out_rows, out_offsets=self.out_offsets,
+                                                        n_overflow=self.n_overflow)
+
+
 def pairwise_iou(a, b, mode=1):
     """(na, >=4) x (nb, >=4) f64 CUDA -> (na, nb) f64; a plays xywh_true."""
     require_cuda(a, b)

@@ -27,7 +27,7 @@ rc = f(buf.ctypes.data, buf.size)
 assert rc == 0, rc
 p = buf.reshape(128, 16).astype(np.int64)
 t0 = p[:, 0].min()
-names = ["entry", "ticket", "hist", "cstart", "slots", "rows", "visrank", "own_greedy", "greedy_all", "prefix", "lookback", "outcopy"]
+names = ["entry", "ticket", "hist", "cstart", "slots", "rows", "pairs", "order+scan+rank", "barrier", "prefix", "lookback", "outcopy"]
 rel = p[:, :12] - t0
 print("kernel span ns:", rel[:, 11].max())
 print("start spread ns: max", rel[:, 0].max())

@@ -87,6 +87,34 @@ def test_ties_duplicates_and_big_segments():
         assert np.array_equal(rows[offs[0]:offs[1]], o)
 
 
+def test_class_sizes_around_the_mask_width():
+    """Classes of exactly 1, 32, 33, 64, 65, 128 (pair masks) and 129 rows (warp sweep) in one image,
+    with heavy overlap and ties."""
+    rng = np.random.default_rng(11)
+    S, C = 24, 7
+    sizes = [1, 32, 33, 64, 65, 128, 129]
+    p = np.zeros((2, S * S, 5 + C), dtype=np.float32)
+    for img in range(2):
+        cells = rng.permutation(S * S)[:sum(sizes)]
+        at = 0
+        for c, n in enumerate(sizes):
+            sel = cells[at:at + n]
+            at += n
+            p[img, sel, 0:2] = rng.uniform(0.0, 1.0, (n, 2))
+            p[img, sel, 2:4] = rng.uniform(0.15, 0.5, (n, 2))
+            p[img, sel, 4] = np.round(rng.uniform(0.6, 1.0, n), 1 if img else 3)    # image 1: many equal confidences
+            p[img, sel, 5 + c] = 0.9
+    t = torch.from_numpy(p.reshape(2, S, S, 5 + C)).cuda()
+    for mode in (1, 2):
+        for nms_thr in (0.1, 0.45):
+            ref_rows, ref_offs = chain([t], C, 0.5, 3, nms_thr, mode)
+            rows, offs, ovf = fused([t], C, 0.5, 3, nms_thr, mode, cap=512)
+            assert ovf == 0 and np.array_equal(offs, ref_offs) and np.array_equal(rows, ref_rows)
+            assert 0 < offs[-1] < 2 * sum(sizes)
+    o = ot.nms(ot.decode(p[1].reshape(S, S, -1), class_num=C, threshold=0.5, version=3).reshape(-1, 7), C, 0.45, 2)
+    assert np.array_equal(rows[offs[1]:offs[2]], o)
+
+
 def test_overflow_is_reported_and_the_checked_form_falls_back():
     cfg = synth.make_config("v4-608", batch=4, seed=21)
     preds = [torch.from_numpy(a).cuda() for a in cfg["y_preds"]]

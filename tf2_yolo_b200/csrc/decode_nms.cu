@@ -25,7 +25,7 @@
 
 namespace yb {
 
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 1024;
 constexpr int kFusedWarps = kFusedThreads / 32;
 
 constexpr unsigned long long kStFlagAgg = 1ull << 62, kStFlagIncl = 2ull << 62, kStFlagMask = 3ull << 62;
@@ -53,9 +53,13 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Classes of up to kMaskMembers rows take the mask path of the greedy sweep (every pair tested in
+// parallel, then one short scan per class); larger classes keep one warp each.
+constexpr int kMaskWords = 4, kMaskMembers = 32 * kMaskWords;
+
 // shared-memory carve-up for R = row_cap rows and C classes (host and device agree through this)
 struct FusedSmem {
-    size_t rows, conf, key, cls, vis, vrank, rank, outsrc, ccount, cstart, ckept, total;
+    size_t rows, conf, key, cls, vis, vrank, rank, outsrc, mask, ccount, cstart, ckept, cpair, cdead, total;
     __host__ __device__ FusedSmem(int R, int C) {
         size_t o = 0;
         auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
@@ -64,12 +68,15 @@ struct FusedSmem {
         key = take(4 * (size_t)R);
         cls = take(2 * (size_t)R);
         vis = take(2 * (size_t)R);
-        vrank = take(2 * (size_t)R);
+        vrank = take(4 * (size_t)R);
         rank = take(2 * (size_t)R);
         outsrc = take(2 * (size_t)R);
+        mask = take(4 * (size_t)kMaskWords * R);
         ccount = take(4 * (size_t)C);
         cstart = take(4 * ((size_t)C + 1));
         ckept = take(4 * ((size_t)C + 1));
+        cpair = take(4 * ((size_t)C + 1));
+        cdead = take(4 * (size_t)kMaskWords * C);
         total = o;
     }
 };
@@ -86,6 +93,11 @@ __device__ __forceinline__ unsigned long long prof_now() {
 #define PROF(k) do { } while (0)
 #endif
 
+// pairs of a class that takes the mask path
+__device__ __forceinline__ unsigned mask_pairs(unsigned n) {
+    return (n >= 2u && n <= (unsigned)kMaskMembers) ? n * (n - 1u) / 2u : 0u;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kFusedThreads)
 decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
@@ -98,13 +110,16 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     unsigned int* s_key = reinterpret_cast<unsigned int*>(fsm + lay.key);
     unsigned short* s_cls = reinterpret_cast<unsigned short*>(fsm + lay.cls);
     unsigned short* s_vis = reinterpret_cast<unsigned short*>(fsm + lay.vis);
-    unsigned short* s_vrank = reinterpret_cast<unsigned short*>(fsm + lay.vrank);
+    unsigned int* s_vrank = reinterpret_cast<unsigned int*>(fsm + lay.vrank);
+    unsigned int* s_mask = reinterpret_cast<unsigned int*>(fsm + lay.mask);
+    unsigned int* s_cdead = reinterpret_cast<unsigned int*>(fsm + lay.cdead);
+    unsigned int* s_cpair = reinterpret_cast<unsigned int*>(fsm + lay.cpair);
     unsigned short* s_rank = reinterpret_cast<unsigned short*>(fsm + lay.rank);
     unsigned short* s_outsrc = reinterpret_cast<unsigned short*>(fsm + lay.outsrc);
     unsigned int* s_ccount = reinterpret_cast<unsigned int*>(fsm + lay.ccount);
     unsigned int* s_cstart = reinterpret_cast<unsigned int*>(fsm + lay.cstart);
     unsigned int* s_ckept = reinterpret_cast<unsigned int*>(fsm + lay.ckept);
-    __shared__ unsigned int s_img, s_kept, s_next_class;
+    __shared__ unsigned int s_img, s_kept;
     __shared__ long long s_base;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -112,7 +127,6 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     PROF(0);
     if (tid == 0) {
         s_img = atomicAdd(F.ticket, 1u);   // images in ticket order: predecessors are running
-        s_next_class = 0u;
     }
     for (int c = tid; c < C; c += kFusedThreads) {
         s_ccount[c] = 0u;
@@ -130,10 +144,32 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
     for (int i = tid; i < n_rows; i += kFusedThreads) atomicAdd(&s_ccount[bucket[i].key & 255u], 1u);
     __syncthreads();
     PROF(2);
-    for (int c = tid; c <= C; c += kFusedThreads) {
-        unsigned sum = 0;
-        for (int j = 0; j < c; ++j) sum += s_ccount[j];
-        s_cstart[c] = sum;
+    // exclusive prefixes over the classes (C <= 256): warp 0, eight classes per lane
+    if (warp == 0) {
+        unsigned cnt[8], sum = 0, prs = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane * 8 + k;
+            const unsigned n = c < C ? s_ccount[c] : 0u;
+            cnt[k] = n;
+            sum += n;
+            prs += mask_pairs(n);
+        }
+        unsigned xs = sum, xp = prs;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ts = __shfl_up_sync(0xffffffffu, xs, o), tp = __shfl_up_sync(0xffffffffu, xp, o);
+            if (lane >= o) { xs += ts; xp += tp; }
+        }
+        unsigned es = xs - sum, ep = xp - prs;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane * 8 + k;
+            if (c <= C) { s_cstart[c] = es; s_cpair[c] = ep; }
+            es += cnt[k];
+            ep += mask_pairs(cnt[k]);
+        }
+        if (lane == 31 && C == 256) { s_cstart[256] = es; s_cpair[256] = ep; }
     }
     __syncthreads();
     PROF(3);
@@ -175,34 +211,99 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         o[5] = (double)cls;
         o[6] = (double)fr.p;
         s_cls[rank] = (unsigned short)cls;
+        s_vrank[rank] = 0u;
+        *reinterpret_cast<uint4*>(s_mask + (size_t)rank * kMaskWords) = make_uint4(0u, 0u, 0u, 0u);
         s_conf[rank] = __dmul_rn((double)fr.c, (double)fr.p);   // conf = c * p in float64 (utils/tools.py:716)
     }
     __syncthreads();
     PROF(5);
     for (int c = tid; c < C; c += kFusedThreads) s_ckept[c] = 0u;
-    // ---- 3. visit rank of every row inside its class (np.argsort(conf)[::-1], utils/tools.py:717) ---
+    const bool pos_thr = F.nms_thr > 0.0;
+    const double nms_thr = F.nms_thr;
+    // ---- 3. every pair of a class, in parallel, one pair per thread and turn.  Member i of a class
+    //         is visited at rank #{j : j before i} (np.argsort(conf)[::-1], utils/tools.py:717); if
+    //         it is visited alive it removes the later members its IoU test hits (:722-726) - that
+    //         set is a mask over the class, independent of the sweep.  Pair q of the image -> class
+    //         (search in the prefix of n(n-1)/2) -> members i < j (row of the triangle) ---------------
+    const int n_pairs = (int)s_cpair[C];
+    {
+        // a thread takes a contiguous run of pairs: one search, then (i, j) -> (i, j + 1) -> next row
+        // of the triangle -> next class; the box of member i is built once per row
+        const int len = (n_pairs + kFusedThreads - 1) / kFusedThreads;
+        int q = tid * len;
+        const int q_end = min(n_pairs, q + len);
+        if (q < q_end) {
+            int lo = 0, hi = C;                               // largest c with s_cpair[c] <= q
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((int)s_cpair[mid] <= q) lo = mid; else hi = mid;
+            }
+            int c = lo, n = (int)s_ccount[c], start = (int)s_cstart[c];
+            const int k = q - (int)s_cpair[c];
+            const int m = 2 * n - 1;
+            int i = (int)(((float)m - sqrtf((float)(m * m - 8 * k))) * 0.5f);
+            i = max(0, min(i, n - 2));
+            while (i * (m - i) / 2 > k) --i;                  // pairs before row i: i (2n - i - 1) / 2
+            while ((i + 1) * (m - i - 1) / 2 <= k) ++i;
+            int j = i + 1 + (k - i * (m - i) / 2);
+            const double* pi = s_rows + (size_t)(start + i) * 7;
+            BoxC bi = make_box(pi[0], pi[1], pi[2], pi[3]);
+            double ci = s_conf[start + i];
+            for (;;) {
+                const int ri = start + i, rj = start + j;
+                const bool i_first = visited_before(ci, i, s_conf[rj], j);
+                atomicAdd(&s_vrank[i_first ? rj : ri], 1u);    // the later one is visited after one more
+                const double* pj = s_rows + (size_t)rj * 7;
+                const BoxC bj = make_box(pj[0], pj[1], pj[2], pj[3]);
+                // the division-free test is symmetric bit for bit (min/max, commutative sums, squares);
+                // the exact expression gets the boxes in the order of the sweep
+                const int fast = suppresses_fast<MODE>(bi, bj, nms_thr, pos_thr);
+                const int ra = i_first ? ri : rj, rb = i_first ? rj : ri;
+                if (fast > 0 || (fast < 0 && suppresses_exact<MODE>(s_rows, ra, rb, nms_thr))) {
+                    const int mb = rb - start;
+                    atomicOr(&s_mask[(size_t)ra * kMaskWords + (mb >> 5)], 1u << (mb & 31));
+                }
+                if (++q >= q_end) break;
+                if (++j >= n) {
+                    ++i;
+                    if (i >= n - 1) {                         // next class with pairs (there is one: q < n_pairs)
+                        do {
+                            ++c;
+                            n = (int)s_ccount[c];
+                        } while (n < 2 || n > kMaskMembers);
+                        start = (int)s_cstart[c];
+                        i = 0;
+                    }
+                    j = i + 1;
+                    pi = s_rows + (size_t)(start + i) * 7;
+                    bi = make_box(pi[0], pi[1], pi[2], pi[3]);
+                    ci = s_conf[start + i];
+                }
+            }
+        }
+    }
+    // rows of a class too large for a mask: only the visit rank (the warp sweep below does the rest)
     for (int r = tid; r < n_rows; r += kFusedThreads) {
         const int c = s_cls[r];
-        const int start = (int)s_cstart[c], n = (int)s_ccount[c], i = r - start;
+        const int n = (int)s_ccount[c];
+        if (n <= kMaskMembers) continue;
+        const int start = (int)s_cstart[c], i = r - start;
         const double ci = s_conf[r];
         int vis = 0;
         for (int j = 0; j < n; ++j) vis += (j != i && visited_before(s_conf[start + j], j, ci, i)) ? 1 : 0;
-        s_vis[start + vis] = (unsigned short)i;
-        s_vrank[r] = (unsigned short)vis;
+        s_vrank[r] = (unsigned)vis;
     }
     __syncthreads();
     PROF(6);
-    const bool pos_thr = F.nms_thr > 0.0;
-    const double nms_thr = F.nms_thr;
-    // ---- 4. one warp per class: greedy sweep in visit order.  Classes are handed out by a counter
-    //         (a static round-robin leaves warps idle while one works through two large classes) ----
-    for (;;) {
-        int c = 0;
-        if (lane == 0) c = (int)atomicAdd(&s_next_class, 1u);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c >= C) break;
+    for (int r = tid; r < n_rows; r += kFusedThreads) {
+        const int start = (int)s_cstart[s_cls[r]];
+        s_vis[start + (int)s_vrank[r]] = (unsigned short)(r - start);
+    }
+    __syncthreads();
+    // ---- 4a. classes too large for a mask: one warp each, greedy sweep in visit order --------------
+    for (int c = warp; c < C; c += kFusedWarps) {
         const int n = (int)s_ccount[c];
-        if (n == 0) continue;
+        if (n <= kMaskMembers) continue;
         const int start = (int)s_cstart[c];
         // lane l owns members l, l+32, ...; dead bit t of a lane = member l + 32 t
         unsigned dead = 0;
@@ -233,18 +334,73 @@ decode_nms_image_kernel(const __grid_constant__ FusedLaunch F) {
         }
         if (lane == 0) s_ckept[c] = (unsigned)kept_before;
     }
+    // ---- 4b. the other classes: one thread each walks the visit order over the masks (neighbouring
+    //          classes on different warps: a warp takes as long as its longest class) ----------------
+    {
+        const int c = lane * kFusedWarps + warp;
+        const int n = c < C ? (int)s_ccount[c] : 0;
+        if (c < C && n <= kMaskMembers) {
+            const int start = (int)s_cstart[c];
+            unsigned long long d0 = 0, d1 = 0;
+#pragma unroll 4
+            for (int v = 0; v < n; ++v) {        // no branch: the loads of the next turns do not wait for this one
+                const int iv = s_vis[start + v];
+                const uint4 m = *reinterpret_cast<const uint4*>(s_mask + (size_t)(start + iv) * kMaskWords);
+                const unsigned long long w = iv < 64 ? d0 : d1;
+                // a suppressed box suppresses nothing (:723)
+                const unsigned long long live = ((w >> (iv & 63)) & 1ull) ? 0ull : ~0ull;
+                d0 |= ((unsigned long long)m.x | ((unsigned long long)m.y << 32)) & live;
+                d1 |= ((unsigned long long)m.z | ((unsigned long long)m.w << 32)) & live;
+            }
+            uint4 d;
+            d.x = (unsigned)d0; d.y = (unsigned)(d0 >> 32); d.z = (unsigned)d1; d.w = (unsigned)(d1 >> 32);
+            *reinterpret_cast<uint4*>(s_cdead + (size_t)c * kMaskWords) = d;
+            s_ckept[c] = (unsigned)(n - __popcll(d0) - __popcll(d1));
+        }
+    }
+    __syncthreads();
+    // survivors of the mask classes: position inside the class, original order
+    for (int r = tid; r < n_rows; r += kFusedThreads) {
+        const int c = s_cls[r];
+        if ((int)s_ccount[c] > kMaskMembers) continue;
+        const int i = r - (int)s_cstart[c];
+        const unsigned* d = s_cdead + (size_t)c * kMaskWords;
+        const int wi = i >> 5;
+        const unsigned dw = d[wi];
+        if ((dw >> (i & 31)) & 1u) {
+            s_rank[r] = 0xffffu;
+        } else {
+            int dead_before = __popc(dw & ((1u << (i & 31)) - 1u));
+            for (int w = 0; w < wi; ++w) dead_before += __popc(d[w]);
+            s_rank[r] = (unsigned short)(i - dead_before);
+        }
+    }
     PROF(7);      // thread 0's own classes done
     __syncthreads();
     PROF(8);
     // ---- 5. survivors of the image: class-major positions; the image's offset by look-back ---------
-    if (tid == 0) {
-        unsigned sum = 0;
-        for (int c = 0; c < C; ++c) {
-            const unsigned k = s_ckept[c];
-            s_ckept[c] = sum;          // exclusive prefix of the kept counts
-            sum += k;
+    if (warp == 0) {                   // exclusive prefix of the kept counts
+        unsigned cnt[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane * 8 + k;
+            cnt[k] = c < C ? s_ckept[c] : 0u;
+            sum += cnt[k];
         }
-        s_kept = sum;
+        unsigned xs = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ts = __shfl_up_sync(0xffffffffu, xs, o);
+            if (lane >= o) xs += ts;
+        }
+        unsigned es = xs - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = lane * 8 + k;
+            if (c < C) s_ckept[c] = es;
+            es += cnt[k];
+        }
+        if (lane == 31) s_kept = xs;
     }
     __syncthreads();
     PROF(9);

@@ -280,10 +280,11 @@ def run_ours(args):
     step_no = [0]
 
     def join_collectives():      # every rank's loss scalars are global after this
-        for i in range(2):
-            if in_flight[i] is not None:
-                in_flight[i].wait()
-                in_flight[i] = None
+        for pending in (in_flight, static_pending):
+            for i in range(2):
+                if pending[i] is not None:
+                    pending[i].wait()
+                    pending[i] = None
     fused_out = dict(out_rows=torch.empty((ROWS_PER_IMG_FUSED * batch, 7), dtype=torch.float64, device=dev),
                      out_offsets=torch.empty(batch + 1, dtype=torch.int64, device=dev),
                      n_overflow=torch.zeros(1, dtype=torch.int32, device=dev))
@@ -332,16 +333,26 @@ def run_ours(args):
         return loss, offs, res
 
     # The timed step of the default mode: the same two launches over static buffers, replayed from a
-    # CUDA graph (engine.TrainEvalStep, workspaces zeroed once - no memsets); for N > 1 the graph
-    # also holds the all-reduce of the three loss scalars.  --no-graph times the eager calls.
-    static_step = None
+    # CUDA graph (engine.TrainEvalStep, workspaces zeroed once - no memsets).  For N > 1 two such
+    # graphs alternate, each with its own loss scalars: their all-reduce (the only collective) is
+    # issued asynchronously after the replay and joined when that graph comes round again.
+    # --no-graph times the eager calls.
+    static_steps = None
     if mode == "fused" and not args.no_graph:
-        def allreduce_loss(st):
-            if world > 1:
-                dist.all_reduce(st.loss)
-        static_step = engine.TrainEvalStep(params, dev_t, dev_p, CONF_THR, NMS_THR, NMS_MODE,
-                                           rows_per_img_cap=ROWS_PER_IMG_FUSED, global_batch=global_batch,
-                                           dpreds=dpreds, tail=allreduce_loss, graph=True)
+        static_steps = [engine.TrainEvalStep(params, dev_t, dev_p, CONF_THR, NMS_THR, NMS_MODE,
+                                             rows_per_img_cap=ROWS_PER_IMG_FUSED, global_batch=global_batch,
+                                             dpreds=dpreds, graph=True) for _ in range(1 if world == 1 else 2)]
+    static_pending = [None, None]
+
+    def static_step(k):
+        i = k % len(static_steps)
+        if static_pending[i] is not None:
+            static_pending[i].wait()
+            static_pending[i] = None
+        res = static_steps[i].run()
+        if world > 1:
+            static_pending[i] = dist.all_reduce(static_steps[i].loss, async_op=True)
+        return res
 
     def barrier():
         join_collectives()
@@ -392,20 +403,20 @@ def run_ours(args):
     while len(round_ms) < n_rounds:
         barrier()
         ev0.record()
-        if static_step is not None:
-            for _ in range(args.steps):
-                g_out = static_step.run()
+        if static_steps is not None:
+            for k in range(args.steps):
+                g_out = static_step(k)
             out = (g_out[0], None, g_out[3])
         else:
             for _ in range(args.steps):
                 out = step(dev_t, dev_p, record=True)
-            join_collectives()          # the round ends when every step's collective has completed
+        join_collectives()              # the round ends when every step's collective has completed
         ev1.record()
         barrier()
         round_ms.append(agree(ev0.elapsed_time(ev1), dist.ReduceOp.MAX if world > 1 else None))
         if len(round_ms) == 1:
             n_rounds = int(min(200, max(1, np.ceil(MIN_TIMED_S * 1e3 / max(round_ms[0], 1e-3)))))
-        if static_step is not None and len(round_ms) % 4 == 1:
+        if static_steps is not None and len(round_ms) % 4 == 1:
             # the loss kernel alone cannot be bracketed inside a graph: between the timed rounds the
             # same step runs as two eager launches with an event between them (not counted in ms)
             for _ in range(args.steps):
@@ -416,7 +427,7 @@ def run_ours(args):
     ms = float(np.median(round_ms)) / args.steps
     loss_ms = float(np.median([a.elapsed_time(b) for a, b in loss_ev]))
     loss_vals = out[0].cpu().numpy().tolist()
-    if static_step is not None:   # the replayed step returns what the eager step returned
+    if static_steps is not None:   # the replayed step returns what the eager step returned
         barrier()
         if not torch.equal(out[0], eager_out[0]):
             raise SystemExit("graph replay: loss differs from the eager step's")
@@ -480,7 +491,7 @@ def run_ours(args):
                                     "image; roofline counts only the loss's algorithmic bytes"
                                     % ("_clean, replayed from a CUDA graph by engine.TrainEvalStep; the loss kernel's "
                                        "own duration is taken from eager rounds of the same step run between the "
-                                       "timed rounds" if static_step is not None else ""),
+                                       "timed rounds" if static_steps is not None else ""),
                            "chain": "7 launches per step: loss fwd+grad + decode counting pass (yb_loss_decode_fused), "
                                     "scan, emit, NMS classify / scatter / sweep / emit",
                            "unfused": "separate loss and decode launches"}[mode],
@@ -522,7 +533,15 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(cfg)
         emit(json.dumps(line))
     if world > 1:
+        # nothing of the measurement is left to do: a stuck NCCL teardown must not hold the launcher
+        import threading
+        dog = threading.Timer(60.0, os._exit, (0,))
+        dog.daemon = True
+        dog.start()
+        static_steps = None          # graphs go before the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        dog.cancel()
 
 
 class _StdoutGuard:

@@ -128,7 +128,7 @@ def run_kmeans(out, rank, world, dev, group, n=50_000_000, k=9):
         ms_graph = f"graph capture failed: {type(e).__name__}: {e}"
         torch.cuda.synchronize()
     # the all-reduce inside the assignment launch, over NVLink peer memory (one launch per iteration)
-    ms_peer, t_full_peer, peer_same = None, None, None
+    ms_peer, ms_peer_graph, t_full_peer, peer_same = None, None, None, None
     if world > 1:
         loop_p = engine.KMeansLloyd(shard, torch.from_numpy(c0).to(dev), YB_DIST_IOU, 0.0, 1 << 40, sharded=True,
                                     peer_group=group)
@@ -141,6 +141,16 @@ def run_kmeans(out, rank, world, dev, group, n=50_000_000, k=9):
         e1.record()
         barrier(world)
         ms_peer = max_over_ranks(e0.elapsed_time(e1) / reps, world, dev)
+        # the same from CUDA-graph batches of 8 iterations (what utils.kmeans queues between two looks)
+        for _ in range(2):
+            loop_p.step_many(8)
+        barrier(world)
+        e0.record()
+        for _ in range(5):
+            loop_p.step_many(8)
+        e1.record()
+        barrier(world)
+        ms_peer_graph = max_over_ranks(e0.elapsed_time(e1) / 40, world, dev)
         peer_same = int(loop_p.read_state()[0])      # 0 = running (no exchange timed out)
         barrier(world)
         loop_p.close()
@@ -175,7 +185,8 @@ def run_kmeans(out, rank, world, dev, group, n=50_000_000, k=9):
         out["kmeans_50M"] = {
             "n_gpus": world, "boxes": n, "k": k, "ms_per_iteration": ms, "ms_per_iteration_cuda_graph": ms_graph,
             "boxes_per_s": n / (ms * 1e-3), "GBps_aggregate": 16 * n / ms / 1e6,
-            "ms_per_iteration_peer_exchange_in_kernel": ms_peer, "peer_exchange_status": peer_same,
+            "ms_per_iteration_peer_exchange_in_kernel": ms_peer,
+            "ms_per_iteration_peer_exchange_cuda_graph": ms_peer_graph, "peer_exchange_status": peer_same,
             "full_run_s_sharded_peer_exchange": t_full_peer,
             "centres_peer_equal_nccl": bool(np.array_equal(c_peer, c_sharded)) if world > 1 else None,
             "collective": f"all-reduce of {k * 3} doubles per iteration, same stream, no host sync",
@@ -322,7 +333,12 @@ def main():
         if a.json:
             json.dump(out, open(a.json, "w"), indent=1)
     if world > 1:
+        import threading
+        dog = threading.Timer(60.0, os._exit, (0,))   # a stuck teardown must not hold the launcher
+        dog.daemon = True
+        dog.start()
         dist.destroy_process_group()
+        dog.cancel()
 
 
 if __name__ == "__main__":

@@ -85,9 +85,12 @@ __device__ inline bool km_peer_allreduce(const KmLaunch& L, double* fin, int nv)
         double* slot = reinterpret_cast<double*>(L.mailbox[peer] + peer_slot_offset(parity, L.rank, L.world));
         slot[j] = fin[j];
     }
-    __threadfence_system();
     __syncthreads();
     if (tid < L.world) {
+        // the CTA's stores happen before this thread's fence (barrier), the fence before the flag: a
+        // peer that acquires the flag sees them all (the pattern of a cooperative grid barrier) -
+        // one fence per peer instead of one per thread
+        __threadfence_system();
         unsigned long long* flag = reinterpret_cast<unsigned long long*>(
             L.mailbox[tid] + peer_slot_offset(parity, L.rank, L.world) + kPeerSlotDoubles * 8);
         st_release_sys(flag, seq);
@@ -99,7 +102,7 @@ __device__ inline bool km_peer_allreduce(const KmLaunch& L, double* fin, int nv)
                 s_ok = 0;
                 break;
             }
-            __nanosleep(100);
+            __nanosleep(20);
         }
     }
     __syncthreads();
@@ -144,42 +147,49 @@ __device__ inline double km_np_sum(const double* a, int n) {
     return res;
 }
 
-// One thread.  fin: [c*(d+1)+j] sums, [c*(d+1)+d] counts (as doubles, exact).  Returns nothing;
-// leaves the centres untouched when it freezes on an empty cluster.
-__device__ inline void km_lloyd_update(int k, int d, int kind, const double* fin, double* centers,
-                                       long long* state, double stop_dist, long long max_iter) {
+// The first max(k, 1) threads of a CTA, all of them calling (one __syncthreads inside).  fin:
+// [c*(d+1)+j] sums, [c*(d+1)+d] counts (as doubles, exact); dist: k doubles of shared scratch.
+// Thread c owns cluster c (its three IEEE divisions run beside the other clusters'), thread 0
+// closes the iteration.  Leaves the centres untouched when it freezes on an empty cluster.
+__device__ inline void km_lloyd_update(int k, int d, int kind, const double* fin, const double* old_centers,
+                                       double* centers, long long* state, double stop_dist, long long max_iter,
+                                       double* dist) {
+    const int c = threadIdx.x;
     double* hist = reinterpret_cast<double*>(state + 4);
     double* saved = hist + YB_KMEANS_HIST;
-    for (int c = 0; c < k; ++c)
-        if (!(fin[c * (d + 1) + d] > 0.0)) {            // kmeans.py:85: len(index) > 0
+    bool empty = false;
+    for (int q = 0; q < k; ++q) empty = empty || !(fin[q * (d + 1) + d] > 0.0);   // kmeans.py:85: len(index) > 0
+    if (empty) {                                          // uniform: every thread read the same sums
+        if (c == 0) {
             for (int i = 0; i < k * (d + 1); ++i) saved[i] = fin[i];
             __threadfence();
             state[0] = 3;
-            return;
         }
-    double dist[16];
-    for (int c = 0; c < k; ++c) {
+        return;
+    }
+    if (c < k) {
         double nc[4];
         for (int j = 0; j < d; ++j) nc[j] = fin[c * (d + 1) + j] / fin[c * (d + 1) + d];   // cluster mean
         if (kind == YB_DIST_IOU) {                       // kmeans.py:12-22, 32
-            const double ca = __dmul_rn(centers[c * d], centers[c * d + 1]);
+            const double ca = __dmul_rn(old_centers[c * d], old_centers[c * d + 1]);
             const double na = __dmul_rn(nc[0], nc[1]);
             dist[c] = 1.0 - km_np_min(ca, na) / km_np_max(ca, na);
         } else {                                         // kmeans.py:39
             double sq = 0.0;
             for (int j = 0; j < d; ++j) {
-                const double df = centers[c * d + j] - nc[j];
+                const double df = old_centers[c * d + j] - nc[j];
                 sq = __dadd_rn(sq, __dmul_rn(df, df));
             }
             dist[c] = sqrt(sq);
         }
         for (int j = 0; j < d; ++j) centers[c * d + j] = nc[j];
     }
+    __syncthreads();
+    if (c != 0) return;
     const double loss = km_np_sum(dist, k) / (double)k;  // np.mean, kmeans.py:92
     const long long done = state[1] + 1;
     hist[(done - 1) % YB_KMEANS_HIST] = loss;
-    state[1] = done;
-    __threadfence();
+    state[1] = done;                                     // (read by later launches and by the host after a sync)
     if (loss < stop_dist) state[0] = 1;                  // kmeans.py:97 (epoch = done + 1)
     else if (done + 1 > max_iter) state[0] = 2;
 }
@@ -210,6 +220,16 @@ constexpr int kCntBits = 7;                   // packed per-lane counters: 9 slo
 // waits on its own mbarriers): no block-wide barrier anywhere in the streaming loop.  Every thread
 // owns one column of the accumulator planes, so the per-box update is a plain load / add / store
 // at a dynamic slot index (no atomics, no k-way predicated adds).
+#ifdef YB_KM_PROF
+__device__ unsigned long long g_km_prof[1024 * 8];
+#define KPROF(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_km_prof[blockIdx.x * 8 + (k)] = global_timer_ns(); } while (0)
+extern "C" int yb_debug_km_prof(unsigned long long* host, int n_words) {
+    return (int)cudaMemcpyFromSymbol(host, g_km_prof, sizeof(unsigned long long) * (size_t)n_words);
+}
+#else
+#define KPROF(k) do { } while (0)
+#endif
+
 template <int K, int D, bool kIou, bool kAssign>
 __global__ void __launch_bounds__(kKmThreads, 2)
 kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
@@ -228,21 +248,43 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     __shared__ int s_thr_hi[K];            // high words of the k-1 decision thresholds (INT_MAX beyond)
     __shared__ int2 s_win[K];              // slot s is certain for win.x < hiword(area) < win.y
     __shared__ unsigned char s_lut[kBoxes ? kLutCells : 16];  // cell of hiword(area) -> certain slot | 0xFF
-    __shared__ int s_is_last;
+    __shared__ int s_is_last, s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k = L.k;  // <= K
     const int n_stages = L.n_stages, tile_pts = L.tile_pts;
     if (L.state != nullptr && __ldcg(&L.state[0]) != 0) return;   // frozen Lloyd loop: nothing to do
+    KPROF(0);
 
     if (tid == 0) {
         for (int w = 0; w < kKmWarps; ++w)
             for (int i = 0; i < kKmMaxStages; ++i) mbar_init(&full[w][i], 1);
         mbar_fence_init();
+        s_bad = (D < 2) ? 1 : 0;
     }
     if (tid < K * D) s_center[tid] = (tid < k * D) ? L.centers[tid] : 0.0;
     for (int i = tid; i < K * D * kKmThreads; i += kKmThreads) s_acc[i] = 0.0;
     for (int i = tid; i < K * kKmThreads; i += kKmThreads) s_cnt[i] = 0;
     __syncthreads();
+    // the first tiles of every warp's ring are on their way while the CTA builds its tables
+    const long long n_tiles = (L.n + tile_pts - 1) / tile_pts;
+    const long long wg = (long long)blockIdx.x * kKmWarps + warp, n_wg = (long long)gridDim.x * kKmWarps;
+    const long long n_my = (n_tiles > wg) ? (n_tiles - wg + n_wg - 1) / n_wg : 0;
+    double* my_ring = ring + (size_t)warp * n_stages * tile_pts * D;
+    uint64_t* my_full = full[warp];
+    const long long tile_step = n_wg * tile_pts;
+    auto issue = [&](long long p0, int stage) {   // lane 0 only
+        const int np = (int)min((long long)tile_pts, L.n - p0);
+        const uint32_t bytes = (uint32_t)np * D * 8u;
+        if (L.bulk_ok && (bytes & 15u) == 0u) {
+            mbar_arrive_expect_tx(&my_full[stage], bytes);
+            bulk_g2s(my_ring + (size_t)stage * tile_pts * D, L.data + p0 * D, bytes, &my_full[stage]);
+        } else {
+            mbar_arrive(&my_full[stage]);  // the warp reads global memory directly for this tile
+        }
+    };
+    long long p_issue = wg * tile_pts;   // first point of the next tile to issue
+    if (lane == 0)
+        for (int t = 0; t < n_stages - 1 && t < n_my; ++t, p_issue += tile_step) issue(p_issue, t);
     if (tid < K) s_carea[tid] = (tid < k && D >= 2) ? __dmul_rn(s_center[tid * D], s_center[tid * D + 1]) : 0.0;
     __syncthreads();
     // iou_dist is a function of the AREA only and monotone in it on either side of the box's area
@@ -262,42 +304,44 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
     // threshold counts the thresholds below the high word and tests the slot's window; what is
     // still uncertain (near ties, duplicate / non-finite / extreme centroids, far-away boxes, NaN)
     // takes the exact k-way loop with IEEE divisions.
-    if (tid == 0) {
-        int bad = (D < 2) ? 1 : 0;
-        for (int c = 0; c < k; ++c) {
-            const double a = s_carea[c];
-            if (!(a > 1e-100) || !(a < 1e100)) bad = 1;
-            int r = 0;
-            for (int q = 0; q < k; ++q) r += (s_carea[q] < a || (s_carea[q] == a && q < c)) ? 1 : 0;
-            s_sarea[r] = a;
-            s_sidx[r] = c;
-            s_rank[c] = r;
-        }
-        for (int j = 0; j + 1 < k && !bad; ++j)
-            if (!(s_sarea[j + 1] - s_sarea[j] > 1e-6 * s_sarea[j + 1])) bad = 1;
+    // (thread c ranks centroid c, thread sl derives slot sl's window: the square roots and divisions
+    // of the k slots run side by side - on one thread they were ~10 us in front of every launch)
+    if (tid < k) {
+        const double a = s_carea[tid];
+        if (!(a > 1e-100) || !(a < 1e100)) s_bad = 1;
+        int r = 0;
+        for (int q = 0; q < k; ++q) r += (s_carea[q] < a || (s_carea[q] == a && q < tid)) ? 1 : 0;
+        s_sarea[r] = a;
+        s_sidx[r] = tid;
+        s_rank[tid] = r;
+    }
+    __syncthreads();
+    if (tid + 1 < k && !(s_sarea[tid + 1] - s_sarea[tid] > 1e-6 * s_sarea[tid + 1])) s_bad = 1;
+    __syncthreads();
+    if (tid < K) {
+        const int sl = tid;
+        const bool bad = s_bad != 0;
         const double tiny = 9.5367431640625e-07, huge = 1048576.0;  // 2^-20, 2^20
-        for (int sl = 0; sl < K; ++sl) {
-            double lo = INFINITY, hi = -INFINITY;   // never certain
-            int th = INT_MAX;
-            if (!bad && sl < k) {
-                lo = s_sarea[sl] * tiny * (1.0 + 1e-12);
-                hi = s_sarea[sl] * huge * (1.0 - 1e-12);
-                if (sl > 0) {
-                    const double A0 = s_sarea[sl - 1], A1 = s_sarea[sl];
-                    const double g = sqrt(A0 * A1), dl = 2e-15 + 1e-15 * sqrt(A1 / A0);
-                    lo = fmax(lo, g * (1.0 + dl));
-                }
-                if (sl + 1 < k) {
-                    const double A0 = s_sarea[sl], A1 = s_sarea[sl + 1];
-                    const double g = sqrt(A0 * A1), dl = 2e-15 + 1e-15 * sqrt(A1 / A0);
-                    hi = fmin(hi, g * (1.0 - dl));
-                    th = __double2hiint(g);
-                }
+        double lo = INFINITY, hi = -INFINITY;   // never certain
+        int th = INT_MAX;
+        if (!bad && sl < k) {
+            lo = s_sarea[sl] * tiny * (1.0 + 1e-12);
+            hi = s_sarea[sl] * huge * (1.0 - 1e-12);
+            if (sl > 0) {
+                const double A0 = s_sarea[sl - 1], A1 = s_sarea[sl];
+                const double g = sqrt(A0 * A1), dl = 2e-15 + 1e-15 * sqrt(A1 / A0);
+                lo = fmax(lo, g * (1.0 + dl));
             }
-            // hiword(a) > hiword(lo) => a > lo;  hiword(a) < hiword(hi) => a < hi
-            s_win[sl] = (lo < hi) ? make_int2(__double2hiint(lo), __double2hiint(hi)) : make_int2(INT_MAX, INT_MIN);
-            s_thr_hi[sl] = th;
+            if (sl + 1 < k) {
+                const double A0 = s_sarea[sl], A1 = s_sarea[sl + 1];
+                const double g = sqrt(A0 * A1), dl = 2e-15 + 1e-15 * sqrt(A1 / A0);
+                hi = fmin(hi, g * (1.0 - dl));
+                th = __double2hiint(g);
+            }
         }
+        // hiword(a) > hiword(lo) => a > lo;  hiword(a) < hiword(hi) => a < hi
+        s_win[sl] = (lo < hi) ? make_int2(__double2hiint(lo), __double2hiint(hi)) : make_int2(INT_MAX, INT_MIN);
+        s_thr_hi[sl] = th;
     }
     __syncthreads();
     int thr_hi[K > 1 ? K - 1 : 1];   // threshold high words in registers
@@ -319,9 +363,6 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         __syncthreads();
     }
 
-    const long long n_tiles = (L.n + tile_pts - 1) / tile_pts;
-    const long long wg = (long long)blockIdx.x * kKmWarps + warp, n_wg = (long long)gridDim.x * kKmWarps;
-    const long long n_my = (n_tiles > wg) ? (n_tiles - wg + n_wg - 1) / n_wg : 0;
     double* my_acc = s_acc + tid * D;
     int* my_cnt = s_cnt + tid;
 
@@ -413,22 +454,7 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         my_cnt[slot * kKmThreads] += 1;
     };
 
-    double* my_ring = ring + (size_t)warp * n_stages * tile_pts * D;
-    uint64_t* my_full = full[warp];
-    const long long tile_step = n_wg * tile_pts;
-    auto issue = [&](long long p0, int stage) {   // lane 0 only
-        const int np = (int)min((long long)tile_pts, L.n - p0);
-        const uint32_t bytes = (uint32_t)np * D * 8u;
-        if (L.bulk_ok && (bytes & 15u) == 0u) {
-            mbar_arrive_expect_tx(&my_full[stage], bytes);
-            bulk_g2s(my_ring + (size_t)stage * tile_pts * D, L.data + p0 * D, bytes, &my_full[stage]);
-        } else {
-            mbar_arrive(&my_full[stage]);  // the warp reads global memory directly for this tile
-        }
-    };
-    long long p_issue = wg * tile_pts;   // first point of the next tile to issue
-    if (lane == 0)
-        for (int t = 0; t < n_stages - 1 && t < n_my; ++t, p_issue += tile_step) issue(p_issue, t);
+    KPROF(1);
     int stage = 0, issue_stage = n_stages - 1;
     uint32_t parity = 0;
     long long p0 = wg * tile_pts;
@@ -476,39 +502,68 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         }
     }
     if (kPacked) flush_counts();
+    KPROF(2);
     __syncthreads();   // every warp has left its ring: s_red may reuse it
+    KPROF(3);
 
     // ---- reduction: thread columns -> warp -> CTA -> global partials -> last CTA ----
     constexpr int NV = K * (D + 1);
-    for (int c = 0; c < K; ++c) {   // c = cluster index; its accumulator slot is its sorted rank (boxes)
+    // value v = (cluster c, coordinate j | count) lives in 256 thread columns of one accumulator plane
+    // (cluster c's plane is its sorted rank for boxes).  Thread (v, seg) adds 32 columns, in a fixed
+    // order that starts at its own lane (spreads the shared-memory banks), then eight segments are
+    // added per value: plain shared-memory loads instead of 27 x 5 rounds of fp64 shuffles per warp.
+    constexpr int kSegs = kKmThreads / 32;
+    for (int idx = tid; idx < NV * kSegs; idx += kKmThreads) {
+        const int v = idx / kSegs, seg = idx - v * kSegs;
+        const int c = v / (D + 1), j = v - c * (D + 1);
         const int sl = (kBoxes && c < k) ? s_rank[c] : c;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const double sres = warp_sum(my_acc[sl * (D * kKmThreads) + j]);
-            if (lane == 0) s_red[warp * NV + c * (D + 1) + j] = sres;
+        double sres = 0.0;
+        if (j < D) {
+            const double* plane = s_acc + (size_t)sl * (D * kKmThreads) + j;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) sres += plane[(size_t)(seg * 32 + ((r + lane) & 31)) * D];
+        } else {
+            const int* plane = s_cnt + sl * kKmThreads;
+            int cs = 0;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) cs += plane[seg * 32 + ((r + lane) & 31)];
+            sres = (double)cs;   // exact below 2^53
         }
-        const int cs = warp_sum(my_cnt[sl * kKmThreads]);
-        if (lane == 0) s_red[warp * NV + c * (D + 1) + D] = (double)cs;  // exact below 2^53
+        s_red[seg * NV + v] = sres;
     }
     __syncthreads();
     if (tid < NV) {
         double sres = 0.0;
-        for (int w = 0; w < kKmWarps; ++w) sres += s_red[w * NV + tid];
+        for (int w = 0; w < kSegs; ++w) sres += s_red[w * NV + tid];
         L.partials[(size_t)blockIdx.x * NV + tid] = sres;
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) s_is_last = (atomicAdd(L.counter, 1u) == gridDim.x - 1);
     __syncthreads();
+    KPROF(4);
     if (!s_is_last) return;
     __threadfence();
     double* s_fin = s_red;   // [K*(D+1)]: the global sums / counts (s_red is dead: partials are in global memory)
     __syncthreads();
-    for (int i = warp; i < NV; i += kKmWarps) {
-        double sres = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) sres += __ldcg(&L.partials[(size_t)b * NV + i]);
-        sres = warp_sum(sres);
-        if (lane == 0) {
+    // the partials of all CTAs: a [gridDim][NV] matrix.  Thread (g, i) adds the rows g, g + G, ... of
+    // column i (neighbouring threads read neighbouring doubles, many rows in flight per thread), then
+    // the G groups are added per column - a fixed order, so every run and every rank gets the same bits
+    {
+        constexpr int G = kKmThreads / NV;
+        double* s_grp = s_red + NV * 2;                  // [G][NV], behind s_fin and the update's scratch
+        if (tid < G * NV) {
+            const int g = tid / NV, i = tid - g * NV;
+            double sres = 0.0;
+#pragma unroll 8
+            for (int b2 = g; b2 < (int)gridDim.x; b2 += G) sres += __ldcg(&L.partials[(size_t)b2 * NV + i]);
+            s_grp[g * NV + i] = sres;
+        }
+        __syncthreads();
+        if (tid < NV) {
+            const int i = tid;
+            double sres = 0.0;
+            for (int g = 0; g < G; ++g) sres += s_grp[g * NV + i];
             const int c = i / (D + 1), j = i - c * (D + 1);
             s_fin[i] = sres;
             if (c < k) {
@@ -523,6 +578,7 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         }
     }
     __syncthreads();
+    KPROF(5);
     if (tid == 0) *L.counter = 0u;
     bool ok = true;
     if (L.mailbox[0] != nullptr) {
@@ -530,21 +586,24 @@ kmeans_assign_kernel(const __grid_constant__ KmLaunch L) {
         // exceed k, so send all NV entries (unused ones are zero)
         ok = km_peer_allreduce(L, s_fin, NV);
     }
-    if (tid == 0 && ok && L.centers_rw != nullptr)   // every CTA has long copied the centres: update them in place
-        km_lloyd_update(k, D, L.kind, s_fin, L.centers_rw, L.state, L.stop_dist, L.max_iter);
+    KPROF(6);
+    // every CTA has long copied the centres: update them in place (ok is the same in every thread)
+    if (ok && L.centers_rw != nullptr)
+        km_lloyd_update(k, D, L.kind, s_fin, s_center, L.centers_rw, L.state, L.stop_dist, L.max_iter, s_fin + NV);
+    KPROF(7);
 }
 
 // sharded Lloyd loop: the update alone, on the all-reduced [sums | counts] (one thread)
 __global__ void kmeans_update_kernel(const double* __restrict__ packed, double* centers, int k, int d, int kind,
                                      long long* state, double stop_dist, long long max_iter) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    __shared__ double fin[16 * 5], dist[16];
     if (state[0] != 0) return;
-    double fin[16 * 5];
-    for (int c = 0; c < k; ++c) {
-        for (int j = 0; j < d; ++j) fin[c * (d + 1) + j] = packed[c * d + j];
-        fin[c * (d + 1) + d] = packed[k * d + c];
+    for (int i = threadIdx.x; i < k * (d + 1); i += blockDim.x) {
+        const int c = i / (d + 1), j = i - c * (d + 1);
+        fin[i] = j < d ? packed[c * d + j] : packed[k * d + c];
     }
-    km_lloyd_update(k, d, kind, fin, centers, state, stop_dist, max_iter);
+    __syncthreads();
+    km_lloyd_update(k, d, kind, fin, centers, centers, state, stop_dist, max_iter, dist);
 }
 
 __global__ void minmax_kernel(const double* __restrict__ x, long long n, double* __restrict__ partials,

@@ -650,6 +650,7 @@ class KMeansLloyd:
         """Release the peer mappings and the mailbox (after a barrier: nobody may still write to it)."""
         if self.peers is not None:
             torch.cuda.synchronize()
+            self.__dict__.pop("_graphs", None)
             for p in self._opened:
                 N.lib.yb_peer_close(C.c_void_p(p))
             N.lib.yb_peer_free(C.c_void_p(self._own_mailbox))
@@ -668,6 +669,26 @@ class KMeansLloyd:
                                            self.kind, self.stop, self.max_iter, _ptr(self.state), _ptr(self.packed),
                                            _ptr(assign), C.c_void_p(self.ws_ptr), self.ws_bytes, _stream()),
                 "yb_kmeans_lloyd_step")
+
+    def step_many(self, n):
+        """n iterations of the loop whose exchange (if any) happens inside the launch - unsharded, or
+        sharded over peer memory - replayed from a CUDA graph captured once per n: the host's launch
+        cost (one ctypes call per iteration) is out of the loop.  Every rank must ask for the same n."""
+        if self.packed is not None:
+            raise N.YoloB200Error("step_many: the NCCL-exchanged loop queues step() / all-reduce / update() itself")
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(n)
+        if g is None:
+            with torch.cuda.device(self.data.device):
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):   # capture runs nothing: the loop state is untouched
+                    for _ in range(n):
+                        self.step()
+                torch.cuda.current_stream().wait_stream(side)
+            graphs[n] = g
+        g.replay()
 
     def update(self):
         """Sharded loop: the update on the all-reduced ``packed`` sums / counts."""

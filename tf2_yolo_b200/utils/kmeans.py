@@ -150,11 +150,13 @@ def kmeans(data, n_cluster, dist_func, stop_dist, max_iternum=10000, verbose=Tru
         seen = 0          # updates whose loss has been reported
         check_every = max(1, min(int(check_every), engine.N.YB_KMEANS_HIST))
         while True:
-            for _ in range(check_every):
-                loop.step()
-                if sharded and peer is None:
+            if sharded and peer is None:
+                for _ in range(check_every):
+                    loop.step()
                     dist_util.allreduce_sum(loop.packed, process_group)   # same stream, no host sync
                     loop.update()
+            else:   # the whole iteration is one launch: the batch is one CUDA-graph replay
+                loop.step_many(check_every)
             status, done, hist, sums, counts = loop.read_state()
             if verbose:
                 for e in range(seen + 1, done + 1):

@@ -87,24 +87,21 @@ def grid_config(name, version, out):
     assert int(fout["n_overflow"].item()) == 0
     t_inf, _ = timed(lambda: engine.decode_nms_batch(yp, C, 0.5, version, 0.45, mode, rows_per_img_cap=2048, out=fout),
                      flush=flush, burst=burst)
-    # the same step replayed from a CUDA graph (what a training loop would do with static shapes)
+    # the same step over static buffers replayed from a CUDA graph, workspaces zeroed once (no memsets):
+    # what a training loop with fixed shapes runs (engine.TrainEvalStep)
     t_graph = None
     try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            step()
-            with torch.cuda.graph(g, stream=side):
-                step()
-        torch.cuda.current_stream().wait_stream(side)
-        t_graph, _ = timed(g.replay, flush=flush, burst=burst)
+        st = engine.TrainEvalStep(params, yt, yp, 0.5, 0.45, mode, rows_per_img_cap=2048, dpreds=dp)
+        t_graph, _ = timed(st.run, flush=flush, burst=burst)
+        assert torch.equal(st.out_offsets, fout["out_offsets"]) and int(st.n_overflow.item()) == 0
     except Exception as e:  # noqa: BLE001
         t_graph = f"graph capture failed: {type(e).__name__}: {e}"
         torch.cuda.synchronize()
     out[name] = {
         "step_two_launches_ms": t_step, "step_graph_replay_ms": t_graph, "decode_nms_two_launches_ms": t_inf,
         "step_images_per_s": batch / (t_step * 1e-3), "step_frac_of_measured_hbm": loss_bytes / t_step / 1e6 / PEAK,
+        "graph_step_images_per_s": batch / (t_graph * 1e-3) if isinstance(t_graph, float) else None,
+        "graph_step_frac_of_measured_hbm": loss_bytes / t_graph / 1e6 / PEAK if isinstance(t_graph, float) else None,
         "batch": batch, "loss_ms": t_loss, "loss_GBps": loss_bytes / t_loss / 1e6,
         "loss_frac_of_measured_hbm": loss_bytes / t_loss / 1e6 / PEAK, "loss_bytes": loss_bytes,
         "decode_ms": t_dec, "decode_GBps": dec_bytes / t_dec / 1e6, "decode_frac": dec_bytes / t_dec / 1e6 / PEAK,
@@ -140,9 +137,11 @@ def kmeans_bench(out, n=50_000_000, k=9):
     # one iteration of the device Lloyd loop (assignment + update + stop test in one launch)
     loop = engine.KMeansLloyd(data, centers.clone(), YB_DIST_IOU, 0.0, 1 << 40)
     t3, _ = timed(loop.step, burst=8)
+    t4, _ = timed(lambda: loop.step_many(8), burst=1)
+    t4 /= 8
     out["kmeans_50M"] = {"boxes": n, "k": k, "ms_per_iteration": t, "GBps": 16 * n / t / 1e6,
                          "frac_of_measured_hbm": 16 * n / t / 1e6 / PEAK, "ms_with_assignments": t2,
-                         "ms_per_lloyd_iteration_device_loop": t3,
+                         "ms_per_lloyd_iteration_device_loop": t3, "ms_per_lloyd_iteration_graph_batches": t4,
                          "lloyd_frac_of_measured_hbm": 16 * n / t3 / 1e6 / PEAK}
     from tf2_yolo_b200.utils import kmeans as km
     import contextlib

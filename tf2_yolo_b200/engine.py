@@ -367,18 +367,12 @@ def decode_nms_batch_exact(preds, class_num=1, threshold=0.5, version=1, nms_thr
     return g["out_rows"][:int(g["out_offsets"][-1].item())], g["out_offsets"]
 
 
-def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold=0.45, iou_mode=1,
-                          rows_per_img_cap=1024, global_batch=None, dpreds=None, want_terms=False, out=None,
-                          out_capacity=None, split_hook=None, loss_out=None, loss_box=None):
-    """The train-and-evaluate step in two launches (yb_loss_decode_nms_fused): loss forward +
-    gradient with the decode counting pass riding on its read of y_pred, then decode + NMS with one
-    CTA per image.  Returns (loss [n], dpreds, terms, dict(out_rows, out_offsets, n_overflow))."""
+def _fill_step_scales(params, y_trues, y_preds, global_batch, dpreds):
+    """yb_loss_scale array of a step over whole images (every scale holds the same n_img images)."""
     n = len(params)
-    require_cuda(*y_trues, *y_preds)
-    dev = y_preds[0].device
+    n_img = y_preds[0].shape[0]
     scales = (N.LossScale * n)()
     outs = []
-    n_img = y_preds[0].shape[0]
     for i, (p, yt, yp) in enumerate(zip(params, y_trues, y_preds)):
         if yt.dtype != torch.float32 or yp.dtype != torch.float32:
             raise N.YoloB200Error("loss tensors must be float32")
@@ -393,6 +387,19 @@ def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold
         scales[i].y_true, scales[i].y_pred, scales[i].dpred = yt.data_ptr(), yp.data_ptr(), d.data_ptr()
         scales[i].n_cells = n_img * cells_per_img
         scales[i].p = q
+    return scales, outs, n_img
+
+
+def loss_decode_nms_fused(params, y_trues, y_preds, threshold=0.5, nms_threshold=0.45, iou_mode=1,
+                          rows_per_img_cap=1024, global_batch=None, dpreds=None, want_terms=False, out=None,
+                          out_capacity=None, split_hook=None, loss_out=None, loss_box=None):
+    """The train-and-evaluate step in two launches (yb_loss_decode_nms_fused): loss forward +
+    gradient with the decode counting pass riding on its read of y_pred, then decode + NMS with one
+    CTA per image.  Returns (loss [n], dpreds, terms, dict(out_rows, out_offsets, n_overflow))."""
+    n = len(params)
+    require_cuda(*y_trues, *y_preds)
+    dev = y_preds[0].device
+    scales, outs, n_img = _fill_step_scales(params, y_trues, y_preds, global_batch, dpreds)
     dparams, _ = make_decode_params(y_preds, params[0].class_num, threshold, params[0].version)
     if out_capacity is None:
         out_capacity = rows_per_img_cap * max(n_img, 1)
@@ -448,22 +455,7 @@ class TrainEvalStep:
         self.n = n
         self.n_img = n_img = y_preds[0].shape[0]
         self._keep = (list(y_trues), list(y_preds))
-        self.scales = (N.LossScale * n)()
-        self.dpreds = []
-        for i, (p, yt, yp) in enumerate(zip(params, y_trues, y_preds)):
-            if yt.dtype != torch.float32 or yp.dtype != torch.float32:
-                raise N.YoloB200Error("loss tensors must be float32")
-            cells_per_img = p.grid_h * p.grid_w
-            pcf = (5 * p.bbox_num + p.class_num) if p.version == 1 else p.bbox_num * (5 + p.class_num)
-            if yp.numel() != n_img * cells_per_img * pcf or yt.numel() != n_img * cells_per_img * (5 + p.class_num):
-                raise ValueError("every scale must hold the same images with matching grid / info sizes")
-            q = N.LossParams.from_buffer_copy(p)
-            q.inv_batch = 1.0 / float(global_batch if global_batch is not None else max(n_img, 1))
-            d = dpreds[i] if dpreds is not None else torch.empty_like(yp)
-            self.dpreds.append(d)
-            self.scales[i].y_true, self.scales[i].y_pred, self.scales[i].dpred = yt.data_ptr(), yp.data_ptr(), d.data_ptr()
-            self.scales[i].n_cells = n_img * cells_per_img
-            self.scales[i].p = q
+        self.scales, self.dpreds, _ = _fill_step_scales(params, y_trues, y_preds, global_batch, dpreds)
         dparams, _ = make_decode_params(y_preds, params[0].class_num, threshold, params[0].version)
         self.args = (float(threshold), float(nms_threshold), int(iou_mode), int(rows_per_img_cap))
         if out_capacity is None:
@@ -612,6 +604,7 @@ class KMeansLloyd:
             N.check(N.lib.yb_kmeans_lloyd_init(_ptr(self.state), self.k, self.d, C.c_void_p(self.ws_ptr), self.ws_bytes,
                                                _stream()), "yb_kmeans_lloyd_init")
             self.peers = None
+            self._graphs = {}      # step_many: one captured batch per length
             if peer_group is not None:
                 self._open_peers(peer_group)
 
@@ -650,7 +643,7 @@ class KMeansLloyd:
         """Release the peer mappings and the mailbox (after a barrier: nobody may still write to it)."""
         if self.peers is not None:
             torch.cuda.synchronize()
-            self.__dict__.pop("_graphs", None)
+            self._graphs.clear()
             for p in self._opened:
                 N.lib.yb_peer_close(C.c_void_p(p))
             N.lib.yb_peer_free(C.c_void_p(self._own_mailbox))
@@ -676,8 +669,7 @@ class KMeansLloyd:
         cost (one ctypes call per iteration) is out of the loop.  Every rank must ask for the same n."""
         if self.packed is not None:
             raise N.YoloB200Error("step_many: the NCCL-exchanged loop queues step() / all-reduce / update() itself")
-        graphs = self.__dict__.setdefault("_graphs", {})
-        g = graphs.get(n)
+        g = self._graphs.get(n)
         if g is None:
             with torch.cuda.device(self.data.device):
                 side = torch.cuda.Stream()
@@ -687,7 +679,7 @@ class KMeansLloyd:
                     for _ in range(n):
                         self.step()
                 torch.cuda.current_stream().wait_stream(side)
-            graphs[n] = g
+            self._graphs[n] = g
         g.replay()
 
     def update(self):

@@ -22,6 +22,9 @@ if "kmeans" in what:
     centers = torch.from_numpy(np.sort(rng.uniform(0.02, 0.8, (9, 2)), axis=0)).cuda()
     for _ in range(4):
         engine.kmeans_assign(data, centers, YB_DIST_IOU)
+    loop = engine.KMeansLloyd(data, centers.clone(), YB_DIST_IOU, 0.0, 1 << 40)   # the device Lloyd loop
+    for _ in range(4):
+        loop.step()
     torch.cuda.synchronize()
     del data
 if "nms" in what:

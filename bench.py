@@ -8,7 +8,8 @@ Workload (one "step"): YOLOv4-608, 3 FPN scales x 3 anchors, 80 classes, batch 1
 per GPU of synthetic head outputs + labels:
     fused CIoU loss forward+gradient (all scales, one launch)
     -> decode at joint-confidence 0.5 -> per-class DIoU-NMS at 0.45.
-`value`  : images/s, inputs resident in HBM, timed with CUDA events (max over ranks).
+`value`  : images/s, inputs resident in HBM, timed with CUDA events (max over ranks); the step
+           is two launches over static buffers replayed from a CUDA graph (--no-graph: eager).
 `e2e`    : same step through the reference-facing Python API with HOST buffers
            (pinned H2D of labels + head outputs inside the timed region, D2H of the
            loss scalars and the NMS survivors; the gradient stays on the device for

@@ -203,3 +203,21 @@ def test_config3_two_launch_step_equals_the_chain_at_batch_128():
     assert int(r["n_overflow"].item()) == 0
     assert torch.equal(loss, loss0) and all(torch.equal(a, b) for a, b in zip(d, d0))
     assert torch.equal(r["out_offsets"], g["out_offsets"]) and torch.equal(r["out_rows"][:n], g["out_rows"][:n])
+
+
+def test_config5_ap_table_of_500_images_equals_the_oracle_checked_fixture():
+    """PR curves / mAP (utils/measurement.py:198-447) over 500 v4-608 images: the 81-row AP table
+    must equal tests/golden/map500_ap_oracle_checked.npz bit for bit.  That table was produced by
+    this path on a B200 and then compared with the CPU oracle over the same 500 images
+    (benchmarks/map_subsample_check.py, 1925 s of oracle time: profiles/r2/map500_oracle_check.json) -
+    identical, max |diff| 0."""
+    import os
+    from tf2_yolo_b200.utils import measurement as meas
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "map500_ap_oracle_checked.npz"))
+    n = int(ref["images"])
+    cfg = synth.make_config("v4-608", batch=n, seed=50)
+    assert sum(float(p.sum()) for p in cfg["y_preds"]) == float(ref["checksum"])   # the same synthetic images
+    pr = meas.PRfunc(cfg["y_trues"][-1].astype(np.float64), *cfg["y_preds"], class_names=[str(i) for i in range(80)],
+                     conf_threshold=0.05, nms_mode=1, nms_threshold=0.5, max_per_img=100, version=4)
+    got = pr.get_map()["ap"].values.astype(np.float64)
+    assert np.array_equal(got, ref["ap"])

@@ -7,12 +7,18 @@
 // image never leave the SM: the counting pass (decode_count_kernel or the fused loss kernel) files
 // every hit - the head's values it holds anyway - into the image's bucket; the image's CTA orders
 // them (row-major cell, box, class), builds the float64 rows [x, y, w, h, c, class, p] in shared
-// memory in the reference's order, groups them by class, runs the greedy (D)IoU-NMS of every class
-// on one warp each (visit order = confidence descending, equal confidences -> higher original
-// index first; suppression on >=; division-free pair test with the pinned exact fallback, see
-// nms_pair.cuh) and writes the survivors class-major, original order inside a class, at the
-// image's offset in the compact output - found with a decoupled look-back over the earlier images
-// (tickets make every predecessor of a CTA already running, so the chain cannot stall).
+// memory in the reference's order, groups them by class and runs the greedy (D)IoU-NMS of every
+// class (visit order = confidence descending, equal confidences -> higher original index first;
+// suppression on >=; division-free pair test with the pinned exact fallback, see nms_pair.cuh).
+// The pair test of two boxes does not depend on the state of the sweep, so for classes of up to
+// 128 rows ALL pairs of ALL classes are tested in parallel (a flat list of pairs, contiguous runs
+// per thread): the earlier-visited box of a pair gets the later one's bit in its 128-bit mask, and
+// the sweep itself is one thread per class walking the visit order: dead |= mask[v] if v is alive.
+// Larger classes keep one warp each.  Survivors leave class-major, original order inside a class, at
+// the image's offset in the compact output - found with a decoupled look-back over the earlier
+// images (tickets make every predecessor of a CTA already running, so the chain cannot stall).
+// The last CTA to finish leaves the control block (bucket counters, look-back words, tickets) zeroed:
+// a caller that zeroed the workspace once never has to again (yb_loss_decode_nms_fused_clean).
 // Results are bit-identical to the six-launch chain.  An image with more rows than the caller's
 // rows_per_img_cap is not processed: it contributes no rows and is counted in *n_overflow; the
 // caller falls back to yb_decode + yb_nms (same contract as the row capacity of yb_decode).

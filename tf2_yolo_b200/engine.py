@@ -442,9 +442,11 @@ class TrainEvalStep:
     What a training loop with fixed shapes does with loss_decode_nms_fused: the tensors handed in
     are the buffers every step reads (refill them in place), the workspaces belong to this object
     and are zeroed once - both kernels leave them zeroed (yb_loss_decode_nms_fused_clean) - so a
-    step is exactly two kernel nodes, plus whatever `tail` enqueues (e.g. the all-reduce of the
-    loss scalars), captured once and replayed by run().  graph=False launches the same two kernels
-    eagerly."""
+    step is exactly two kernel nodes, plus whatever `tail` enqueues on the capturing stream, captured
+    once and replayed by run().  graph=False launches the same two kernels eagerly.
+    A collective is better issued after run() than captured through `tail`: bench.py alternates two
+    steps and all-reduces each one's loss asynchronously (a graph that holds NCCL kernels has to be
+    destroyed before the process group, or the teardown can hang)."""
 
     def __init__(self, params, y_trues, y_preds, threshold=0.5, nms_threshold=0.45, iou_mode=1,
                  rows_per_img_cap=1024, global_batch=None, dpreds=None, want_terms=False, out=None,
